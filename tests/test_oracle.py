@@ -1,0 +1,147 @@
+"""The oracle is pinned here: every function of oracle/dct_oracle.c against the golden vectors
+captured from the unmodified reference (tests/golden/, see make_golden.py), bit for bit, and --
+where oracle/_ref/libdct_ref.so exists -- against the reference itself on random planes."""
+import numpy as np
+import pytest
+
+from conftest import unhex
+from oracle import binding as B
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+@pytest.mark.parametrize("n", [4, 8, 16])
+def test_dct_matrix_bit_exact(oracle, golden_blocks, n):
+    # reference: src/dct.c:19-30
+    want = unhex(golden_blocks["dct_matrix"][str(n)], (n, n))
+    assert np.array_equal(bits(oracle.dct_matrix(n)), bits(want))
+
+
+@pytest.mark.parametrize("n", [4, 8, 16])
+def test_quant_tables_bit_exact(oracle, golden_blocks, n):
+    # reference: src/quantization.c:51-99, incl. the un-rounded doubles (q90: 16*0.2 != 3.2)
+    for q in (1, 10, 25, 49, 50, 51, 75, 90, 95, 100):
+        want = unhex(golden_blocks["quant_table"][f"{n}:{q}"], (n, n))
+        assert np.array_equal(bits(oracle.quant_table(q, n)), bits(want)), (n, q)
+
+
+def test_quality_is_clamped(oracle):
+    # reference: src/quantization.c:26-31
+    assert np.array_equal(oracle.quant_table(0), oracle.quant_table(1))
+    assert np.array_equal(oracle.quant_table(1000), oracle.quant_table(100))
+    assert np.all(oracle.quant_table(100) == 1.0)
+
+
+@pytest.mark.parametrize("n", [4, 8, 16])
+def test_zigzag_order(oracle, golden_blocks, n):
+    # reference: src/entropy.c:158-178 (N=8 is the JPEG order)
+    assert list(oracle.zigzag_order(n)) == golden_blocks["zigzag"][str(n)]
+    if n == 8:
+        assert list(oracle.zigzag_order(8))[:10] == [0, 1, 8, 16, 9, 2, 3, 10, 17, 24]
+
+
+def test_known_answer_block(oracle, golden_blocks):
+    # reference: tests/test_dct.c:33-42 -> dct_forward; tests/test_entropy.c:311-316, :370-373
+    kat = golden_blocks["kat"]
+    blk = np.array(kat["pixels"], dtype=np.float64).reshape(8, 8) - 128.0
+    c = oracle.dct_forward(blk)
+    assert np.array_equal(bits(c), bits(unhex(kat["coeffs"], (8, 8))))
+    assert abs(c[0, 0] - (-415.375)) < 1e-12 and abs(c[0, 1] - (-30.1857172768)) < 1e-9
+    var = oracle.block_variance(blk)
+    assert var == float.fromhex(kat["variance"]) and abs(var - 437.5095214844) < 1e-9
+    assert np.array_equal(bits(oracle.dct_inverse(c)), bits(unhex(kat["roundtrip"], (8, 8))))
+    assert list(oracle.round_to_int(c).ravel()) == kat["rounded"]
+    for key, case in kat["cases"].items():
+        q, adaptive = (int(v) for v in key.split(":"))
+        Q = oracle.quant_table(q)
+        qc = oracle.quantize(Q, c, adaptive, var)
+        assert list(qc.ravel()) == case["quantized"], key
+        dq = oracle.dequantize(Q, qc, adaptive, var)
+        assert np.array_equal(bits(dq), bits(unhex(case["dequantized"], (8, 8)))), key
+        assert np.array_equal(bits(oracle.dct_inverse(dq)), bits(unhex(case["idct"], (8, 8)))), key
+        assert np.array_equal(bits(oracle.adjust_table(Q, var, 1)), bits(unhex(case["adjust_q"], (8, 8))))
+        R = oracle.dequant_table(Q)
+        assert np.array_equal(bits(oracle.adjust_table(R, var, 0)), bits(unhex(case["adjust_r"], (8, 8))))
+    # the textbook result
+    assert kat["cases"]["50:0"]["quantized"][:8] == [-26, -3, -6, 2, 2, -1, 0, 0]
+    # S2: the non-adaptive dequantize multiplies by 1/Q
+    assert unhex(kat["cases"]["50:0"]["dequantized"])[0] == -26 * (1.0 / 16.0)
+
+
+@pytest.mark.parametrize("n", [4, 16])
+def test_generic_block_sizes(oracle, golden_blocks, n):
+    # reference: the same triple loops for block_size != 8; custom table src/quantization.c:78-96
+    k = golden_blocks["kat"][f"n{n}"]
+    b = unhex(k["block"], (n, n))
+    c = oracle.dct_forward(b)
+    assert np.array_equal(bits(c), bits(unhex(k["coeffs"], (n, n))))
+    Q = oracle.quant_table(50, n)
+    qc = oracle.quantize(Q, c)
+    assert list(qc.ravel()) == k["quantized"]
+    assert np.array_equal(bits(oracle.dequantize(Q, qc)), bits(unhex(k["dequantized"], (n, n))))
+    assert np.array_equal(bits(oracle.dct_inverse(c)), bits(unhex(k["idct"], (n, n))))
+
+
+def test_plane_goldens(oracle, golden_planes):
+    for key in golden_planes["cases"]:
+        name, q, a = key.split("/")
+        q, adaptive = int(q[1:]), int(a[1:])
+        px = golden_planes[f"{name}/px"]
+        H, W = px.shape
+        Q = oracle.quant_table(q)
+        cn, var, _ = oracle.fwd_quant_plane(px, Q, adaptive, B.NATURAL)
+        assert np.array_equal(cn, golden_planes[key + "/coef"]), key
+        if key + "/coef_zz" in golden_planes:
+            cz, _, _ = oracle.fwd_quant_plane(px, Q, adaptive, B.ZIGZAG, nthreads=3)
+            assert np.array_equal(cz, golden_planes[key + "/coef_zz"]), key
+            assert np.array_equal(cz, cn[:, oracle.zigzag_order(8)])
+            rz, _ = oracle.dequant_idct_plane(cz, W, H, Q, adaptive, B.ZIGZAG, var)
+            assert np.array_equal(rz, golden_planes[key + "/rec"]), key
+        if adaptive:
+            assert np.array_equal(bits(var), bits(golden_planes[key + "/var"])), key
+        rec, _ = oracle.dequant_idct_plane(cn, W, H, Q, adaptive, B.NATURAL, var, nthreads=2)
+        assert np.array_equal(rec, golden_planes[key + "/rec"]), key
+
+
+def test_forced_dc_tie_is_counted(oracle, golden_planes):
+    # block 3 of the adversarial strip has sum(px-128) = 64 -> DC = 8.0 -> 8/16 = 0.5 exactly
+    px = golden_planes["adv/px"]
+    _, _, ties = oracle.fwd_quant_plane(px, oracle.quant_table(50))
+    assert ties >= 1
+
+
+def test_a5_image_hashes(oracle, golden_blocks):
+    # 512x512 U q50 hashes measured on the reference
+    px = oracle.fill_xorshift(512, 512)
+    assert [int(v) for v in px.ravel()[:16]] == golden_blocks["a5"]["input_head"]
+    Q = oracle.quant_table(50)
+    coef, _, ties = oracle.fwd_quant_plane(px, Q, nthreads=4)
+    assert f"{oracle.fnv_i16(coef):016x}" == golden_blocks["a5"]["coef_hash"] == "8c0f119ff9a3b113"
+    rec, _ = oracle.dequant_idct_plane(coef, 512, 512, Q, nthreads=4)
+    assert f"{oracle.fnv_u8_blockorder(rec):016x}" == golden_blocks["a5"]["pixel_hash"] == "6724fe6c8009af02"
+    assert ties == 94
+    vals, counts = np.unique(rec, return_counts=True)
+    assert dict(zip(vals.tolist(), counts.tolist())) == {127: 2014, 128: 257987, 129: 2143}
+
+
+@pytest.mark.skipif(not B.have_ref(), reason="oracle/_ref not built (no /root/reference on this box)")
+@pytest.mark.parametrize("quality,adaptive,layout", [(50, 0, 0), (90, 0, 1), (10, 1, 0), (75, 1, 1), (100, 0, 0)])
+def test_oracle_equals_reference_on_random_planes(oracle, quality, adaptive, layout):
+    ref = B.load("ref")
+    rng = np.random.default_rng(quality * 10 + adaptive)
+    px = rng.integers(0, 256, size=(128, 192), dtype=np.uint8)
+    Q = oracle.quant_table(quality)
+    assert np.array_equal(bits(Q), bits(ref.quant_table(quality)))
+    co, vo, _ = oracle.fwd_quant_plane(px, Q, adaptive, layout, nthreads=2)
+    cr, vr, _ = ref.fwd_quant_plane(px, Q, adaptive, layout, nthreads=2)
+    assert np.array_equal(co, cr) and np.array_equal(bits(vo), bits(vr))
+    po, _ = oracle.dequant_idct_plane(co, 192, 128, Q, adaptive, layout, vo)
+    pr, _ = ref.dequant_idct_plane(cr, 192, 128, Q, adaptive, layout, vr)
+    assert np.array_equal(po, pr)
+    # arbitrary (not K1-produced) coefficients too
+    junk = rng.integers(-2000, 2000, size=co.shape).astype(np.int16)
+    po, _ = oracle.dequant_idct_plane(junk, 192, 128, Q, adaptive, layout, vo)
+    pr, _ = ref.dequant_idct_plane(junk, 192, 128, Q, adaptive, layout, vr)
+    assert np.array_equal(po, pr)
