@@ -1,0 +1,397 @@
+"""Host-side mirror of the reference's interface, over libdct_cuda's C ABI (ctypes).
+
+The reference (erkinov-wtf/dct) is compiled C; its public surface for this path is
+include/dct.h and include/quantization.h.  This module binds the very symbols a C caller
+links against -- same names, same argument meaning -- plus the plane calls of
+include/dct_cuda.h, so that the parity tests read like the reference's own tests:
+
+    ctx  = dct_init(8);  qctx = quant_init(8, 50, 0)          # tests/test_entropy.c:283-287
+    coeffs = dct_forward(ctx, block)                           # tests/test_entropy.c:311
+    q = quantize(qctx, coeffs, variance)                       # tests/test_entropy.c:316
+
+and, for whole planes (the throughput path):
+
+    plan = Plan(ctx, qctx)
+    coef = plan.fwd_quant(pixels)                              # numpy (host) or torch cuda tensor
+    rec  = plan.dequant_idct(coef, W, H)
+
+There is no fallback of any kind: if libdct_cuda.so is not built, importing this module
+raises; if no CUDA device is usable, Plan() and the per-block compute calls fail.
+torch is used only to hold device memory and streams (data_ptr / cuda_stream), never to compute.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdct_cuda.so")
+
+NATURAL, ZIGZAG = 0, 1
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} is not built: run `python -m dct_b200.build` (there is no CPU fallback)")
+_lib = C.CDLL(LIB_PATH)
+
+_PP_D = C.POINTER(C.POINTER(C.c_double))
+_PP_I = C.POINTER(C.POINTER(C.c_int))
+
+
+class DCTContext(C.Structure):  # include/dct.h
+    _fields_ = [("block_size", C.c_int), ("dct_matrix", _PP_D), ("transposed_dct", _PP_D)]
+
+
+class QuantContext(C.Structure):  # include/quantization.h
+    _fields_ = [("block_size", C.c_int), ("quality", C.c_int), ("quant_matrix", _PP_D),
+                ("dequant_matrix", _PP_D), ("adaptive", C.c_int)]
+
+
+class Stats(C.Structure):  # dct_cuda_stats
+    _fields_ = [("blocks", C.c_uint64), ("replayed_blocks", C.c_uint64), ("near_ties", C.c_uint64),
+                ("saturated", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class PlaneDesc(C.Structure):  # dct_cuda_plane
+    _fields_ = [("plan", C.c_void_p), ("pixels_in", C.c_void_p), ("pixels_out", C.c_void_p),
+                ("pitch", C.c_size_t), ("width", C.c_int), ("height", C.c_int), ("coef", C.c_void_p),
+                ("variance", C.c_void_p)]
+
+
+def _sig(name, restype, *argtypes):
+    fn = getattr(_lib, name)
+    fn.restype, fn.argtypes = restype, list(argtypes)
+    return fn
+
+
+_P_DCT, _P_Q = C.POINTER(DCTContext), C.POINTER(QuantContext)
+_dct_init = _sig("dct_init", _P_DCT, C.c_int)
+_dct_free = _sig("dct_free", None, _P_DCT)
+_dct_forward = _sig("dct_forward", None, _P_DCT, _PP_D, _PP_D)
+_dct_inverse = _sig("dct_inverse", None, _P_DCT, _PP_D, _PP_D)
+_create_block = _sig("create_block_from_pixels", _PP_D, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.c_int)
+_copy_block = _sig("copy_block_to_coefficients", None, _PP_D, _PP_I, C.c_int)
+_quant_init = _sig("quant_init", _P_Q, C.c_int, C.c_int, C.c_int)
+_quant_free = _sig("quant_free", None, _P_Q)
+_gen_q = _sig("generate_quant_matrix", _PP_D, C.c_int, C.c_int)
+_gen_r = _sig("generate_dequant_matrix", _PP_D, _PP_D, C.c_int)
+_quantize = _sig("quantize", None, _P_Q, _PP_D, _PP_I, C.c_double)
+_dequantize = _sig("dequantize", None, _P_Q, _PP_I, _PP_D, C.c_double)
+_variance = _sig("calculate_block_variance", C.c_double, _PP_D, C.c_int)
+_adjust = _sig("adjust_matrix_for_block", _PP_D, _P_Q, C.c_double, C.c_int)
+
+_last_error = _sig("dct_cuda_last_error", C.c_char_p)
+_device_count = _sig("dct_cuda_device_count", C.c_int)
+_plan_create = _sig("dct_cuda_plan_create", C.c_void_p, _P_DCT, _P_Q, C.c_int)
+_plan_refresh = _sig("dct_cuda_plan_refresh", C.c_int, C.c_void_p)
+_plan_destroy = _sig("dct_cuda_plan_destroy", None, C.c_void_p)
+_fwd_dev = _sig("dct_cuda_fwd_quant_u8_dev", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
+_inv_dev = _sig("dct_cuda_dequant_idct_u8_dev", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+_fwd_planes = _sig("dct_cuda_fwd_quant_planes_dev", C.c_int, C.POINTER(PlaneDesc), C.c_int, C.c_int, C.c_void_p)
+_inv_planes = _sig("dct_cuda_dequant_idct_planes_dev", C.c_int, C.POINTER(PlaneDesc), C.c_int, C.c_int, C.c_void_p)
+_fwd_host = _sig("dct_cuda_fwd_quant_u8", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                 C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Stats))
+_inv_host = _sig("dct_cuda_dequant_idct_u8", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                 C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Stats))
+_fwd_multi = _sig("dct_cuda_fwd_quant_u8_multi", C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t,
+                  C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Stats))
+_inv_multi = _sig("dct_cuda_dequant_idct_u8_multi", C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int,
+                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Stats))
+_stats_fetch = _sig("dct_cuda_stats_fetch", C.c_int, C.c_void_p, C.POINTER(Stats), C.c_void_p)
+_rec_to_block = _sig("dct_cuda_record_to_block", None, C.POINTER(C.c_int16), C.c_int, _PP_I)
+_block_to_rec = _sig("dct_cuda_block_to_record", None, _PP_I, C.c_int, C.POINTER(C.c_int16))
+_host_alloc = _sig("dct_cuda_host_alloc", C.c_void_p, C.c_size_t)
+_host_free = _sig("dct_cuda_host_free", None, C.c_void_p)
+
+
+class DctCudaError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise DctCudaError(f"libdct_cuda error {rc}: {_last_error().decode(errors='replace')}")
+
+
+def device_count() -> int:
+    return int(_device_count())
+
+
+# ---- ragged <-> numpy (the reference's blocks are row-pointer arrays, include/utils.h) --------
+class _Ragged:
+    """A caller-owned ragged n x n array: independent row buffers + a pointer table."""
+
+    def __init__(self, n, ctype, init=None):
+        self.n, self.ctype = n, ctype
+        self.rows = [(ctype * n)() for _ in range(n)]
+        if init is not None:
+            a = np.asarray(init)
+            for i in range(n):
+                for j in range(n):
+                    self.rows[i][j] = a[i, j].item()
+        self.table = (C.POINTER(ctype) * n)(*[C.cast(r, C.POINTER(ctype)) for r in self.rows])
+
+    @property
+    def ptr(self):
+        return C.cast(self.table, C.POINTER(C.POINTER(self.ctype)))
+
+    def numpy(self):
+        dt = np.float64 if self.ctype is C.c_double else np.int32
+        return np.array([[self.rows[i][j] for j in range(self.n)] for i in range(self.n)], dtype=dt)
+
+
+def _take_ragged(pp, n):
+    """Copies a library-returned ragged double array and releases it the way free_array does."""
+    out = np.array([[pp[i][j] for j in range(n)] for i in range(n)], dtype=np.float64)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    for i in range(n):
+        libc.free(C.cast(pp[i], C.c_void_p))
+    libc.free(C.cast(pp, C.c_void_p))
+    return out
+
+
+def matrix_of(pp, n):
+    return np.array([[pp[i][j] for j in range(n)] for i in range(n)], dtype=np.float64)
+
+
+# ---- include/dct.h ---------------------------------------------------------------------------
+def dct_init(block_size: int):
+    return _dct_init(int(block_size))
+
+
+def dct_free(ctx):
+    _dct_free(ctx)
+
+
+def dct_forward(ctx, block):
+    n = ctx.contents.block_size
+    a, b = _Ragged(n, C.c_double, block), _Ragged(n, C.c_double)
+    _dct_forward(ctx, a.ptr, b.ptr)
+    return b.numpy()
+
+
+def dct_inverse(ctx, block):
+    n = ctx.contents.block_size
+    a, b = _Ragged(n, C.c_double, block), _Ragged(n, C.c_double)
+    _dct_inverse(ctx, a.ptr, b.ptr)
+    return b.numpy()
+
+
+def create_block_from_pixels(pixels, width, row_start, col_start, block_size):
+    px = np.ascontiguousarray(pixels, dtype=np.uint8)
+    pp = _create_block(px.ctypes.data_as(C.POINTER(C.c_ubyte)), width, row_start, col_start, block_size)
+    return _take_ragged(pp, block_size)
+
+
+def copy_block_to_coefficients(block):
+    n = np.asarray(block).shape[0]
+    a, b = _Ragged(n, C.c_double, block), _Ragged(n, C.c_int)
+    _copy_block(a.ptr, b.ptr, n)
+    return b.numpy()
+
+
+# ---- include/quantization.h ------------------------------------------------------------------
+def quant_init(block_size: int, quality: int, adaptive: int):
+    return _quant_init(int(block_size), int(quality), int(adaptive))
+
+
+def quant_free(ctx):
+    _quant_free(ctx)
+
+
+def generate_quant_matrix(block_size, quality):
+    return _take_ragged(_gen_q(block_size, quality), block_size)
+
+
+def generate_dequant_matrix(quant_matrix):
+    n = np.asarray(quant_matrix).shape[0]
+    a = _Ragged(n, C.c_double, quant_matrix)
+    return _take_ragged(_gen_r(a.ptr, n), n)
+
+
+def quantize(ctx, dct_coeffs, block_variance=0.0):
+    n = ctx.contents.block_size
+    a, b = _Ragged(n, C.c_double, dct_coeffs), _Ragged(n, C.c_int)
+    _quantize(ctx, a.ptr, b.ptr, float(block_variance))
+    return b.numpy()
+
+
+def dequantize(ctx, quant_coeffs, block_variance=0.0):
+    n = ctx.contents.block_size
+    a, b = _Ragged(n, C.c_int, quant_coeffs), _Ragged(n, C.c_double)
+    _dequantize(ctx, a.ptr, b.ptr, float(block_variance))
+    return b.numpy()
+
+
+def calculate_block_variance(block):
+    n = np.asarray(block).shape[0]
+    return float(_variance(_Ragged(n, C.c_double, block).ptr, n))
+
+
+def adjust_matrix_for_block(ctx, variance, is_quantize):
+    return _take_ragged(_adjust(ctx, float(variance), int(is_quantize)), ctx.contents.block_size)
+
+
+def set_quant_table(qctx, table):
+    """Overwrites ctx->quant_matrix (and the matching 1/Q), the way a chroma table gets in."""
+    n = qctx.contents.block_size
+    t = np.asarray(table, dtype=np.float64)
+    for i in range(n):
+        for j in range(n):
+            qctx.contents.quant_matrix[i][j] = t[i, j]
+            qctx.contents.dequant_matrix[i][j] = 1.0 / t[i, j]
+
+
+def record_to_block(record, layout=NATURAL):
+    rec = np.ascontiguousarray(record, dtype=np.int16)
+    b = _Ragged(8, C.c_int)
+    _rec_to_block(rec.ctypes.data_as(C.POINTER(C.c_int16)), layout, b.ptr)
+    return b.numpy()
+
+
+def block_to_record(block, layout=NATURAL):
+    rec = np.zeros(64, dtype=np.int16)
+    _block_to_rec(_Ragged(8, C.c_int, block).ptr, layout, rec.ctypes.data_as(C.POINTER(C.c_int16)))
+    return rec
+
+
+# ---- include/dct_cuda.h ------------------------------------------------------------------------
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(getattr(stream, "cuda_stream", stream))
+
+
+class Plan:
+    """dct_cuda_plan: a (DCTContext, QuantContext) pair bound to one GPU."""
+
+    def __init__(self, dct_ctx, quant_ctx, device: int = 0):
+        self.dct_ctx, self.quant_ctx, self.device = dct_ctx, quant_ctx, device
+        self.adaptive = int(quant_ctx.contents.adaptive)
+        self._h = _plan_create(dct_ctx, quant_ctx, device)
+        if not self._h:
+            raise DctCudaError(_last_error().decode(errors="replace"))
+
+    def close(self):
+        if self._h:
+            _plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def refresh(self):
+        _check(_plan_refresh(self._h))
+        self.adaptive = int(self.quant_ctx.contents.adaptive)
+
+    # -- host arrays (numpy): pipelined H2D / kernels / D2H inside the library --------------
+    def fwd_quant(self, pixels, layout=NATURAL, coef_out=None, var_out=None, want_stats=False):
+        if _is_torch(pixels):
+            return self.fwd_quant_dev(pixels, layout, coef_out, var_out)
+        assert pixels.dtype == np.uint8 and pixels.ndim == 2 and pixels.strides[1] == 1
+        H, W = pixels.shape
+        nb = (H // 8) * (W // 8)
+        coef = coef_out if coef_out is not None else np.empty((nb, 64), dtype=np.int16)
+        var = var_out if var_out is not None else (np.empty(nb, dtype=np.float64) if self.adaptive else None)
+        st = Stats()
+        _check(_fwd_host(self._h, pixels.ctypes.data, pixels.strides[0], W, H, coef.ctypes.data, layout,
+                         var.ctypes.data if var is not None else None, C.byref(st)))
+        out = (coef, var) if self.adaptive else coef
+        return (out, st.as_dict()) if want_stats else out
+
+    def dequant_idct(self, coef, W, H, layout=NATURAL, var=None, pixels_out=None, want_stats=False):
+        if _is_torch(coef):
+            return self.dequant_idct_dev(coef, W, H, layout, var, pixels_out)
+        coef = np.ascontiguousarray(coef, dtype=np.int16)
+        px = pixels_out if pixels_out is not None else np.empty((H, W), dtype=np.uint8)
+        if var is not None:
+            var = np.ascontiguousarray(var, dtype=np.float64)
+        st = Stats()
+        _check(_inv_host(self._h, coef.ctypes.data, W, H, layout, var.ctypes.data if var is not None else None,
+                         px.ctypes.data, px.strides[0], C.byref(st)))
+        return (px, st.as_dict()) if want_stats else px
+
+    # -- raw host pointers (pinned torch tensors in bench.py) ---------------------------------
+    def fwd_quant_ptr(self, px_ptr, pitch, W, H, coef_ptr, layout=NATURAL, var_ptr=None):
+        _check(_fwd_host(self._h, px_ptr, pitch, W, H, coef_ptr, layout, var_ptr, None))
+
+    def dequant_idct_ptr(self, coef_ptr, W, H, px_ptr, pitch, layout=NATURAL, var_ptr=None):
+        _check(_inv_host(self._h, coef_ptr, W, H, layout, var_ptr, px_ptr, pitch, None))
+
+    # -- device tensors (torch, cuda): asynchronous on the current / given stream -----------
+    def fwd_quant_dev(self, pixels, layout=NATURAL, coef_out=None, var_out=None, stream=None):
+        import torch
+        assert pixels.is_cuda and pixels.dtype == torch.uint8 and pixels.dim() == 2 and pixels.stride(1) == 1
+        H, W = pixels.shape
+        nb = (H // 8) * (W // 8)
+        coef = coef_out if coef_out is not None else torch.empty((nb, 64), dtype=torch.int16, device=pixels.device)
+        var = var_out
+        if self.adaptive and var is None:
+            var = torch.empty(nb, dtype=torch.float64, device=pixels.device)
+        _check(_fwd_dev(self._h, pixels.data_ptr(), pixels.stride(0), W, H, coef.data_ptr(), layout,
+                        var.data_ptr() if var is not None else None, _stream_ptr(stream)))
+        return (coef, var) if self.adaptive else coef
+
+    def dequant_idct_dev(self, coef, W, H, layout=NATURAL, var=None, pixels_out=None, stream=None):
+        import torch
+        assert coef.is_cuda and coef.dtype == torch.int16 and coef.is_contiguous()
+        px = pixels_out if pixels_out is not None else torch.empty((H, W), dtype=torch.uint8, device=coef.device)
+        _check(_inv_dev(self._h, coef.data_ptr(), W, H, layout, var.data_ptr() if var is not None else None,
+                        px.data_ptr(), px.stride(0), _stream_ptr(stream)))
+        return px
+
+    def stats(self, stream=None):
+        st = Stats()
+        _check(_stats_fetch(self._h, C.byref(st), _stream_ptr(stream)))
+        return st.as_dict()
+
+
+def fwd_quant_multi(plans, pixels, layout=NATURAL):
+    """One host plane over several GPUs (block-row ranges, no inter-GPU traffic)."""
+    H, W = pixels.shape
+    nb = (H // 8) * (W // 8)
+    adaptive = plans[0].adaptive
+    coef = np.empty((nb, 64), dtype=np.int16)
+    var = np.empty(nb, dtype=np.float64) if adaptive else None
+    hs = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    st = Stats()
+    _check(_fwd_multi(hs, len(plans), pixels.ctypes.data, pixels.strides[0], W, H, coef.ctypes.data, layout,
+                      var.ctypes.data if var is not None else None, C.byref(st)))
+    return ((coef, var) if adaptive else coef), st.as_dict()
+
+
+def dequant_idct_multi(plans, coef, W, H, layout=NATURAL, var=None):
+    px = np.empty((H, W), dtype=np.uint8)
+    hs = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    st = Stats()
+    _check(_inv_multi(hs, len(plans), coef.ctypes.data, W, H, layout, var.ctypes.data if var is not None else None,
+                      px.ctypes.data, px.strides[0], C.byref(st)))
+    return px, st.as_dict()
+
+
+def exported_symbols():
+    """Names include/*.h declare; tests check that the library exports every one of them."""
+    return ["dct_init", "dct_free", "dct_forward", "dct_inverse", "create_block_from_pixels",
+            "copy_block_to_coefficients", "quant_init", "quant_free", "generate_quant_matrix",
+            "generate_dequant_matrix", "quantize", "dequantize", "calculate_block_variance",
+            "adjust_matrix_for_block", "dct_cuda_last_error", "dct_cuda_device_count", "dct_cuda_plan_create",
+            "dct_cuda_plan_refresh", "dct_cuda_plan_destroy", "dct_cuda_plan_device", "dct_cuda_fwd_quant_u8_dev",
+            "dct_cuda_dequant_idct_u8_dev", "dct_cuda_fwd_quant_planes_dev", "dct_cuda_dequant_idct_planes_dev",
+            "dct_cuda_fwd_quant_u8", "dct_cuda_dequant_idct_u8", "dct_cuda_fwd_quant_u8_multi",
+            "dct_cuda_dequant_idct_u8_multi", "dct_cuda_stats_fetch", "dct_cuda_record_to_block",
+            "dct_cuda_block_to_record", "dct_cuda_host_alloc", "dct_cuda_host_free"]

@@ -1,0 +1,127 @@
+// butterfly.cuh -- scaled 8-point forward / inverse DCT flowgraphs, 30 operations each.
+//
+// Replaces the inner triple loops of the reference's dct_forward (src/dct.c:57-74) and
+// dct_inverse (src/dct.c:85-102) on the fast path.  The arithmetic is NOT the reference's
+// (that is replayed bit-for-bit in replay_f64.cu); it is a Arai-Agui-Nakajima style
+// factorisation whose per-coefficient output scale is folded into the quantisation
+// multiplier.  tools/derive_bands.py executes this exact sequence of operations on
+// (functional, error-bound) pairs to derive the band inside which a result is re-done in
+// fp64 -- keep the two in step, operation for operation.
+//
+// Every operation is an explicit round-to-nearest intrinsic so that nvcc can neither
+// contract nor re-associate: the error analysis is of this code, not of what a compiler
+// might make of it.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dctb {
+
+template <typename T> struct Ops;
+
+template <> struct Ops<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float c) { return __fmul_rn(a, c); }
+    static __device__ __forceinline__ float fma(float a, float c, float b) { return __fmaf_rn(a, c, b); }
+    static __device__ __forceinline__ float fms(float a, float c, float b) { return __fmaf_rn(a, c, -b); }
+};
+
+template <> struct Ops<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double c) { return __dmul_rn(a, c); }
+    static __device__ __forceinline__ double fma(double a, double c, double b) { return __fma_rn(a, c, b); }
+    static __device__ __forceinline__ double fms(double a, double c, double b) { return __fma_rn(a, c, -b); }
+};
+
+// exact reals; T(...) rounds them once, exactly as numpy.float32(c) does in the model
+#define DCTB_C4    0.70710678118654752440
+#define DCTB_C382  0.38268343236508977173
+#define DCTB_C541  0.54119610014619698440
+#define DCTB_C1306 1.30656296487637652786
+#define DCTB_SQRT2 1.41421356237309504880
+#define DCTB_C1847 1.84775906502257351226
+#define DCTB_C1082 1.08239220029239396880
+#define DCTB_C2613 2.61312592975275305571
+
+// x[k*S], k = 0..7, transformed in place.  out[k] = a_k * sqrt(8) * (orthonormal DCT-II)[k],
+// a_0 = 1, a_k = sqrt(2) cos(k pi / 16).
+template <typename T, int S>
+__device__ __forceinline__ void fdct8(T *x)
+{
+    using O = Ops<T>;
+    const T s07 = O::add(x[0 * S], x[7 * S]), d07 = O::sub(x[0 * S], x[7 * S]);
+    const T s16 = O::add(x[1 * S], x[6 * S]), d16 = O::sub(x[1 * S], x[6 * S]);
+    const T s25 = O::add(x[2 * S], x[5 * S]), d25 = O::sub(x[2 * S], x[5 * S]);
+    const T s34 = O::add(x[3 * S], x[4 * S]), d34 = O::sub(x[3 * S], x[4 * S]);
+    const T e0 = O::add(s07, s34), e3 = O::sub(s07, s34);
+    const T e1 = O::add(s16, s25), e2 = O::sub(s16, s25);
+    x[0 * S] = O::add(e0, e1);
+    x[4 * S] = O::sub(e0, e1);
+    const T t = O::add(e2, e3);
+    x[2 * S] = O::fma(t, T(DCTB_C4), e3);
+    x[6 * S] = O::fma(t, T(-DCTB_C4), e3);
+    const T a = O::add(d34, d25), b = O::add(d25, d16), c = O::add(d16, d07);
+    const T z5 = O::mul(O::sub(a, c), T(DCTB_C382));
+    const T z2 = O::fma(a, T(DCTB_C541), z5), z4 = O::fma(c, T(DCTB_C1306), z5);
+    const T z11 = O::fma(b, T(DCTB_C4), d07), z13 = O::fma(b, T(-DCTB_C4), d07);
+    x[5 * S] = O::add(z13, z2);
+    x[3 * S] = O::sub(z13, z2);
+    x[1 * S] = O::add(z11, z4);
+    x[7 * S] = O::sub(z11, z4);
+}
+
+// v[k*S] pre-multiplied by a_k / sqrt(8); transformed in place to the 8 spatial samples.
+template <typename T, int S>
+__device__ __forceinline__ void idct8(T *v)
+{
+    using O = Ops<T>;
+    const T t10 = O::add(v[0 * S], v[4 * S]), t11 = O::sub(v[0 * S], v[4 * S]);
+    const T t13 = O::add(v[2 * S], v[6 * S]);
+    const T t12 = O::fms(O::sub(v[2 * S], v[6 * S]), T(DCTB_SQRT2), t13);
+    const T e0 = O::add(t10, t13), e3 = O::sub(t10, t13);
+    const T e1 = O::add(t11, t12), e2 = O::sub(t11, t12);
+    const T z13 = O::add(v[5 * S], v[3 * S]), z10 = O::sub(v[5 * S], v[3 * S]);
+    const T z11 = O::add(v[1 * S], v[7 * S]), z12 = O::sub(v[1 * S], v[7 * S]);
+    const T t7 = O::add(z11, z13);
+    const T zd = O::sub(z11, z13);
+    const T z5 = O::mul(O::add(z10, z12), T(DCTB_C1847));
+    const T t10o = O::fma(z12, T(-DCTB_C1082), z5);
+    const T t12o = O::fma(z10, T(-DCTB_C2613), z5);
+    const T t6 = O::sub(t12o, t7);
+    const T t5 = O::fms(zd, T(DCTB_SQRT2), t6);
+    const T t4 = O::sub(t10o, t5);
+    v[0 * S] = O::add(e0, t7);
+    v[1 * S] = O::add(e1, t6);
+    v[2 * S] = O::add(e2, t5);
+    v[3 * S] = O::add(e3, t4);
+    v[4 * S] = O::sub(e3, t4);
+    v[5 * S] = O::sub(e2, t5);
+    v[6 * S] = O::sub(e1, t6);
+    v[7 * S] = O::sub(e0, t7);
+}
+
+// zigzag position -> natural index (8i+j); the scan of src/entropy.c:158-178 for N = 8
+// (checked against the reference's block_to_zigzag in tests/test_host_logic.py).
+struct ZigZag {
+    int nat[64];
+    constexpr ZigZag() : nat{}
+    {
+        int idx = 0;
+        for (int s = 0; s <= 14; ++s) {
+            if (s % 2 == 0) {
+                for (int i = (s < 8) ? s : 7; i >= 0 && (s - i) < 8; --i) nat[idx++] = i * 8 + (s - i);
+            } else {
+                for (int i = (s < 8) ? 0 : s - 7; i < 8 && (s - i) >= 0; ++i) nat[idx++] = i * 8 + (s - i);
+            }
+        }
+    }
+};
+constexpr ZigZag kZigZag{};
+
+template <int LAYOUT> __host__ __device__ constexpr int storage_to_natural(int p)
+{
+    return LAYOUT == 1 ? kZigZag.nat[p] : p;
+}
+
+}  // namespace dctb

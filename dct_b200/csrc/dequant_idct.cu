@@ -1,0 +1,163 @@
+// dequant_idct.cu -- K2: int16 records -> dequantise -> 8x8 inverse DCT -> +128, round, clamp -> u8.
+//
+// Fuses, for every 8x8 block, the reference's
+//   zigzag_to_block (src/entropy.c:183-210, ZIGZAG layout only),
+//   dequantize (src/quantization.c:133-151: non-adaptive q * (1/Q) -- sic, SURVEY.md S2;
+//   adaptive q * (1.0 / ((1/Q) * (1/(2-nv)))), DC unscaled), dct_inverse (src/dct.c:80-105)
+// and the pixel rule p = clamp(round(x + 128.0), 0, 255) into one pass: 128 B in, 64 B out.
+//
+// Mapping mirrors K1: one thread per block, a warp owns 32 consecutive records (4 KB, read
+// with 512-byte contiguous LDG.128 through a padded shared-memory stage) and writes a
+// 256-pixel x 8-row tile with 8 STG.64 per lane (256 contiguous bytes per warp instruction).
+// The fp32 error bound is dynamic here (inputs are arbitrary int16): 2^-24 * sum gain_k |v_k|.
+#include "butterfly.cuh"
+#include "kernels.cuh"
+
+namespace dctb {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kStageWordsPerBlock = 36;
+constexpr int kStageWordsPerWarp = 32 * kStageWordsPerBlock;
+
+constexpr float kMagic128 = 12583040.0f;   // 1.5 * 2^23 + 128
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void stg_stream_u2(void *p, uint32_t a, uint32_t b)
+{
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+
+// halves of a word of two int16 (already XORed with 0x8000 each) -> float(int16), exactly
+template <int hi> __device__ __forceinline__ float biased_half_to_float(uint32_t wx)
+{
+    const uint32_t m = __byte_perm(wx, 0x4B000000u, hi ? 0x7432 : 0x7410);   // 2^23 + (q + 32768)
+    return __fadd_rn(__uint_as_float(m), -8421376.0f);                        // -(2^23 + 32768)
+}
+
+template <int LAYOUT, bool ADAPTIVE>
+__global__ void __launch_bounds__(kThreads) k_dequant_idct_u8(const __grid_constant__ InvParams p)
+{
+    __shared__ uint4 stage[kWarps * kStageWordsPerWarp / 4];
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warp_base = blockIdx.x * kThreads + warp * 32;
+    const uint32_t b = warp_base + lane;
+    const bool valid = b < p.nblocks;
+
+    // 4 KB of records: coalesced 16-byte chunks -> padded stage -> one record per lane
+    uint32_t *wstage = reinterpret_cast<uint32_t *>(stage) + warp * kStageWordsPerWarp;
+    const uint4 *srcv = reinterpret_cast<const uint4 *>(p.coef) + (size_t)warp_base * 8;
+    uint4 chunk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t c = j * 32 + lane;
+        chunk[j] = (warp_base + (c >> 3) < p.nblocks) ? ldg_stream_u4(srcv + c) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t c = j * 32 + lane;
+        *reinterpret_cast<uint4 *>(wstage + (c >> 3) * kStageWordsPerBlock + 4 * (c & 7)) = chunk[j];
+    }
+    __syncwarp();
+    uint32_t w[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint4 t = *reinterpret_cast<const uint4 *>(wstage + lane * kStageWordsPerBlock + 4 * j);
+        w[4 * j] = t.x, w[4 * j + 1] = t.y, w[4 * j + 2] = t.z, w[4 * j + 3] = t.w;
+    }
+
+    float s = 1.0f;
+    if constexpr (ADAPTIVE) {
+        // multiplier 1/((1/Q)*(1/(2-nv))) = Q*(2-nv) up to fp64 rounding; exact form in K3
+        const double var = (p.var_in != nullptr && valid) ? p.var_in[b] : 0.0;
+        const float nv = fminf(1.0f, fmaxf(0.1f, __fmul_rn((float)var, 1.0f / 1000.0f)));
+        s = __fsub_rn(2.0f, nv);
+    }
+
+    float v[64];
+    float bound = 0.f;   // sum gain_k * |v_k|
+    static_for<0, 32>([&](auto M) {
+        constexpr int m = decltype(M)::value;
+        constexpr int k0 = storage_to_natural<LAYOUT>(2 * m), k1 = storage_to_natural<LAYOUT>(2 * m + 1);
+        const uint32_t wx = w[m] ^ 0x80008000u;
+        float f0 = biased_half_to_float<0>(wx), f1 = biased_half_to_float<1>(wx);
+        if constexpr (ADAPTIVE) {
+            if (k0 != 0) f0 = __fmul_rn(f0, s);
+            f1 = __fmul_rn(f1, s);
+        }
+        v[k0] = __fmul_rn(f0, p.rs[k0]);
+        v[k1] = __fmul_rn(f1, p.rs[k1]);
+        bound = __fmaf_rn(fabsf(v[k0]), p.gain[k0], bound);
+        bound = __fmaf_rn(fabsf(v[k1]), p.gain[k1], bound);
+    });
+    // |fp32 pixel - exact pixel| <= 2^-24 * bound (derive_bands.py) ; + floor for the residual's own rounding
+    const float thr = __fsub_rn(0.5f, __fmaf_rn(bound, 5.9604645e-8f * 1.0625f, p.band_floor));
+
+    // columns (D^T * in), then rows (temp * D): same order as src/dct.c:85-102
+#pragma unroll
+    for (int j = 0; j < 8; ++j) idct8<float, 8>(&v[j]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) idct8<float, 1>(&v[8 * i]);
+
+    const uint32_t bb = valid ? b : p.nblocks - 1;
+    const uint32_t by = bb / p.bw, bx = bb - by * p.bw;
+    uint8_t *dst = p.px + (long long)by * 8 * p.pitch + (long long)bx * 8;
+
+    bool flag = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t tb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float x = fminf(fmaxf(v[8 * i + j], -128.0f), 127.0f);
+            const float t = __fadd_rn(x, kMagic128);            // low byte = round(x + 128)
+            const float e = __fsub_rn(x, __fsub_rn(t, kMagic128));   // x - round(x), exact
+            flag |= fabsf(e) >= thr;
+            tb[j] = __float_as_uint(t);
+        }
+        const uint32_t lo = __byte_perm(__byte_perm(tb[0], tb[1], 0x0040), __byte_perm(tb[2], tb[3], 0x0040), 0x5410);
+        const uint32_t hi = __byte_perm(__byte_perm(tb[4], tb[5], 0x0040), __byte_perm(tb[6], tb[7], 0x0040), 0x5410);
+        if (valid) stg_stream_u2(dst + i * p.pitch, lo, hi);
+    }
+
+    const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
+    if (ballot != 0) {
+        const int leader = __ffs(ballot) - 1;
+        unsigned base = 0;
+        if ((int)lane == leader) base = atomicAdd(&p.ctr->wl_count, (unsigned)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (flag && valid) {
+            const unsigned pos = base + __popc(ballot & ((1u << lane) - 1u));
+            if (pos < p.wl_cap) p.worklist[pos] = b;
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s)
+{
+    if (p.nblocks == 0) return cudaSuccess;
+    const unsigned grid = (p.nblocks + kThreads - 1) / kThreads;
+    if (layout == LAYOUT_ZIGZAG) {
+        if (adaptive) k_dequant_idct_u8<LAYOUT_ZIGZAG, true><<<grid, kThreads, 0, s>>>(p);
+        else          k_dequant_idct_u8<LAYOUT_ZIGZAG, false><<<grid, kThreads, 0, s>>>(p);
+    } else {
+        if (adaptive) k_dequant_idct_u8<LAYOUT_NATURAL, true><<<grid, kThreads, 0, s>>>(p);
+        else          k_dequant_idct_u8<LAYOUT_NATURAL, false><<<grid, kThreads, 0, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace dctb

@@ -1,0 +1,101 @@
+// kernels.cuh -- parameter blocks and launch entry points shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+#include <utility>
+
+namespace dctb {
+
+enum { LAYOUT_NATURAL = 0, LAYOUT_ZIGZAG = 1 };
+
+// Device-side counters of one plan (zeroed by the host before each plane call).
+struct Counters {
+    unsigned int wl_count;         // blocks appended to the replay worklist by K1/K2
+    unsigned int pad;
+    unsigned long long replayed;   // blocks re-done in fp64 by K3 (== min(wl_count, capacity))
+    unsigned long long near_ties;  // fp64 values within 1e-9 of a .5 boundary seen by K3
+    unsigned long long saturated;  // fp64 quantised values outside int16 (exotic tables only)
+};
+
+// fp64 tables exactly as the host contexts hold them (src/dct.c:19-30, src/quantization.c:51-111)
+struct ExactTables {
+    double D[64];   // dct_matrix, row-major
+    double Q[64];   // quant_matrix
+    double R[64];   // dequant_matrix
+};
+
+// K1: forward DCT + quantise.  One thread per 8x8 block.
+struct FwdParams {
+    const uint8_t *px;
+    long long pitch;       // bytes between pixel rows (multiple of 8)
+    uint32_t bw;           // blocks per block-row (W/8)
+    uint32_t nblocks;
+    int16_t *coef;         // block-major records, 64 x int16 = 128 B per block
+    double *var_out;       // adaptive only: per-block spatial variance (may be null)
+    uint32_t *worklist;
+    uint32_t wl_cap;
+    Counters *ctr;
+    float r[64];           // natural index: 1 / (Q_k * 8 a_u a_v)
+    float thr[64];         // natural index: 0.5 - band_k ; |residual| >= thr  => replay in fp64
+};
+
+// K2: dequantise + inverse DCT.  One thread per 8x8 block.
+struct InvParams {
+    const int16_t *coef;
+    const double *var_in;  // adaptive only
+    uint8_t *px;
+    long long pitch;
+    uint32_t bw;
+    uint32_t nblocks;
+    uint32_t *worklist;
+    uint32_t wl_cap;
+    Counters *ctr;
+    float rs[64];          // natural index: dequant multiplier * a_u a_v / 8
+    float gain[64];        // natural index: error gain of the butterfly per unit |input|
+    float band_floor;
+};
+
+// K3: exact fp64 replay of the blocks on the worklist (or of every block when wl == null).
+struct ReplayParams {
+    const ExactTables *tab;
+    const uint32_t *worklist;   // null => replay all nblocks
+    Counters *ctr;
+    uint32_t nblocks;
+    uint32_t wl_cap;
+    uint32_t bw;
+    int adaptive;
+    int layout;
+    long long pitch;
+    const uint8_t *px_in;       // forward
+    int16_t *coef_out;
+    double *var_out;
+    const int16_t *coef_in;     // inverse
+    const double *var_in;
+    uint8_t *px_out;
+};
+
+cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s);
+cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s);
+cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s);
+cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s);
+
+// generic-N single block kernels behind the per-block drop-in API (K4/K6)
+cudaError_t launch_block_dct_f64(int n, const double *d_D, const double *d_in, double *d_out, int inverse,
+                                 cudaStream_t s);
+cudaError_t launch_block_quantize_f64(int n, const double *d_Q, int adaptive, double variance,
+                                      const double *d_c, int *d_q, cudaStream_t s);
+cudaError_t launch_block_dequantize_f64(int n, const double *d_R, int adaptive, double variance,
+                                        const int *d_q, double *d_c, cudaStream_t s);
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
+template <int B, int E, typename F> __device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+}  // namespace dctb

@@ -1,0 +1,724 @@
+// shim.cu -- the C ABI of libdct_cuda: plans, plane calls, and the per-block compute calls of
+// include/dct.h / include/quantization.h (dct_forward, dct_inverse, quantize, dequantize).
+//
+// Reference interfaces replaced: include/dct.h:51,61 and include/quantization.h:69,79 (per
+// block), and the block loop a caller of those would write (tests/test_entropy.c:302-316,
+// :370-384) for the plane calls.  No CPU arithmetic happens on these paths; if CUDA is not
+// usable they fail (stderr + exit for the reference-style void calls, error code otherwise).
+#include <dct_cuda.h>
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "band_tables.h"
+#include "butterfly.cuh"
+#include "kernels.cuh"
+
+using namespace dctb;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                 \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(DCT_CUDA_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),      \
+                        __FILE__, __LINE__);                                                         \
+    } while (0)
+
+extern "C" const char *dct_cuda_last_error(void) { return g_err; }
+
+extern "C" int dct_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kLanes = 3;                       // depth of the host-plane pipeline
+constexpr size_t kStripPixels = 16u << 20;      // ~16 Mpx per strip
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    Counters *d_ctr = nullptr;
+    uint32_t *d_wl = nullptr;
+    uint32_t wl_cap = 0;
+    // strip buffers of the host-plane pipeline
+    uint8_t *d_px = nullptr;
+    int16_t *d_coef = nullptr;
+    double *d_var = nullptr;
+    size_t cap_blocks = 0;
+    uint64_t blocks = 0;                        // blocks queued since the last stats fetch
+};
+
+}  // namespace
+
+struct dct_cuda_plan {
+    int device = 0;
+    const DCTContext *dct = nullptr;
+    const QuantContext *quant = nullptr;
+    int adaptive = 0;
+    bool exotic = false;                        // tables outside the fast path's proven domain
+    ExactTables h_tab;
+    ExactTables *d_tab = nullptr;
+    float r[64], thr[64];                       // K1
+    float rs[64], gain[64], band_floor;         // K2
+    Lane lane[kLanes];
+    Counters *h_ctr = nullptr;                  // pinned, kLanes entries
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int read_tables(dct_cuda_plan *p)
+{
+    const DCTContext *d = p->dct;
+    const QuantContext *q = p->quant;
+    if (d->block_size != 8 || q->block_size != 8)
+        return fail(DCT_CUDA_EINVAL, "plane kernels are 8x8 only (block_size %d / %d); use the per-block calls",
+                    d->block_size, q->block_size);
+    p->adaptive = q->adaptive ? 1 : 0;
+    bool exotic = false;
+    for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) {
+            const int k = 8 * i + j;
+            p->h_tab.D[k] = d->dct_matrix[i][j];
+            p->h_tab.Q[k] = q->quant_matrix[i][j];
+            p->h_tab.R[k] = q->dequant_matrix[i][j];
+            const double Q = p->h_tab.Q[k], R = p->h_tab.R[k];
+            // the fp32 path's proof assumes Q in [1, 1e6] (|c/Q| < 2^15, clamp of adjust_matrix inert)
+            if (!(Q >= 1.0 && Q <= 1e6) || !std::isfinite(R) || R == 0.0) exotic = true;
+        }
+    p->exotic = exotic;
+
+    const double u = std::ldexp(1.0, -24);
+    for (int k = 0; k < 64; ++k) {
+        const double Q = p->h_tab.Q[k], R = p->h_tab.R[k];
+        // K1: y = c_scaled * r, r = 1/(Q * scale_k).  band = (beta_k + extra) / Q + floor:
+        //   beta_k   fp32 butterfly error + rounding of r itself (derive_bands.py)
+        //   extra    adaptive only: the fp32 1/(2-nv) and its product with r, <= 12u relative
+        const double extra = p->adaptive ? 12.0 * u * kFwdCmax[k] : 0.0;
+        const double band = ((double)kFwdBeta[k] * 1.02 + extra) / Q + std::ldexp(1.0, -22);
+        p->r[k] = (float)(1.0 / (Q * kFwdScale[k]));
+        double thr = 0.5 - band;
+        if (exotic || !(thr > 0.0)) thr = -1.0;   // everything replays
+        p->thr[k] = (float)thr;
+        if ((double)p->thr[k] > thr) p->thr[k] = std::nextafterf(p->thr[k], -1.0f);   // round down
+        // K2: v = q * rs.  non-adaptive: rs = R * prescale (sic: the reference multiplies by 1/Q);
+        //     adaptive: rs = (1/R) * prescale, times (2-nv) per block in the kernel.
+        const double mult = p->adaptive ? 1.0 / R : R;
+        p->rs[k] = (float)(mult * kInvPrescale[k]);
+        p->gain[k] = exotic ? 1e30f : kInvGain[k] * 1.02f;
+    }
+    p->band_floor = 1.0e-6f;
+    return DCT_CUDA_OK;
+}
+
+int ensure_worklist(Lane &ln, size_t nblocks)
+{
+    if (ln.wl_cap >= nblocks) return DCT_CUDA_OK;
+    if (ln.d_wl) {
+        CU_TRY(cudaStreamSynchronize(ln.stream));
+        CU_TRY(cudaDeviceSynchronize());
+        CU_TRY(cudaFree(ln.d_wl));
+        ln.d_wl = nullptr;
+        ln.wl_cap = 0;
+    }
+    CU_TRY(cudaMalloc(&ln.d_wl, nblocks * sizeof(uint32_t)));
+    ln.wl_cap = (uint32_t)nblocks;
+    return DCT_CUDA_OK;
+}
+
+// `dev`: the pitch is used by the kernels directly (8-byte rows); host planes are re-packed by the copy
+int check_plane(const void *a, const void *b, size_t pitch, int W, int H, bool dev)
+{
+    if (!a || !b) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
+    if (W < 0 || H < 0 || (W % 8) || (H % 8))
+        return fail(DCT_CUDA_EINVAL, "width and height must be non-negative multiples of 8 (got %dx%d)", W, H);
+    if (pitch < (size_t)W || (dev && (pitch % 8)))
+        return fail(DCT_CUDA_EINVAL, "pitch %zu must be >= width%s", pitch, dev ? " and a multiple of 8" : "");
+    if ((uint64_t)(W / 8) * (uint64_t)(H / 8) > 0xFFFFFFF0ull) return fail(DCT_CUDA_EINVAL, "too many blocks");
+    return DCT_CUDA_OK;
+}
+
+// queue K1 (+K3) for one device-resident plane on lane `ln`, stream `s`
+int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int W, int H, int16_t *d_coef,
+              int layout, double *d_var, cudaStream_t s)
+{
+    const uint32_t bw = W / 8, nblocks = bw * (uint32_t)(H / 8);
+    if (nblocks == 0) return DCT_CUDA_OK;
+    if (((uintptr_t)d_px % 8) || ((uintptr_t)d_coef % 16))
+        return fail(DCT_CUDA_EINVAL, "pixels must be 8-byte and coefficients 16-byte aligned");
+    if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
+    int rc = ensure_worklist(ln, nblocks);
+    if (rc) return rc;
+    CU_TRY(cudaMemsetAsync(&ln.d_ctr->wl_count, 0, sizeof(unsigned), s));
+
+    ReplayParams rp{};
+    rp.tab = p->d_tab;
+    rp.ctr = ln.d_ctr;
+    rp.nblocks = nblocks;
+    rp.wl_cap = ln.wl_cap;
+    rp.bw = bw;
+    rp.adaptive = p->adaptive;
+    rp.layout = layout;
+    rp.pitch = (long long)pitch;
+    rp.px_in = d_px;
+    rp.coef_out = d_coef;
+    rp.var_out = p->adaptive ? d_var : nullptr;
+    if (!p->exotic) {
+        FwdParams fp{};
+        fp.px = d_px;
+        fp.pitch = (long long)pitch;
+        fp.bw = bw;
+        fp.nblocks = nblocks;
+        fp.coef = d_coef;
+        fp.var_out = p->adaptive ? d_var : nullptr;
+        fp.worklist = ln.d_wl;
+        fp.wl_cap = ln.wl_cap;
+        fp.ctr = ln.d_ctr;
+        memcpy(fp.r, p->r, sizeof fp.r);
+        memcpy(fp.thr, p->thr, sizeof fp.thr);
+        CU_TRY(launch_fwd_quant_u8(fp, layout, p->adaptive, s));
+        rp.worklist = ln.d_wl;
+    }
+    CU_TRY(launch_replay_fwd(rp, s));
+    ln.blocks += nblocks;
+    return DCT_CUDA_OK;
+}
+
+int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, int layout, const double *d_var,
+              uint8_t *d_px, size_t pitch, cudaStream_t s)
+{
+    const uint32_t bw = W / 8, nblocks = bw * (uint32_t)(H / 8);
+    if (nblocks == 0) return DCT_CUDA_OK;
+    if (((uintptr_t)d_px % 8) || ((uintptr_t)d_coef % 16))
+        return fail(DCT_CUDA_EINVAL, "pixels must be 8-byte and coefficients 16-byte aligned");
+    if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
+    if (p->adaptive && !d_var) return fail(DCT_CUDA_EINVAL, "adaptive plan needs the per-block variance array");
+    int rc = ensure_worklist(ln, nblocks);
+    if (rc) return rc;
+    CU_TRY(cudaMemsetAsync(&ln.d_ctr->wl_count, 0, sizeof(unsigned), s));
+
+    ReplayParams rp{};
+    rp.tab = p->d_tab;
+    rp.ctr = ln.d_ctr;
+    rp.nblocks = nblocks;
+    rp.wl_cap = ln.wl_cap;
+    rp.bw = bw;
+    rp.adaptive = p->adaptive;
+    rp.layout = layout;
+    rp.pitch = (long long)pitch;
+    rp.coef_in = d_coef;
+    rp.var_in = p->adaptive ? d_var : nullptr;
+    rp.px_out = d_px;
+    if (!p->exotic) {
+        InvParams ip{};
+        ip.coef = d_coef;
+        ip.var_in = p->adaptive ? d_var : nullptr;
+        ip.px = d_px;
+        ip.pitch = (long long)pitch;
+        ip.bw = bw;
+        ip.nblocks = nblocks;
+        ip.worklist = ln.d_wl;
+        ip.wl_cap = ln.wl_cap;
+        ip.ctr = ln.d_ctr;
+        memcpy(ip.rs, p->rs, sizeof ip.rs);
+        memcpy(ip.gain, p->gain, sizeof ip.gain);
+        ip.band_floor = p->band_floor;
+        CU_TRY(launch_dequant_idct_u8(ip, layout, p->adaptive, s));
+        rp.worklist = ln.d_wl;
+    }
+    CU_TRY(launch_replay_inv(rp, s));
+    ln.blocks += nblocks;
+    return DCT_CUDA_OK;
+}
+
+int ensure_strip_buffers(dct_cuda_plan *p, Lane &ln, size_t blocks)
+{
+    if (ln.cap_blocks >= blocks) return DCT_CUDA_OK;
+    CU_TRY(cudaStreamSynchronize(ln.stream));
+    if (ln.d_px) cudaFree(ln.d_px);
+    if (ln.d_coef) cudaFree(ln.d_coef);
+    if (ln.d_var) cudaFree(ln.d_var);
+    ln.d_px = nullptr, ln.d_coef = nullptr, ln.d_var = nullptr, ln.cap_blocks = 0;
+    CU_TRY(cudaMalloc(&ln.d_px, blocks * 64));
+    CU_TRY(cudaMalloc(&ln.d_coef, blocks * 128));
+    if (p->adaptive) CU_TRY(cudaMalloc(&ln.d_var, blocks * sizeof(double)));
+    ln.cap_blocks = blocks;
+    return DCT_CUDA_OK;
+}
+
+int collect_stats(dct_cuda_plan *p, dct_cuda_stats *out, cudaStream_t user_stream)
+{
+    // lane 0 may have been driven on a caller's stream
+    CU_TRY(cudaStreamSynchronize(user_stream));
+    dct_cuda_stats st{};
+    for (int l = 0; l < kLanes; ++l) {
+        Lane &ln = p->lane[l];
+        CU_TRY(cudaStreamSynchronize(ln.stream));
+        CU_TRY(cudaMemcpy(&p->h_ctr[l], ln.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemset(ln.d_ctr, 0, sizeof(Counters)));
+        st.blocks += ln.blocks;
+        st.replayed_blocks += p->h_ctr[l].replayed;
+        st.near_ties += p->h_ctr[l].near_ties;
+        st.saturated += p->h_ctr[l].saturated;
+        ln.blocks = 0;
+    }
+    if (out) *out = st;
+    return DCT_CUDA_OK;
+}
+
+}  // namespace
+
+extern "C" dct_cuda_plan *dct_cuda_plan_create(const DCTContext *dct, const QuantContext *quant, int device)
+{
+    if (!dct || !quant) {
+        fail(DCT_CUDA_EINVAL, "NULL context");
+        return nullptr;
+    }
+    const int ndev = dct_cuda_device_count();
+    if (ndev <= 0) {
+        fail(DCT_CUDA_ENODEV, "no CUDA device available (libdct_cuda has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        fail(DCT_CUDA_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+        return nullptr;
+    }
+    dct_cuda_plan *p = new (std::nothrow) dct_cuda_plan();
+    if (!p) {
+        fail(DCT_CUDA_ENOMEM, "out of host memory");
+        return nullptr;
+    }
+    p->device = device;
+    p->dct = dct;
+    p->quant = quant;
+    DeviceGuard g(device);
+    auto init = [&]() -> int {
+        int rc = read_tables(p);
+        if (rc) return rc;
+        CU_TRY(cudaMalloc(&p->d_tab, sizeof(ExactTables)));
+        CU_TRY(cudaMemcpy(p->d_tab, &p->h_tab, sizeof(ExactTables), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMallocHost(&p->h_ctr, kLanes * sizeof(Counters)));
+        for (int l = 0; l < kLanes; ++l) {
+            CU_TRY(cudaStreamCreateWithFlags(&p->lane[l].stream, cudaStreamNonBlocking));
+            CU_TRY(cudaMalloc(&p->lane[l].d_ctr, sizeof(Counters)));
+            CU_TRY(cudaMemset(p->lane[l].d_ctr, 0, sizeof(Counters)));
+        }
+        return DCT_CUDA_OK;
+    };
+    if (init() != DCT_CUDA_OK) {
+        dct_cuda_plan_destroy(p);
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" int dct_cuda_plan_refresh(dct_cuda_plan *p)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    DeviceGuard g(p->device);
+    CU_TRY(cudaDeviceSynchronize());
+    int rc = read_tables(p);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpy(p->d_tab, &p->h_tab, sizeof(ExactTables), cudaMemcpyHostToDevice));
+    return DCT_CUDA_OK;
+}
+
+extern "C" void dct_cuda_plan_destroy(dct_cuda_plan *p)
+{
+    if (!p) return;
+    DeviceGuard g(p->device);
+    cudaDeviceSynchronize();
+    for (int l = 0; l < kLanes; ++l) {
+        Lane &ln = p->lane[l];
+        if (ln.d_ctr) cudaFree(ln.d_ctr);
+        if (ln.d_wl) cudaFree(ln.d_wl);
+        if (ln.d_px) cudaFree(ln.d_px);
+        if (ln.d_coef) cudaFree(ln.d_coef);
+        if (ln.d_var) cudaFree(ln.d_var);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+    }
+    if (p->d_tab) cudaFree(p->d_tab);
+    if (p->h_ctr) cudaFreeHost(p->h_ctr);
+    delete p;
+}
+
+extern "C" int dct_cuda_plan_device(const dct_cuda_plan *p) { return p ? p->device : -1; }
+
+// ------------------------------------------------------------------------------------------
+// device-resident planes
+// ------------------------------------------------------------------------------------------
+extern "C" int dct_cuda_fwd_quant_u8_dev(dct_cuda_plan *p, const uint8_t *d_px, size_t pitch, int W, int H,
+                                         int16_t *d_coef, int layout, double *d_var, void *stream)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    int rc = check_plane(d_px, d_coef, pitch, W, H, true);
+    if (rc) return rc;
+    DeviceGuard g(p->device);
+    return queue_fwd(p, p->lane[0], d_px, pitch, W, H, d_coef, layout, d_var, (cudaStream_t)stream);
+}
+
+extern "C" int dct_cuda_dequant_idct_u8_dev(dct_cuda_plan *p, const int16_t *d_coef, int W, int H, int layout,
+                                            const double *d_var, uint8_t *d_px, size_t pitch, void *stream)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    int rc = check_plane(d_px, d_coef, pitch, W, H, true);
+    if (rc) return rc;
+    DeviceGuard g(p->device);
+    return queue_inv(p, p->lane[0], d_coef, W, H, layout, d_var, d_px, pitch, (cudaStream_t)stream);
+}
+
+extern "C" int dct_cuda_fwd_quant_planes_dev(const dct_cuda_plane *pl, int n, int layout, void *stream)
+{
+    if (!pl || n < 0) return fail(DCT_CUDA_EINVAL, "bad plane list");
+    for (int i = 0; i < n; ++i) {
+        int rc = dct_cuda_fwd_quant_u8_dev(pl[i].plan, (const uint8_t *)pl[i].pixels_in, pl[i].pitch, pl[i].width,
+                                           pl[i].height, (int16_t *)pl[i].coef, layout, pl[i].variance, stream);
+        if (rc) return rc;
+    }
+    return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_dequant_idct_planes_dev(const dct_cuda_plane *pl, int n, int layout, void *stream)
+{
+    if (!pl || n < 0) return fail(DCT_CUDA_EINVAL, "bad plane list");
+    for (int i = 0; i < n; ++i) {
+        int rc = dct_cuda_dequant_idct_u8_dev(pl[i].plan, (const int16_t *)pl[i].coef, pl[i].width, pl[i].height,
+                                              layout, pl[i].variance, (uint8_t *)pl[i].pixels_out, pl[i].pitch,
+                                              stream);
+        if (rc) return rc;
+    }
+    return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_stats_fetch(dct_cuda_plan *p, dct_cuda_stats *stats, void *stream)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    DeviceGuard g(p->device);
+    return collect_stats(p, stats, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// host planes: strips of block rows through a kLanes-deep H2D / kernel / D2H pipeline
+// ------------------------------------------------------------------------------------------
+static int strip_rows(int W, int H)
+{
+    const size_t bw = (size_t)W / 8;
+    if (bw == 0 || H == 0) return 0;
+    size_t rows = std::max<size_t>(1, kStripPixels / (bw * 64));            // block rows per strip
+    const size_t total = (size_t)H / 8;
+    // at least kLanes strips when the plane is big enough to be worth overlapping
+    if (total >= (size_t)kLanes * 4) rows = std::min(rows, (total + kLanes - 1) / kLanes);
+    return (int)std::min(rows, total);
+}
+
+extern "C" int dct_cuda_fwd_quant_u8(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H,
+                                     int16_t *coef, int layout, double *var, dct_cuda_stats *stats)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    int rc = check_plane(px, coef, pitch, W, H, false);
+    if (rc) return rc;
+    if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
+    DeviceGuard g(p->device);
+    const int bw = W / 8, total_rows = H / 8, rows = strip_rows(W, H);
+    if (rows > 0) {
+        for (int l = 0; l < kLanes; ++l)
+            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw))) return rc;
+        int idx = 0;
+        for (int r0 = 0; r0 < total_rows; r0 += rows, ++idx) {
+            Lane &ln = p->lane[idx % kLanes];
+            const int nr = std::min(rows, total_rows - r0);
+            const size_t nb = (size_t)nr * bw, b0 = (size_t)r0 * bw;
+            CU_TRY(cudaMemcpy2DAsync(ln.d_px, (size_t)W, px + (size_t)r0 * 8 * pitch, pitch, (size_t)W, (size_t)nr * 8,
+                                     cudaMemcpyHostToDevice, ln.stream));
+            if ((rc = queue_fwd(p, ln, ln.d_px, (size_t)W, W, nr * 8, ln.d_coef, layout, ln.d_var, ln.stream))) return rc;
+            CU_TRY(cudaMemcpyAsync(coef + b0 * 64, ln.d_coef, nb * 128, cudaMemcpyDeviceToHost, ln.stream));
+            if (p->adaptive && var)
+                CU_TRY(cudaMemcpyAsync(var + b0, ln.d_var, nb * sizeof(double), cudaMemcpyDeviceToHost, ln.stream));
+        }
+    }
+    for (int l = 0; l < kLanes; ++l) CU_TRY(cudaStreamSynchronize(p->lane[l].stream));
+    if (stats) return collect_stats(p, stats, nullptr);
+    return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_dequant_idct_u8(dct_cuda_plan *p, const int16_t *coef, int W, int H, int layout,
+                                        const double *var, uint8_t *px, size_t pitch, dct_cuda_stats *stats)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    int rc = check_plane(px, coef, pitch, W, H, false);
+    if (rc) return rc;
+    if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
+    if (p->adaptive && !var) return fail(DCT_CUDA_EINVAL, "adaptive plan needs the per-block variance array");
+    DeviceGuard g(p->device);
+    const int bw = W / 8, total_rows = H / 8, rows = strip_rows(W, H);
+    if (rows > 0) {
+        for (int l = 0; l < kLanes; ++l)
+            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw))) return rc;
+        int idx = 0;
+        for (int r0 = 0; r0 < total_rows; r0 += rows, ++idx) {
+            Lane &ln = p->lane[idx % kLanes];
+            const int nr = std::min(rows, total_rows - r0);
+            const size_t nb = (size_t)nr * bw, b0 = (size_t)r0 * bw;
+            CU_TRY(cudaMemcpyAsync(ln.d_coef, coef + b0 * 64, nb * 128, cudaMemcpyHostToDevice, ln.stream));
+            if (p->adaptive)
+                CU_TRY(cudaMemcpyAsync(ln.d_var, var + b0, nb * sizeof(double), cudaMemcpyHostToDevice, ln.stream));
+            if ((rc = queue_inv(p, ln, ln.d_coef, W, nr * 8, layout, ln.d_var, ln.d_px, (size_t)W, ln.stream))) return rc;
+            CU_TRY(cudaMemcpy2DAsync(px + (size_t)r0 * 8 * pitch, pitch, ln.d_px, (size_t)W, (size_t)W, (size_t)nr * 8,
+                                     cudaMemcpyDeviceToHost, ln.stream));
+        }
+    }
+    for (int l = 0; l < kLanes; ++l) CU_TRY(cudaStreamSynchronize(p->lane[l].stream));
+    if (stats) return collect_stats(p, stats, nullptr);
+    return DCT_CUDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// several GPUs: block-row ranges, one host thread per plan, no inter-GPU traffic
+// ------------------------------------------------------------------------------------------
+template <typename F> static int run_sharded(dct_cuda_plan *const *plans, int n, int H, dct_cuda_stats *stats, F &&body)
+{
+    if (!plans || n <= 0) return fail(DCT_CUDA_EINVAL, "no plans");
+    const int total_rows = H / 8;
+    std::vector<int> rcs(n, 0);
+    std::vector<dct_cuda_stats> sts(n);
+    std::vector<std::string> errs(n);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n; ++g) {
+        const int r0 = (int)((long long)total_rows * g / n), r1 = (int)((long long)total_rows * (g + 1) / n);
+        th.emplace_back([&, g, r0, r1]() {
+            memset(&sts[g], 0, sizeof sts[g]);
+            rcs[g] = (r1 > r0) ? body(plans[g], r0, r1, &sts[g]) : 0;
+            if (rcs[g]) errs[g] = dct_cuda_last_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    dct_cuda_stats sum{};
+    for (int g = 0; g < n; ++g) {
+        if (rcs[g]) return fail(rcs[g], "GPU shard %d: %s", g, errs[g].c_str());
+        sum.blocks += sts[g].blocks, sum.replayed_blocks += sts[g].replayed_blocks;
+        sum.near_ties += sts[g].near_ties, sum.saturated += sts[g].saturated;
+    }
+    if (stats) *stats = sum;
+    return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_fwd_quant_u8_multi(dct_cuda_plan *const *plans, int n, const uint8_t *px, size_t pitch, int W,
+                                           int H, int16_t *coef, int layout, double *var, dct_cuda_stats *stats)
+{
+    int rc = check_plane(px, coef, pitch, W, H, false);
+    if (rc) return rc;
+    const size_t bw = (size_t)W / 8;
+    return run_sharded(plans, n, H, stats, [&](dct_cuda_plan *p, int r0, int r1, dct_cuda_stats *st) {
+        return dct_cuda_fwd_quant_u8(p, px + (size_t)r0 * 8 * pitch, pitch, W, (r1 - r0) * 8, coef + (size_t)r0 * bw * 64,
+                                     layout, var ? var + (size_t)r0 * bw : nullptr, st);
+    });
+}
+
+extern "C" int dct_cuda_dequant_idct_u8_multi(dct_cuda_plan *const *plans, int n, const int16_t *coef, int W, int H,
+                                              int layout, const double *var, uint8_t *px, size_t pitch,
+                                              dct_cuda_stats *stats)
+{
+    int rc = check_plane(px, coef, pitch, W, H, false);
+    if (rc) return rc;
+    const size_t bw = (size_t)W / 8;
+    return run_sharded(plans, n, H, stats, [&](dct_cuda_plan *p, int r0, int r1, dct_cuda_stats *st) {
+        return dct_cuda_dequant_idct_u8(p, coef + (size_t)r0 * bw * 64, W, (r1 - r0) * 8, layout,
+                                        var ? var + (size_t)r0 * bw : nullptr, px + (size_t)r0 * 8 * pitch, pitch, st);
+    });
+}
+
+// ------------------------------------------------------------------------------------------
+// adapters for the host consumer
+// ------------------------------------------------------------------------------------------
+extern "C" void dct_cuda_record_to_block(const int16_t *rec, int layout, int **block)
+{
+    for (int k = 0; k < 64; ++k) {
+        const int nat = layout == DCT_CUDA_ZIGZAG ? kZigZag.nat[k] : k;
+        block[nat >> 3][nat & 7] = rec[k];
+    }
+}
+
+extern "C" void dct_cuda_block_to_record(int **block, int layout, int16_t *rec)
+{
+    for (int k = 0; k < 64; ++k) {
+        const int nat = layout == DCT_CUDA_ZIGZAG ? kZigZag.nat[k] : k;
+        rec[k] = (int16_t)block[nat >> 3][nat & 7];
+    }
+}
+
+extern "C" void *dct_cuda_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        fail(DCT_CUDA_ENOMEM, "cudaMallocHost(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void dct_cuda_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------
+// per-block drop-in calls: include/dct.h:51,61  include/quantization.h:69,79
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct BlockScratch {
+    bool ready = false;
+    double *d_tab = nullptr, *d_in = nullptr, *d_out = nullptr;
+    int *d_int = nullptr;
+    double *h = nullptr;      // pinned: 3 * 1024 doubles
+    int *h_int = nullptr;     // pinned: 1024 ints
+    cudaStream_t stream = nullptr;
+};
+std::mutex g_block_mu;
+BlockScratch g_block;
+
+[[noreturn]] void die(const char *what, cudaError_t e)
+{
+    fprintf(stderr, "libdct_cuda: %s failed: %s (no CPU fallback)\n", what, cudaGetErrorString(e));
+    exit(EXIT_FAILURE);
+}
+#define CU_DIE(expr)                                  \
+    do {                                              \
+        cudaError_t e_ = (expr);                      \
+        if (e_ != cudaSuccess) die(#expr, e_);        \
+    } while (0)
+
+BlockScratch &scratch()
+{
+    if (!g_block.ready) {
+        CU_DIE(cudaMalloc(&g_block.d_tab, 1024 * sizeof(double)));
+        CU_DIE(cudaMalloc(&g_block.d_in, 1024 * sizeof(double)));
+        CU_DIE(cudaMalloc(&g_block.d_out, 1024 * sizeof(double)));
+        CU_DIE(cudaMalloc(&g_block.d_int, 1024 * sizeof(int)));
+        CU_DIE(cudaMallocHost(&g_block.h, 3 * 1024 * sizeof(double)));
+        CU_DIE(cudaMallocHost(&g_block.h_int, 1024 * sizeof(int)));
+        CU_DIE(cudaStreamCreateWithFlags(&g_block.stream, cudaStreamNonBlocking));
+        g_block.ready = true;
+    }
+    return g_block;
+}
+
+void check_n(int n)
+{
+    if (n < 1 || n > 32) {
+        fprintf(stderr, "libdct_cuda: block_size %d unsupported (1..32)\n", n);
+        exit(EXIT_FAILURE);
+    }
+}
+
+void block_transform(DCTContext *ctx, double **input, double **output, int inverse)
+{
+    const int n = ctx->block_size;
+    check_n(n);
+    std::lock_guard<std::mutex> lk(g_block_mu);
+    BlockScratch &s = scratch();
+    double *hD = s.h, *hI = s.h + 1024, *hO = s.h + 2048;
+    for (int i = 0; i < n; ++i) {
+        memcpy(hD + i * n, ctx->dct_matrix[i], n * sizeof(double));   // rows are separate mallocs
+        memcpy(hI + i * n, input[i], n * sizeof(double));
+    }
+    const size_t bytes = (size_t)n * n * sizeof(double);
+    CU_DIE(cudaMemcpyAsync(s.d_tab, hD, bytes, cudaMemcpyHostToDevice, s.stream));
+    CU_DIE(cudaMemcpyAsync(s.d_in, hI, bytes, cudaMemcpyHostToDevice, s.stream));
+    CU_DIE(launch_block_dct_f64(n, s.d_tab, s.d_in, s.d_out, inverse, s.stream));
+    CU_DIE(cudaMemcpyAsync(hO, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
+    CU_DIE(cudaStreamSynchronize(s.stream));
+    for (int i = 0; i < n; ++i) memcpy(output[i], hO + i * n, n * sizeof(double));
+}
+
+}  // namespace
+
+extern "C" void dct_forward(DCTContext *ctx, double **input, double **output) { block_transform(ctx, input, output, 0); }
+extern "C" void dct_inverse(DCTContext *ctx, double **input, double **output) { block_transform(ctx, input, output, 1); }
+
+extern "C" void quantize(QuantContext *ctx, double **dct_coeffs, int **quant_coeffs, double block_variance)
+{
+    const int n = ctx->block_size;
+    check_n(n);
+    std::lock_guard<std::mutex> lk(g_block_mu);
+    BlockScratch &s = scratch();
+    double *hQ = s.h, *hC = s.h + 1024;
+    for (int i = 0; i < n; ++i) {
+        memcpy(hQ + i * n, ctx->quant_matrix[i], n * sizeof(double));
+        memcpy(hC + i * n, dct_coeffs[i], n * sizeof(double));
+    }
+    const size_t bytes = (size_t)n * n * sizeof(double);
+    CU_DIE(cudaMemcpyAsync(s.d_tab, hQ, bytes, cudaMemcpyHostToDevice, s.stream));
+    CU_DIE(cudaMemcpyAsync(s.d_in, hC, bytes, cudaMemcpyHostToDevice, s.stream));
+    CU_DIE(launch_block_quantize_f64(n, s.d_tab, ctx->adaptive, block_variance, s.d_in, s.d_int, s.stream));
+    CU_DIE(cudaMemcpyAsync(s.h_int, s.d_int, (size_t)n * n * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CU_DIE(cudaStreamSynchronize(s.stream));
+    for (int i = 0; i < n; ++i) memcpy(quant_coeffs[i], s.h_int + i * n, n * sizeof(int));
+}
+
+extern "C" void dequantize(QuantContext *ctx, int **quant_coeffs, double **dct_coeffs, double block_variance)
+{
+    const int n = ctx->block_size;
+    check_n(n);
+    std::lock_guard<std::mutex> lk(g_block_mu);
+    BlockScratch &s = scratch();
+    double *hR = s.h, *hO = s.h + 2048;
+    for (int i = 0; i < n; ++i) {
+        memcpy(hR + i * n, ctx->dequant_matrix[i], n * sizeof(double));
+        memcpy(s.h_int + i * n, quant_coeffs[i], n * sizeof(int));
+    }
+    const size_t bytes = (size_t)n * n * sizeof(double);
+    CU_DIE(cudaMemcpyAsync(s.d_tab, hR, bytes, cudaMemcpyHostToDevice, s.stream));
+    CU_DIE(cudaMemcpyAsync(s.d_int, s.h_int, (size_t)n * n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+    CU_DIE(launch_block_dequantize_f64(n, s.d_tab, ctx->adaptive, block_variance, s.d_int, s.d_out, s.stream));
+    CU_DIE(cudaMemcpyAsync(hO, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
+    CU_DIE(cudaStreamSynchronize(s.stream));
+    for (int i = 0; i < n; ++i) memcpy(dct_coeffs[i], hO + i * n, n * sizeof(double));
+}

@@ -1,0 +1,135 @@
+/*
+ * dct_cuda.h -- plane / batch entry points of libdct_cuda (C ABI, plain pointers and sizes).
+ *
+ * The reference (erkinov-wtf/dct) has no image-level code: its only composed caller,
+ * tests/test_entropy.c:278-405, walks ONE 8x8 block through
+ *     create_block_from_pixels  src/dct.c:109      \
+ *     dct_forward               src/dct.c:52        > dct_cuda_fwd_quant_u8*      (kernel K1 + K3)
+ *     quantize                  src/quantization.c:113 /
+ *     [block_to_zigzag          src/entropy.c:158]    layout = DCT_CUDA_ZIGZAG
+ *     dequantize                src/quantization.c:133 \
+ *     dct_inverse               src/dct.c:80            > dct_cuda_dequant_idct_u8* (kernel K2 + K3)
+ *     +128, round, clamp to u8  tests/test_entropy.c:380-384 /
+ * These entry points are that loop over every block of a plane, bit-identical in their integer
+ * results to calling the reference's functions block by block (exact .5 ties included: blocks
+ * whose fp32 result falls inside the proven error band are re-done in the reference's own
+ * fp64 operation order; their number is reported in dct_cuda_stats).
+ *
+ * Data formats
+ *   pixels        uint8, row-major, `pitch` bytes between rows (multiple of 8), W and H
+ *                 multiples of 8.  A batch of equally sized frames stored back to back is one
+ *                 plane of height n_frames*H.
+ *   coefficients  int16 records, block-major: coef[(by*(W/8) + bx)*64 + k], 128 bytes per block.
+ *                 DCT_CUDA_NATURAL: k = 8*i + j.  DCT_CUDA_ZIGZAG: k = position in
+ *                 block_to_zigzag()'s output.  int16 is lossless: |c| <= 1024 and Q >= 1.
+ *                 dct_cuda_record_to_block() widens one record into the ragged int** that the
+ *                 untouched run_length_encode() (src/entropy.c:216) expects -- NATURAL order,
+ *                 because run_length_encode applies the zigzag itself.
+ *   variance      adaptive contexts only: one double per block (the side information the
+ *                 reference passes as `block_variance`), written by the forward call and read
+ *                 by the inverse call.
+ *
+ * A dct_cuda_plan binds a (DCTContext, QuantContext) pair to one GPU: it uploads the host-made
+ * fp64 tables, derives the fp32 multipliers and error bands, and owns the replay worklist.
+ * Plans are cheap; use one per host thread / stream.  All functions return 0 or a negative
+ * DCT_CUDA_E* code; dct_cuda_last_error() describes the last failure on the calling thread.
+ * There is no CPU fallback anywhere: without a CUDA device every call fails.
+ */
+#ifndef DCT_CUDA_H
+#define DCT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include <dct.h>
+#include <quantization.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCT_CUDA_NATURAL 0
+#define DCT_CUDA_ZIGZAG 1
+
+#define DCT_CUDA_OK 0
+#define DCT_CUDA_EINVAL (-1)  /* bad shape, alignment, layout or NULL argument */
+#define DCT_CUDA_ECUDA (-2)   /* a CUDA call failed; see dct_cuda_last_error() */
+#define DCT_CUDA_ENOMEM (-3)
+#define DCT_CUDA_ENODEV (-4)  /* no usable CUDA device */
+
+typedef struct dct_cuda_plan dct_cuda_plan;
+
+typedef struct {
+    uint64_t blocks;          /* 8x8 blocks processed since the last fetch                          */
+    uint64_t replayed_blocks; /* of those, re-done in fp64 because a value sat inside the band       */
+    uint64_t near_ties;       /* fp64 values within 1e-9 of a .5 rounding boundary (exact ties)      */
+    uint64_t saturated;       /* quantised values outside int16 (only with tables below 1.0)         */
+} dct_cuda_stats;
+
+/* one plane of a multi-plane frame (e.g. Y, Cb, Cr of a 4:2:0 frame, each with its own tables) */
+typedef struct {
+    dct_cuda_plan *plan;
+    const void *pixels_in; /* forward: uint8 source;   inverse: unused  */
+    void *pixels_out;      /* inverse: uint8 destination                 */
+    size_t pitch;
+    int width, height;
+    void *coef;            /* int16 records (forward: destination, inverse: source) */
+    double *variance;      /* adaptive plans only, else NULL */
+} dct_cuda_plane;
+
+const char *dct_cuda_last_error(void);
+int dct_cuda_device_count(void);
+
+/* Binds the contexts to GPU `device`.  The contexts must outlive the plan. */
+dct_cuda_plan *dct_cuda_plan_create(const DCTContext *dct, const QuantContext *quant, int device);
+/* Re-reads the tables after the caller edited quant->quant_matrix / dequant_matrix / adaptive. */
+int dct_cuda_plan_refresh(dct_cuda_plan *plan);
+void dct_cuda_plan_destroy(dct_cuda_plan *plan);
+int dct_cuda_plan_device(const dct_cuda_plan *plan);
+
+/* ---- device-resident planes: all data pointers are device pointers on the plan's GPU; the work
+ * is queued on `stream` (a cudaStream_t, NULL = default stream) and the call returns at once. ---- */
+int dct_cuda_fwd_quant_u8_dev(dct_cuda_plan *plan, const uint8_t *d_pixels, size_t pitch, int width,
+                              int height, int16_t *d_coef, int layout, double *d_variance, void *stream);
+int dct_cuda_dequant_idct_u8_dev(dct_cuda_plan *plan, const int16_t *d_coef, int width, int height,
+                                 int layout, const double *d_variance, uint8_t *d_pixels, size_t pitch,
+                                 void *stream);
+int dct_cuda_fwd_quant_planes_dev(const dct_cuda_plane *planes, int n_planes, int layout, void *stream);
+int dct_cuda_dequant_idct_planes_dev(const dct_cuda_plane *planes, int n_planes, int layout, void *stream);
+
+/* ---- host planes: pointers are host memory (pinned memory overlaps best).  The plane is cut into
+ * block-row strips that flow through a 3-deep H2D / kernel / D2H pipeline on the plan's own
+ * streams; the call returns when the result is in host memory.  `stats` may be NULL. ---- */
+int dct_cuda_fwd_quant_u8(dct_cuda_plan *plan, const uint8_t *pixels, size_t pitch, int width, int height,
+                          int16_t *coef, int layout, double *variance, dct_cuda_stats *stats);
+int dct_cuda_dequant_idct_u8(dct_cuda_plan *plan, const int16_t *coef, int width, int height, int layout,
+                             const double *variance, uint8_t *pixels, size_t pitch, dct_cuda_stats *stats);
+
+/* ---- several GPUs, one host plane: block-row ranges are dealt to the plans (one per GPU, same
+ * tables) and run concurrently, one host thread per GPU; no inter-GPU traffic. ---- */
+int dct_cuda_fwd_quant_u8_multi(dct_cuda_plan *const *plans, int n_plans, const uint8_t *pixels, size_t pitch,
+                                int width, int height, int16_t *coef, int layout, double *variance,
+                                dct_cuda_stats *stats);
+int dct_cuda_dequant_idct_u8_multi(dct_cuda_plan *const *plans, int n_plans, const int16_t *coef, int width,
+                                   int height, int layout, const double *variance, uint8_t *pixels,
+                                   size_t pitch, dct_cuda_stats *stats);
+
+/* Waits for the plan's queued work, returns the counters accumulated since the last fetch and
+ * clears them.  `stream` is the stream the *_dev calls were queued on. */
+int dct_cuda_stats_fetch(dct_cuda_plan *plan, dct_cuda_stats *stats, void *stream);
+
+/* ---- adapters for the untouched host consumer (src/entropy.c) ---- */
+/* widen one 128-byte record into a ragged 8x8 int block in NATURAL order */
+void dct_cuda_record_to_block(const int16_t *record, int layout, int **block);
+/* narrow a ragged 8x8 int block (NATURAL order) into a record of the given layout */
+void dct_cuda_block_to_record(int **block, int layout, int16_t *record);
+
+/* pinned host memory for the host-plane calls */
+void *dct_cuda_host_alloc(size_t bytes);
+void dct_cuda_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DCT_CUDA_H */

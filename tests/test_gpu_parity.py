@@ -1,0 +1,441 @@
+"""GPU parity tests (run with -m gpu on a B200): libdct_cuda, called through its C ABI, against
+the CPU oracle on identical seeded inputs and against the golden vectors captured from the
+reference.  Integer work is compared BIT-EXACT (quantised int16 coefficients, reconstructed u8
+pixels); the per-block fp64 calls are compared bit-exact too (tolerance 0 < the 1e-4 north_star
+allows).  Full BASELINE.json sizes are covered by direct comparison where the oracle finishes in
+seconds and by size-independent properties otherwise."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, unhex
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from dct_b200 import api as _api
+    assert _api.device_count() > 0, "no CUDA device: the GPU tests cannot run (and never fall back)"
+    return _api
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as _t
+    assert _t.cuda.is_available()
+    return _t
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+class Ctx:
+    """dct_init + quant_init + plan, released on exit (mirrors tests/test_entropy.c:283-287, :402-403)."""
+
+    def __init__(self, api, quality=50, adaptive=0, table=None, device=0):
+        self.api = api
+        self.d = api.dct_init(8)
+        self.q = api.quant_init(8, quality, adaptive)
+        if table is not None:
+            api.set_quant_table(self.q, table)
+        self.plan = api.Plan(self.d, self.q, device)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.plan.close()
+        self.api.dct_free(self.d)
+        self.api.quant_free(self.q)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-block drop-in calls
+# ---------------------------------------------------------------------------------------------
+def test_known_answer_block_through_the_dropin_calls(api, golden_blocks):
+    kat = golden_blocks["kat"]
+    blk = np.array(kat["pixels"], dtype=np.float64).reshape(8, 8) - 128.0
+    ctx = api.dct_init(8)
+    c = api.dct_forward(ctx, blk)
+    want = unhex(kat["coeffs"], (8, 8))
+    assert np.abs(c - want).max() <= 1e-4            # north_star tolerance
+    assert np.array_equal(bits(c), bits(want))       # and in fact bit-identical
+    assert np.array_equal(bits(api.dct_inverse(ctx, c)), bits(unhex(kat["roundtrip"], (8, 8))))
+    var = float.fromhex(kat["variance"])
+    for key, case in kat["cases"].items():
+        q, adaptive = (int(v) for v in key.split(":"))
+        qctx = api.quant_init(8, q, adaptive)
+        qc = api.quantize(qctx, c, var)
+        assert list(qc.ravel()) == case["quantized"], key
+        dq = api.dequantize(qctx, qc, var)
+        assert np.array_equal(bits(dq), bits(unhex(case["dequantized"], (8, 8)))), key
+        assert np.array_equal(bits(api.dct_inverse(ctx, dq)), bits(unhex(case["idct"], (8, 8)))), key
+        api.quant_free(qctx)
+    api.dct_free(ctx)
+
+
+@pytest.mark.parametrize("n", [4, 16])
+def test_generic_block_sizes_through_the_dropin_calls(api, golden_blocks, n):
+    k = golden_blocks["kat"][f"n{n}"]
+    ctx, qctx = api.dct_init(n), api.quant_init(n, 50, 0)
+    b = unhex(k["block"], (n, n))
+    c = api.dct_forward(ctx, b)
+    assert np.array_equal(bits(c), bits(unhex(k["coeffs"], (n, n))))
+    qc = api.quantize(qctx, c, 0.0)
+    assert list(qc.ravel()) == k["quantized"]
+    assert np.array_equal(bits(api.dequantize(qctx, qc, 0.0)), bits(unhex(k["dequantized"], (n, n))))
+    assert np.array_equal(bits(api.dct_inverse(ctx, c)), bits(unhex(k["idct"], (n, n))))
+    api.dct_free(ctx), api.quant_free(qctx)
+
+
+def test_dropin_calls_match_oracle_on_random_blocks(api, oracle):
+    rng = np.random.default_rng(5)
+    for n in (8, 32):
+        ctx, qctx = api.dct_init(n), api.quant_init(n, 73, 1)
+        Q = oracle.quant_table(73, n)
+        for _ in range(3):
+            b = rng.normal(0, 60, size=(n, n))
+            c = api.dct_forward(ctx, b)
+            assert np.array_equal(bits(c), bits(oracle.dct_forward(b)))
+            var = oracle.block_variance(b)
+            qc = api.quantize(qctx, c, var)
+            assert np.array_equal(qc, oracle.quantize(Q, c, 1, var))
+            assert np.array_equal(bits(api.dequantize(qctx, qc, var)), bits(oracle.dequantize(Q, qc, 1, var)))
+        api.dct_free(ctx), api.quant_free(qctx)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "dropin_test_dct")),
+                    reason="drop-in binaries not built (make -C oracle dropin, needs /root/reference)")
+@pytest.mark.parametrize("name", ["test_dct", "test_quantization", "test_entropy"])
+def test_reference_test_programs_link_against_libdct_cuda(name):
+    """The reference's own tests/*.c + its untouched utils.c / entropy.c, linked against
+    libdct_cuda instead of dct.o / quantization.o: stdout must be byte-identical."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "dropin_" + name)
+    out = subprocess.run([exe], capture_output=True, check=True, timeout=120).stdout
+    assert out == open(os.path.join(GOLDEN, f"ref_{name}.stdout"), "rb").read()
+
+
+# ---------------------------------------------------------------------------------------------
+# planes: golden fixtures and oracle comparisons
+# ---------------------------------------------------------------------------------------------
+def roundtrip_check(api, oracle, px, quality, adaptive, layout, table=None, nthreads=8, host=True):
+    """fwd + inv through libdct_cuda (host-plane API) vs the oracle; returns the stats."""
+    H, W = px.shape
+    Q = table if table is not None else oracle.quant_table(quality)
+    want_c, want_v, want_ties = oracle.fwd_quant_plane(px, Q, adaptive, layout, nthreads=nthreads)
+    want_p, _ = oracle.dequant_idct_plane(want_c, W, H, Q, adaptive, layout, want_v, nthreads=nthreads)
+    with Ctx(api, quality, adaptive, table) as cx:
+        out, st_f = cx.plan.fwd_quant(px, layout, want_stats=True)
+        got_c, got_v = out if adaptive else (out, None)
+        assert np.array_equal(got_c, want_c), f"coefficients differ in {np.count_nonzero(got_c != want_c)} places"
+        if adaptive:
+            assert np.array_equal(bits(got_v), bits(want_v))
+        got_p, st_i = cx.plan.dequant_idct(got_c, W, H, layout, got_v, want_stats=True)
+        assert np.array_equal(got_p, want_p), f"pixels differ in {np.count_nonzero(got_p != want_p)} places"
+    assert st_f["blocks"] == st_i["blocks"] == (H // 8) * (W // 8)
+    assert st_f["near_ties"] == want_ties      # every fp64 near-tie was inside the fp32 band
+    assert st_f["saturated"] == 0
+    return st_f, st_i
+
+
+def test_golden_planes(api, golden_planes):
+    for key in golden_planes["cases"]:
+        name, q, a = key.split("/")
+        quality, adaptive = int(q[1:]), int(a[1:])
+        px = golden_planes[f"{name}/px"]
+        H, W = px.shape
+        with Ctx(api, quality, adaptive) as cx:
+            out = cx.plan.fwd_quant(px, api.NATURAL)
+            coef, var = out if adaptive else (out, None)
+            assert np.array_equal(coef, golden_planes[key + "/coef"]), key
+            if adaptive:
+                assert np.array_equal(bits(var), bits(golden_planes[key + "/var"])), key
+            if key + "/coef_zz" in golden_planes:
+                oz = cx.plan.fwd_quant(px, api.ZIGZAG)
+                cz = oz[0] if adaptive else oz
+                assert np.array_equal(cz, golden_planes[key + "/coef_zz"]), key
+                rz = cx.plan.dequant_idct(cz, W, H, api.ZIGZAG, var)
+                assert np.array_equal(rz, golden_planes[key + "/rec"]), key
+            rec = cx.plan.dequant_idct(coef, W, H, api.NATURAL, var)
+            assert np.array_equal(rec, golden_planes[key + "/rec"]), key
+
+
+def test_config1_512x512_matches_reference_hashes(api, oracle, golden_blocks):
+    """BASELINE config 1 / SURVEY.md A.5: 512x512 U, q50, round trip; hashes measured on the reference."""
+    px = oracle.fill_xorshift(512, 512)
+    with Ctx(api, 50, 0) as cx:
+        coef, st = cx.plan.fwd_quant(px, want_stats=True)
+        rec = cx.plan.dequant_idct(coef, 512, 512)
+    assert f"{oracle.fnv_i16(coef):016x}" == golden_blocks["a5"]["coef_hash"]
+    assert f"{oracle.fnv_u8_blockorder(rec):016x}" == golden_blocks["a5"]["pixel_hash"]
+    assert st["near_ties"] == 94 and st["replayed_blocks"] >= 94 and st["replayed_blocks"] < 0.05 * 4096
+
+
+@pytest.mark.parametrize("quality", [1, 10, 25, 50, 75, 90, 95, 100])
+@pytest.mark.parametrize("adaptive", [0, 1])
+def test_quality_sweep_uniform_noise(api, oracle, quality, adaptive):
+    rng = np.random.default_rng(quality * 2 + adaptive)
+    px = rng.integers(0, 256, size=(256, 1000 // 8 * 8), dtype=np.uint8)
+    layout = (quality + adaptive) % 2
+    roundtrip_check(api, oracle, px, quality, adaptive, layout)
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (8, 264), (16, 8), (24, 2048 + 8), (1080, 1920), (40, 72)])
+def test_ragged_shapes(api, oracle, shape):
+    """blocks-per-row not a multiple of the 32-record warp tile, single block, tall and wide"""
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    px = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    roundtrip_check(api, oracle, px, 75, 0, api.NATURAL)
+    roundtrip_check(api, oracle, px, 50, 1, api.ZIGZAG)
+
+
+def test_smooth_and_adversarial_content(api, oracle, golden_planes):
+    smooth = oracle.fill_xorshift(256, 512, dist=1)
+    for q in (50, 90):
+        st_f, _ = roundtrip_check(api, oracle, smooth, q, 0, api.NATURAL)
+        roundtrip_check(api, oracle, smooth, q, 1, api.NATURAL)
+    H, W = 64, 512
+    flat0, flat255 = np.zeros((H, W), np.uint8), np.full((H, W), 255, np.uint8)
+    checker = ((np.indices((H, W)).sum(0) % 2) * 255).astype(np.uint8)
+    stripes = np.tile(np.array([0, 255] * (W // 2), np.uint8), (H, 1))
+    # every block has sum(px - 128) = 64 -> DC = 8.0 -> c/Q = 0.5 at q50: a plane of exact ties
+    ties = np.full((H, W), 128, np.uint8)
+    ties[::8, ::8] = 192
+    for px in (flat0, flat255, checker, stripes, ties, golden_planes["adv/px"]):
+        for q in (10, 50, 100):
+            roundtrip_check(api, oracle, np.ascontiguousarray(px), q, 0, api.NATURAL)
+            roundtrip_check(api, oracle, np.ascontiguousarray(px), q, 1, api.ZIGZAG)
+    st, _ = roundtrip_check(api, oracle, ties, 50, 0, api.NATURAL)
+    assert st["near_ties"] >= (H // 8) * (W // 8) and st["replayed_blocks"] == (H // 8) * (W // 8)
+
+
+def test_pitched_planes(api, oracle):
+    rng = np.random.default_rng(3)
+    big = rng.integers(0, 256, size=(128, 640), dtype=np.uint8)
+    px = big[:, 64:64 + 256]                      # pitch 640 > width 256, 8-byte aligned start
+    Q = oracle.quant_table(60)
+    want, _, _ = oracle.fwd_quant_plane(px, Q)
+    with Ctx(api, 60, 0) as cx:
+        got = cx.plan.fwd_quant(px)
+        assert np.array_equal(got, want)
+        out = np.zeros((128, 640), np.uint8)
+        view = out[:, 128:128 + 256]
+        cx.plan.dequant_idct(got, 256, 128, pixels_out=view)
+        wantp, _ = oracle.dequant_idct_plane(want, 256, 128, Q)
+        assert np.array_equal(view, wantp) and out[:, :128].max() == 0 and out[:, 384:].max() == 0
+
+
+def test_inverse_on_arbitrary_coefficients(api, oracle):
+    """K2's dynamic error bound must hold for records K1 never produced (decoder input is untrusted)."""
+    rng = np.random.default_rng(17)
+    W, H = 512, 128
+    nb = (W // 8) * (H // 8)
+    for quality, adaptive, span in [(50, 0, 2000), (50, 1, 300), (90, 1, 2000), (100, 0, 32767), (10, 1, 32767)]:
+        coef = rng.integers(-span, span + 1, size=(nb, 64)).astype(np.int16)
+        coef[rng.random((nb, 64)) < 0.7] = 0
+        coef[0, :] = 32767
+        coef[1, :] = -32768
+        var = rng.random(nb) * 3000.0
+        Q = oracle.quant_table(quality)
+        want, _ = oracle.dequant_idct_plane(coef, W, H, Q, adaptive, 0, var, nthreads=4)
+        with Ctx(api, quality, adaptive) as cx:
+            got = cx.plan.dequant_idct(coef, W, H, 0, var if adaptive else None)
+        assert np.array_equal(got, want), (quality, adaptive, span, np.count_nonzero(got != want))
+
+
+def test_custom_and_exotic_tables(api, oracle):
+    rng = np.random.default_rng(23)
+    px = rng.integers(0, 256, size=(64, 256), dtype=np.uint8)
+    chroma = np.full((8, 8), 99.0)                 # ITU-T T.81 Table K.2
+    chroma[:4, :4] = [[17, 18, 24, 47], [18, 21, 26, 66], [24, 26, 56, 99], [47, 66, 99, 99]]
+    roundtrip_check(api, oracle, px, 50, 0, 0, table=chroma)
+    roundtrip_check(api, oracle, px, 50, 1, 1, table=chroma * 0.37)
+    # entries below 1.0 leave the fast path's proven domain: everything replays, still exact
+    tiny = np.full((8, 8), 0.25)
+    tiny[0, 0] = 3.0
+    st, _ = roundtrip_check(api, oracle, px, 50, 1, 0, table=tiny)
+    assert st["replayed_blocks"] == st["blocks"]
+
+
+def test_plan_refresh_picks_up_edited_tables(api, oracle):
+    rng = np.random.default_rng(29)
+    px = rng.integers(0, 256, size=(32, 64), dtype=np.uint8)
+    with Ctx(api, 50, 0) as cx:
+        a = cx.plan.fwd_quant(px)
+        newQ = oracle.quant_table(20)
+        api.set_quant_table(cx.q, newQ)
+        cx.plan.refresh()
+        b = cx.plan.fwd_quant(px)
+        want, _, _ = oracle.fwd_quant_plane(px, newQ)
+        assert np.array_equal(b, want) and not np.array_equal(a, b)
+
+
+def test_bad_arguments_are_rejected(api, oracle, torch):
+    with Ctx(api) as cx:
+        with pytest.raises(api.DctCudaError, match="multiples of 8"):
+            cx.plan.fwd_quant(np.zeros((12, 16), np.uint8))
+        with pytest.raises(api.DctCudaError, match="pitch"):
+            cx.plan.fwd_quant_dev(torch.zeros((16, 44), dtype=torch.uint8, device="cuda")[:, :24])
+        with pytest.raises(api.DctCudaError, match="aligned"):
+            cx.plan.fwd_quant_dev(torch.zeros((16, 48), dtype=torch.uint8, device="cuda")[:, 4:28])
+        with pytest.raises(api.DctCudaError, match="layout"):
+            cx.plan.fwd_quant(np.zeros((16, 16), np.uint8), layout=7)
+        assert cx.plan.fwd_quant(np.zeros((0, 16), np.uint8)).shape == (0, 64)   # empty plane
+        # host planes may have any pitch and alignment: the copy re-packs them
+        odd = np.random.default_rng(1).integers(0, 256, (16, 45), dtype=np.uint8)[:, 3:27]
+        want, _, _ = oracle.fwd_quant_plane(np.ascontiguousarray(odd), oracle.quant_table(50))
+        assert np.array_equal(cx.plan.fwd_quant(odd), want)
+    d4 = api.dct_init(4)
+    q8 = api.quant_init(8, 50, 0)
+    with pytest.raises(api.DctCudaError, match="8x8 only"):
+        api.Plan(d4, q8)
+    api.dct_free(d4), api.quant_free(q8)
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident API, BASELINE sizes
+# ---------------------------------------------------------------------------------------------
+def test_device_api_equals_host_api(api, oracle, torch):
+    rng = np.random.default_rng(31)
+    px = rng.integers(0, 256, size=(720, 1280), dtype=np.uint8)
+    for adaptive in (0, 1):
+        with Ctx(api, 85, adaptive) as cx:
+            host = cx.plan.fwd_quant(px, api.ZIGZAG)
+            d_px = torch.from_numpy(px).cuda()
+            dev = cx.plan.fwd_quant_dev(d_px, api.ZIGZAG)
+            hc, hv = host if adaptive else (host, None)
+            dc, dv = dev if adaptive else (dev, None)
+            assert np.array_equal(dc.cpu().numpy(), hc)
+            rec = cx.plan.dequant_idct_dev(dc, 1280, 720, api.ZIGZAG, dv)
+            torch.cuda.synchronize()
+            want = cx.plan.dequant_idct(hc, 1280, 720, api.ZIGZAG, hv)
+            assert np.array_equal(rec.cpu().numpy(), want)
+            st = cx.plan.stats()
+            assert st["blocks"] == 2 * 90 * 160
+
+
+def test_config2_4k_frame(api, oracle):
+    """BASELINE config 2: 3840x2160, fwd DCT+quant and dequant+IDCT, full comparison."""
+    rng = np.random.default_rng(2160)
+    px = rng.integers(0, 256, size=(2160, 3840), dtype=np.uint8)
+    st_f, st_i = roundtrip_check(api, oracle, px, 50, 0, api.NATURAL)
+    assert st_f["replayed_blocks"] < 0.05 * st_f["blocks"]
+    assert st_i["replayed_blocks"] < 0.05 * st_i["blocks"]
+
+
+def test_config3_8k_420_frame(api, oracle, torch):
+    """BASELINE config 3: 7680x4320 luma + two 3840x2160 chroma planes, separate tables, one call."""
+    rng = np.random.default_rng(4320)
+    chroma = np.full((8, 8), 99.0)
+    chroma[:4, :4] = [[17, 18, 24, 47], [18, 21, 26, 66], [24, 26, 56, 99], [47, 66, 99, 99]]
+    # the reference's own scaling rule (src/quantization.c:55-73) applied to the chroma base table
+    Qc = np.clip(chroma * ((200.0 - 2 * 75) / 100.0), 1.0, 255.0)
+    Ql = oracle.quant_table(75)
+    shapes = [(4320, 7680), (2160, 3840), (2160, 3840)]
+    planes = [rng.integers(0, 256, size=s, dtype=np.uint8) for s in shapes]
+    with Ctx(api, 75, 0) as luma, Ctx(api, 75, 0, table=Qc) as chr_:
+        descs = (api.PlaneDesc * 3)()
+        d_px = [torch.from_numpy(p).cuda() for p in planes]
+        d_out = [torch.empty_like(t) for t in d_px]
+        d_coef = [torch.empty((s[0] // 8 * (s[1] // 8), 64), dtype=torch.int16, device="cuda") for s in shapes]
+        for i, (s, cx) in enumerate(zip(shapes, (luma, chr_, chr_))):
+            descs[i].plan = cx.plan._h
+            descs[i].pixels_in, descs[i].pixels_out = d_px[i].data_ptr(), d_out[i].data_ptr()
+            descs[i].pitch, descs[i].width, descs[i].height = s[1], s[1], s[0]
+            descs[i].coef, descs[i].variance = d_coef[i].data_ptr(), None
+        stream = torch.cuda.current_stream().cuda_stream
+        assert api._fwd_planes(descs, 3, api.NATURAL, stream) == 0
+        assert api._inv_planes(descs, 3, api.NATURAL, stream) == 0
+        torch.cuda.synchronize()
+        for i, (s, Q) in enumerate(zip(shapes, (Ql, Qc, Qc))):
+            want_c, _, _ = oracle.fwd_quant_plane(planes[i], Q, nthreads=8)
+            assert np.array_equal(d_coef[i].cpu().numpy(), want_c), i
+            want_p, _ = oracle.dequant_idct_plane(want_c, s[1], s[0], Q, nthreads=8)
+            assert np.array_equal(d_out[i].cpu().numpy(), want_p), i
+
+
+def test_config4_frame_batch_is_frame_independent(api, oracle, torch):
+    """BASELINE config 4 (shape only): a batch of 1920x1080 frames stored back to back is one tall
+    plane; the records of frame f equal those of frame f processed alone (what sharding by frame
+    relies on), and a sampled frame matches the oracle."""
+    n, H, W = 48, 1080, 1920
+    g = torch.Generator(device="cuda").manual_seed(4)
+    batch = torch.randint(0, 256, (n * H, W), dtype=torch.uint8, device="cuda", generator=g)
+    with Ctx(api, 50, 0) as cx:
+        coef = cx.plan.fwd_quant_dev(batch)
+        rec = cx.plan.dequant_idct_dev(coef, W, n * H)
+        nbf = (H // 8) * (W // 8)
+        for f in (0, 17, n - 1):
+            alone = cx.plan.fwd_quant_dev(batch[f * H:(f + 1) * H])
+            assert torch.equal(alone, coef[f * nbf:(f + 1) * nbf])
+        f = 29
+        px = batch[f * H:(f + 1) * H].cpu().numpy()
+        Q = oracle.quant_table(50)
+        want_c, _, _ = oracle.fwd_quant_plane(px, Q, nthreads=8)
+        assert np.array_equal(coef[f * nbf:(f + 1) * nbf].cpu().numpy(), want_c)
+        want_p, _ = oracle.dequant_idct_plane(want_c, W, H, Q, nthreads=8)
+        assert np.array_equal(rec[f * H:(f + 1) * H].cpu().numpy(), want_p)
+
+
+def test_config5_huge_plane_sampled_strips(api, oracle, torch):
+    """BASELINE config 5 (one GPU's share and more): a 65536-wide plane, 64-bit addressing; sampled
+    block-row strips against the oracle over a quality sweep, plus idempotence of the strips."""
+    W, H = 65536, 16384                      # 1 Gi pixels: crosses the 2^31-byte offsets
+    g = torch.Generator(device="cuda").manual_seed(5)
+    big = torch.randint(0, 256, (H, W), dtype=torch.uint8, device="cuda", generator=g)
+    bw = W // 8
+    rows = [0, 777, H // 8 - 1]
+    for quality in (10, 50, 95):
+        with Ctx(api, quality, 0) as cx:
+            coef = cx.plan.fwd_quant_dev(big)
+            rec = cx.plan.dequant_idct_dev(coef, W, H)
+            st = cx.plan.stats()
+            assert st["blocks"] == 2 * bw * (H // 8)
+            Q = oracle.quant_table(quality)
+            for r in rows:
+                strip = big[r * 8:(r + 1) * 8].cpu().numpy()
+                want_c, _, _ = oracle.fwd_quant_plane(strip, Q, nthreads=4)
+                got_c = coef[r * bw:(r + 1) * bw].cpu().numpy()
+                assert np.array_equal(got_c, want_c), (quality, r)
+                want_p, _ = oracle.dequant_idct_plane(want_c, W, 8, Q, nthreads=4)
+                assert np.array_equal(rec[r * 8:(r + 1) * 8].cpu().numpy(), want_p), (quality, r)
+            del coef, rec
+    del big
+    torch.cuda.empty_cache()
+
+
+def test_adaptive_round_trip_reconstructs(api, oracle):
+    """Property: with adaptive=1 (the one mode whose dequantize is mathematically right, SURVEY.md
+    S3) a high-quality round trip returns nearly the input; with adaptive=0 it is the reference's
+    flat grey (S2)."""
+    px = oracle.fill_xorshift(256, 256, dist=1)
+    with Ctx(api, 95, 1) as cx:
+        coef, var = cx.plan.fwd_quant(px)
+        rec = cx.plan.dequant_idct(coef, 256, 256, var=var)
+    err = rec.astype(np.int32) - px.astype(np.int32)
+    assert np.sqrt((err ** 2).mean()) < 2.0
+    with Ctx(api, 50, 0) as cx:
+        rec = cx.plan.dequant_idct(cx.plan.fwd_quant(px), 256, 256)
+    assert set(np.unique(rec)) <= {126, 127, 128, 129, 130}
+
+
+def test_multi_gpu_entry_point_with_available_devices(api, oracle):
+    n = min(api.device_count(), 8)
+    rng = np.random.default_rng(41)
+    px = rng.integers(0, 256, size=(1024, 1024), dtype=np.uint8)
+    ctxs = [Ctx(api, 50, 1, device=g) for g in range(n)]
+    try:
+        (coef, var), st = api.fwd_quant_multi([c.plan for c in ctxs], px, api.ZIGZAG)
+        Q = oracle.quant_table(50)
+        want_c, want_v, _ = oracle.fwd_quant_plane(px, Q, 1, api.ZIGZAG, nthreads=8)
+        assert np.array_equal(coef, want_c) and np.array_equal(bits(var), bits(want_v))
+        rec, _ = api.dequant_idct_multi([c.plan for c in ctxs], coef, 1024, 1024, api.ZIGZAG, var)
+        want_p, _ = oracle.dequant_idct_plane(want_c, 1024, 1024, Q, 1, api.ZIGZAG, want_v, nthreads=8)
+        assert np.array_equal(rec, want_p) and st["blocks"] == 128 * 128
+    finally:
+        for c in ctxs:
+            c.__exit__()
