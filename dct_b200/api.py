@@ -104,6 +104,9 @@ _fwd_multi = _sig("dct_cuda_fwd_quant_u8_multi", C.c_int, C.POINTER(C.c_void_p),
 _inv_multi = _sig("dct_cuda_dequant_idct_u8_multi", C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int,
                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Stats))
 _stats_fetch = _sig("dct_cuda_stats_fetch", C.c_int, C.c_void_p, C.POINTER(Stats), C.c_void_p)
+_profile = _sig("dct_cuda_plan_profile", C.c_int, C.c_void_p, C.c_int)
+_profile_fetch = _sig("dct_cuda_profile_fetch", C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                      C.POINTER(C.c_double), C.POINTER(C.c_int))
 _rec_to_block = _sig("dct_cuda_record_to_block", None, C.POINTER(C.c_int16), C.c_int, _PP_I)
 _block_to_rec = _sig("dct_cuda_block_to_record", None, _PP_I, C.c_int, C.POINTER(C.c_int16))
 _host_alloc = _sig("dct_cuda_host_alloc", C.c_void_p, C.c_size_t)
@@ -303,9 +306,13 @@ class Plan:
     def fwd_quant(self, pixels, layout=NATURAL, coef_out=None, var_out=None, want_stats=False):
         if _is_torch(pixels):
             return self.fwd_quant_dev(pixels, layout, coef_out, var_out)
-        assert pixels.dtype == np.uint8 and pixels.ndim == 2 and pixels.strides[1] == 1
+        assert pixels.dtype == np.uint8 and pixels.ndim == 2
         H, W = pixels.shape
         nb = (H // 8) * (W // 8)
+        if pixels.size == 0 and H % 8 == 0 and W % 8 == 0:   # empty plane: nothing to queue
+            out = (np.empty((0, 64), np.int16), np.empty(0)) if self.adaptive else np.empty((0, 64), np.int16)
+            return (out, Stats().as_dict()) if want_stats else out
+        assert pixels.strides[1] == 1
         coef = coef_out if coef_out is not None else np.empty((nb, 64), dtype=np.int16)
         var = var_out if var_out is not None else (np.empty(nb, dtype=np.float64) if self.adaptive else None)
         st = Stats()
@@ -355,6 +362,15 @@ class Plan:
                         px.data_ptr(), px.stride(0), _stream_ptr(stream)))
         return px
 
+    def profile(self, enable=True):
+        _check(_profile(self._h, int(enable)))
+
+    def profile_fetch(self):
+        """-> {fwd_ms, fwd_launches, inv_ms, inv_launches}: device time of the K1 / K2 launches alone."""
+        fm, im, fn, inn = C.c_double(), C.c_double(), C.c_int(), C.c_int()
+        _check(_profile_fetch(self._h, C.byref(fm), C.byref(fn), C.byref(im), C.byref(inn)))
+        return {"fwd_ms": fm.value, "fwd_launches": fn.value, "inv_ms": im.value, "inv_launches": inn.value}
+
     def stats(self, stream=None):
         st = Stats()
         _check(_stats_fetch(self._h, C.byref(st), _stream_ptr(stream)))
@@ -393,5 +409,6 @@ def exported_symbols():
             "dct_cuda_plan_refresh", "dct_cuda_plan_destroy", "dct_cuda_plan_device", "dct_cuda_fwd_quant_u8_dev",
             "dct_cuda_dequant_idct_u8_dev", "dct_cuda_fwd_quant_planes_dev", "dct_cuda_dequant_idct_planes_dev",
             "dct_cuda_fwd_quant_u8", "dct_cuda_dequant_idct_u8", "dct_cuda_fwd_quant_u8_multi",
-            "dct_cuda_dequant_idct_u8_multi", "dct_cuda_stats_fetch", "dct_cuda_record_to_block",
+            "dct_cuda_dequant_idct_u8_multi", "dct_cuda_stats_fetch", "dct_cuda_plan_profile",
+            "dct_cuda_profile_fetch", "dct_cuda_record_to_block",
             "dct_cuda_block_to_record", "dct_cuda_host_alloc", "dct_cuda_host_free"]

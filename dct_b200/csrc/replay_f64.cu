@@ -40,24 +40,24 @@ __device__ __forceinline__ double norm_variance(double variance)
     return fmin(1.0, fmax(0.1, __ddiv_rn(variance, 1000.0)));
 }
 
-constexpr int kBlocksPerCta = 4;   // 64 threads per 8x8 block
+constexpr int kReplayWarps = 8;   // one warp per 8x8 block, 8 independent warps per CTA
 
+// One warp replays one block: lane l owns elements l and l+32 (rows l/8 and l/8+4, column l%8).
+// Only __syncwarp() is needed, so the warps of a CTA never wait for each other and the long
+// dependent DMUL/DADD chains of different blocks overlap.
 template <bool FORWARD>
-__global__ void __launch_bounds__(64 * kBlocksPerCta) k_replay(const ReplayParams p)
+__global__ void __launch_bounds__(32 * kReplayWarps) k_replay(const ReplayParams p)
 {
     __shared__ double sD[64];
     __shared__ double sM[64];                     // quant matrix (fwd) / dequant matrix (inv)
-    __shared__ double sX[kBlocksPerCta][64];
-    __shared__ double sT[kBlocksPerCta][64];
-    __shared__ double sVar[kBlocksPerCta];
-    __shared__ unsigned long long sTies, sSat;
+    __shared__ double sX[kReplayWarps][64];
+    __shared__ double sT[kReplayWarps][64];
 
-    const int tid = threadIdx.x, sub = tid >> 6, e = tid & 63, i = e >> 3, j = e & 7;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     if (tid < 64) {
         sD[tid] = p.tab->D[tid];
         sM[tid] = FORWARD ? p.tab->Q[tid] : p.tab->R[tid];
     }
-    if (tid == 0) sTies = 0, sSat = 0;
     __syncthreads();
 
     unsigned count = p.nblocks;
@@ -65,106 +65,126 @@ __global__ void __launch_bounds__(64 * kBlocksPerCta) k_replay(const ReplayParam
         count = p.ctr->wl_count;
         if (count > p.wl_cap) count = p.wl_cap;
     }
-    const unsigned rounds = (count + kBlocksPerCta - 1) / kBlocksPerCta;
     unsigned ties = 0, sat = 0;
+    double *X = sX[w], *T = sT[w];
+    const int j = lane & 7, i0 = lane >> 3;
 
-    for (unsigned rnd = blockIdx.x; rnd < rounds; rnd += gridDim.x) {
-        const unsigned slot = rnd * kBlocksPerCta + sub;
-        const bool active = slot < count;
-        const unsigned b = active ? (p.worklist ? p.worklist[slot] : slot) : 0;
+    for (unsigned slot = blockIdx.x * kReplayWarps + w; slot < count; slot += gridDim.x * kReplayWarps) {
+        const unsigned b = p.worklist ? p.worklist[slot] : slot;
         const unsigned by = b / p.bw, bx = b - by * p.bw;
-        // position `e` of the record holds natural index nat (zigzag: src/entropy.c:158-178)
-        const int nat = p.layout == LAYOUT_ZIGZAG ? cZigZag.nat[e] : e;
+        double var = 0.0;
 
         if (FORWARD) {
-            // src/dct.c:115  (double)px - 128.0
-            const uint8_t px = p.px_in[((long long)by * 8 + i) * p.pitch + (long long)bx * 8 + j];
-            sX[sub][e] = __dsub_rn((double)px, 128.0);
-        } else {
-            const int q = active ? (int)p.coef_in[(size_t)b * 64 + e] : 0;
-            double m = sM[nat];
-            double val;
-            if (p.adaptive) {
-                const double var = p.var_in ? p.var_in[b] : 0.0;
-                if (nat != 0) m = __dmul_rn(m, __ddiv_rn(1.0, __dsub_rn(2.0, norm_variance(var))));
-                val = __dmul_rn((double)q, __ddiv_rn(1.0, m));
-            } else {
-                val = __dmul_rn((double)q, m);
+            int isum = 0, isq = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = i0 + 4 * h;
+                // src/dct.c:115  (double)px - 128.0
+                const int px = p.px_in[((long long)by * 8 + i) * p.pitch + (long long)bx * 8 + j];
+                X[i * 8 + j] = __dsub_rn((double)px, 128.0);
+                isum += px - 128;
+                isq += (px - 128) * (px - 128);
             }
-            sX[sub][nat] = val;
-        }
-        __syncthreads();
-
-        if (FORWARD) {
-            if (p.adaptive && e == 0) {
-                // src/quantization.c:153-169, sequential like the reference (all terms are exact integers)
-                double sum = 0.0, sum_sq = 0.0;
-                for (int k = 0; k < 64; ++k) {
-                    sum = __dadd_rn(sum, sX[sub][k]);
-                    sum_sq = __dadd_rn(sum_sq, __dmul_rn(sX[sub][k], sX[sub][k]));
+            if (p.adaptive) {
+                // src/quantization.c:153-169.  Every partial sum there is an exactly representable
+                // integer, so the summation order does not matter; the three fp64 ops below see the
+                // same operands as the reference's.
+                isum = __reduce_add_sync(0xffffffffu, isum);
+                isq = __reduce_add_sync(0xffffffffu, isq);
+                const double mean = __ddiv_rn((double)isum, 64.0);
+                var = __dsub_rn(__ddiv_rn((double)isq, 64.0), __dmul_rn(mean, mean));
+                if (lane == 0 && p.var_out) p.var_out[b] = var;
+            }
+        } else {
+            if (p.adaptive) var = p.var_in ? p.var_in[b] : 0.0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = lane + 32 * h;   // record position
+                // position e holds natural index nat (zigzag: src/entropy.c:183-210)
+                const int nat = p.layout == LAYOUT_ZIGZAG ? cZigZag.nat[e] : e;
+                const int q = (int)p.coef_in[(size_t)b * 64 + e];
+                double m = sM[nat];
+                double val;
+                if (p.adaptive) {
+                    if (nat != 0) m = __dmul_rn(m, __ddiv_rn(1.0, __dsub_rn(2.0, norm_variance(var))));
+                    val = __dmul_rn((double)q, __ddiv_rn(1.0, m));
+                } else {
+                    val = __dmul_rn((double)q, m);
                 }
-                const double mean = __ddiv_rn(sum, 64.0);
-                sVar[sub] = __dsub_rn(__ddiv_rn(sum_sq, 64.0), __dmul_rn(mean, mean));
+                X[nat] = val;
             }
-            double acc = 0.0;   // temp[i][j] = sum_k X[i][k] * D[j][k]
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(sX[sub][i * 8 + k], sD[j * 8 + k]));
-            sT[sub][e] = acc;
-        } else {
-            double acc = 0.0;   // temp[i][j] = sum_k D[k][i] * in[k][j]
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(sD[k * 8 + i], sX[sub][k * 8 + j]));
-            sT[sub][e] = acc;
         }
-        __syncthreads();
+        __syncwarp();
 
-        if (FORWARD) {
-            double acc = 0.0;   // out[i][j] = sum_k D[i][k] * temp[k][j]
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(sD[i * 8 + k], sT[sub][k * 8 + j]));
-            double m = sM[e];
-            if (p.adaptive) {
-                const double var = sVar[sub];
-                if (e != 0) {
+        for (int h = 0; h < 2; ++h) {
+            const int i = i0 + 4 * h;
+            double acc = 0.0;
+            if (FORWARD) {   // temp[i][j] = sum_k X[i][k] * D[j][k]
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(X[i * 8 + k], sD[j * 8 + k]));
+            } else {         // temp[i][j] = sum_k D[k][i] * in[k][j]
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(sD[k * 8 + i], X[k * 8 + j]));
+            }
+            T[i * 8 + j] = acc;
+        }
+        __syncwarp();
+
+        int qv[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = i0 + 4 * h, e = i * 8 + j;
+            double acc = 0.0;
+            if (FORWARD) {   // out[i][j] = sum_k D[i][k] * temp[k][j]
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(sD[i * 8 + k], T[k * 8 + j]));
+                double m = sM[e];
+                if (p.adaptive && e != 0) {
                     m = __dmul_rn(m, __dsub_rn(2.0, norm_variance(var)));
                     if (m < 1.0) m = 1.0;
                 }
-                if (e == 0 && active && p.var_out) p.var_out[b] = var;
-            }
-            const double y = __ddiv_rn(acc, m);
-            const double r = round_half_away(y);
-            int q = (int)r;
-            if (r > 32767.0) q = 32767, ++sat;
-            if (r < -32768.0) q = -32768, ++sat;
-            if (active) {
+                const double y = __ddiv_rn(acc, m);
+                const double r = round_half_away(y);
+                int q = (int)r;
+                if (r > 32767.0) q = 32767, ++sat;
+                if (r < -32768.0) q = -32768, ++sat;
                 ties += near_half(y);
-                sX[sub][e] = (double)q;   // own element only; re-read below by position
-            }
-        } else {
-            double acc = 0.0;   // out[i][j] = sum_k temp[i][k] * D[k][j]
+                qv[h] = q;
+            } else {         // out[i][j] = sum_k temp[i][k] * D[k][j]
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(sT[sub][i * 8 + k], sD[k * 8 + j]));
-            const double v = __dadd_rn(acc, 128.0);
-            double r = round_half_away(v);
-            r = r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r);
-            if (active) {
+                for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(T[i * 8 + k], sD[k * 8 + j]));
+                const double v = __dadd_rn(acc, 128.0);
+                double r = round_half_away(v);
+                r = r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r);
                 ties += near_half(v);
                 p.px_out[((long long)by * 8 + i) * p.pitch + (long long)bx * 8 + j] = (uint8_t)r;
             }
         }
-        __syncthreads();
-        if (FORWARD && active) p.coef_out[(size_t)b * 64 + e] = (int16_t)(int)sX[sub][nat];
-        __syncthreads();
+        if (FORWARD) {
+            // re-order through shared memory: record position e <- natural index nat
+            int *Xi = reinterpret_cast<int *>(X);
+            __syncwarp();
+            Xi[i0 * 8 + j] = qv[0];
+            Xi[(i0 + 4) * 8 + j] = qv[1];
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = lane + 32 * h;
+                const int nat = p.layout == LAYOUT_ZIGZAG ? cZigZag.nat[e] : e;
+                p.coef_out[(size_t)b * 64 + e] = (int16_t)Xi[nat];
+            }
+        }
+        __syncwarp();
     }
 
-    if (ties) atomicAdd(&sTies, (unsigned long long)ties);
-    if (sat) atomicAdd(&sSat, (unsigned long long)sat);
-    __syncthreads();
-    if (tid == 0) {
-        if (sTies) atomicAdd(&p.ctr->near_ties, sTies);
-        if (sSat) atomicAdd(&p.ctr->saturated, sSat);
-        if (blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
+    ties = __reduce_add_sync(0xffffffffu, ties);
+    sat = __reduce_add_sync(0xffffffffu, sat);
+    if (lane == 0) {
+        if (ties) atomicAdd(&p.ctr->near_ties, (unsigned long long)ties);
+        if (sat) atomicAdd(&p.ctr->saturated, (unsigned long long)sat);
     }
+    if (tid == 0 && blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
 }
 
 // ---- generic n x n single-block kernels (n <= 32): the per-block drop-in API -------------
@@ -223,21 +243,21 @@ __global__ void k_block_dequantize_f64(int n, const double *R, int adaptive, dou
 
 static unsigned replay_grid(const ReplayParams &p)
 {
-    // worklist mode: the count lives on the device; a fixed grid strides over it
-    if (p.worklist != nullptr) return 148 * 4;
-    const unsigned rounds = (p.nblocks + kBlocksPerCta - 1) / kBlocksPerCta;
-    return rounds < 148u * 8u ? (rounds ? rounds : 1u) : 148u * 8u;
+    // worklist mode: the count lives on the device; a fixed grid (8 CTAs per SM) strides over it
+    if (p.worklist != nullptr) return 148 * 8;
+    const unsigned ctas = (p.nblocks + kReplayWarps - 1) / kReplayWarps;
+    return ctas < 148u * 8u ? (ctas ? ctas : 1u) : 148u * 8u;
 }
 
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s)
 {
-    k_replay<true><<<replay_grid(p), 64 * kBlocksPerCta, 0, s>>>(p);
+    k_replay<true><<<replay_grid(p), 32 * kReplayWarps, 0, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s)
 {
-    k_replay<false><<<replay_grid(p), 64 * kBlocksPerCta, 0, s>>>(p);
+    k_replay<false><<<replay_grid(p), 32 * kReplayWarps, 0, s>>>(p);
     return cudaGetLastError();
 }
 

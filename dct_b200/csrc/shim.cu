@@ -79,6 +79,8 @@ struct Lane {
     double *d_var = nullptr;
     size_t cap_blocks = 0;
     uint64_t blocks = 0;                        // blocks queued since the last stats fetch
+    // optional per-kernel timing (dct_cuda_plan_profile): event pairs around K1 / K2 launches
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_fwd, ev_inv;
 };
 
 }  // namespace
@@ -95,6 +97,7 @@ struct dct_cuda_plan {
     float rs[64], gain[64], band_floor;         // K2
     Lane lane[kLanes];
     Counters *h_ctr = nullptr;                  // pinned, kLanes entries
+    bool profile = false;
 };
 
 namespace {
@@ -222,7 +225,17 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
         fp.ctr = ln.d_ctr;
         memcpy(fp.r, p->r, sizeof fp.r);
         memcpy(fp.thr, p->thr, sizeof fp.thr);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (p->profile) {
+            CU_TRY(cudaEventCreate(&e0));
+            CU_TRY(cudaEventCreate(&e1));
+            CU_TRY(cudaEventRecord(e0, s));
+        }
         CU_TRY(launch_fwd_quant_u8(fp, layout, p->adaptive, s));
+        if (p->profile) {
+            CU_TRY(cudaEventRecord(e1, s));
+            ln.ev_fwd.emplace_back(e0, e1);
+        }
         rp.worklist = ln.d_wl;
     }
     CU_TRY(launch_replay_fwd(rp, s));
@@ -269,7 +282,17 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
         memcpy(ip.rs, p->rs, sizeof ip.rs);
         memcpy(ip.gain, p->gain, sizeof ip.gain);
         ip.band_floor = p->band_floor;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (p->profile) {
+            CU_TRY(cudaEventCreate(&e0));
+            CU_TRY(cudaEventCreate(&e1));
+            CU_TRY(cudaEventRecord(e0, s));
+        }
         CU_TRY(launch_dequant_idct_u8(ip, layout, p->adaptive, s));
+        if (p->profile) {
+            CU_TRY(cudaEventRecord(e1, s));
+            ln.ev_inv.emplace_back(e0, e1);
+        }
         rp.worklist = ln.d_wl;
     }
     CU_TRY(launch_replay_inv(rp, s));
@@ -441,6 +464,42 @@ extern "C" int dct_cuda_stats_fetch(dct_cuda_plan *p, dct_cuda_stats *stats, voi
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     DeviceGuard g(p->device);
     return collect_stats(p, stats, (cudaStream_t)stream);
+}
+
+extern "C" int dct_cuda_plan_profile(dct_cuda_plan *p, int enable)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    p->profile = enable != 0;
+    return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_profile_fetch(dct_cuda_plan *p, double *fwd_ms, int *fwd_launches, double *inv_ms,
+                                      int *inv_launches)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    DeviceGuard g(p->device);
+    CU_TRY(cudaDeviceSynchronize());
+    double ms[2] = {0.0, 0.0};
+    int n[2] = {0, 0};
+    for (int l = 0; l < kLanes; ++l) {
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *lists[2] = {&p->lane[l].ev_fwd, &p->lane[l].ev_inv};
+        for (int d = 0; d < 2; ++d) {
+            for (auto &pr : *lists[d]) {
+                float t = 0.f;
+                CU_TRY(cudaEventElapsedTime(&t, pr.first, pr.second));
+                ms[d] += t;
+                ++n[d];
+                cudaEventDestroy(pr.first);
+                cudaEventDestroy(pr.second);
+            }
+            lists[d]->clear();
+        }
+    }
+    if (fwd_ms) *fwd_ms = ms[0];
+    if (fwd_launches) *fwd_launches = n[0];
+    if (inv_ms) *inv_ms = ms[1];
+    if (inv_launches) *inv_launches = n[1];
+    return DCT_CUDA_OK;
 }
 
 // ------------------------------------------------------------------------------------------

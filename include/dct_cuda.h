@@ -118,6 +118,13 @@ int dct_cuda_dequant_idct_u8_multi(dct_cuda_plan *const *plans, int n_plans, con
  * clears them.  `stream` is the stream the *_dev calls were queued on. */
 int dct_cuda_stats_fetch(dct_cuda_plan *plan, dct_cuda_stats *stats, void *stream);
 
+/* Optional per-kernel timing for benchmarks: while enabled, every K1 / K2 launch is bracketed by
+ * CUDA events on its stream; dct_cuda_profile_fetch() synchronises, returns the summed device
+ * time and the number of launches per direction, and clears the lists. */
+int dct_cuda_plan_profile(dct_cuda_plan *plan, int enable);
+int dct_cuda_profile_fetch(dct_cuda_plan *plan, double *fwd_ms, int *fwd_launches, double *inv_ms,
+                           int *inv_launches);
+
 /* ---- adapters for the untouched host consumer (src/entropy.c) ---- */
 /* widen one 128-byte record into a ragged 8x8 int block in NATURAL order */
 void dct_cuda_record_to_block(const int16_t *record, int layout, int **block);
