@@ -44,16 +44,12 @@ template <> struct Ops<double> {
 #define DCTB_C1082 1.08239220029239396880
 #define DCTB_C2613 2.61312592975275305571
 
-// x[k*S], k = 0..7, transformed in place.  out[k] = a_k * sqrt(8) * (orthonormal DCT-II)[k],
-// a_0 = 1, a_k = sqrt(2) cos(k pi / 16).
+// Everything after the first butterfly stage.  Inputs: s_ab = x_a + x_b, d_ab = x_a - x_b.
+// out[k*S] = a_k * sqrt(8) * (orthonormal DCT-II)[k],  a_0 = 1, a_k = sqrt(2) cos(k pi / 16).
 template <typename T, int S>
-__device__ __forceinline__ void fdct8(T *x)
+__device__ __forceinline__ void fdct8_tail(T *x, T s07, T s16, T s25, T s34, T d07, T d16, T d25, T d34)
 {
     using O = Ops<T>;
-    const T s07 = O::add(x[0 * S], x[7 * S]), d07 = O::sub(x[0 * S], x[7 * S]);
-    const T s16 = O::add(x[1 * S], x[6 * S]), d16 = O::sub(x[1 * S], x[6 * S]);
-    const T s25 = O::add(x[2 * S], x[5 * S]), d25 = O::sub(x[2 * S], x[5 * S]);
-    const T s34 = O::add(x[3 * S], x[4 * S]), d34 = O::sub(x[3 * S], x[4 * S]);
     const T e0 = O::add(s07, s34), e3 = O::sub(s07, s34);
     const T e1 = O::add(s16, s25), e2 = O::sub(s16, s25);
     x[0 * S] = O::add(e0, e1);
@@ -69,6 +65,18 @@ __device__ __forceinline__ void fdct8(T *x)
     x[3 * S] = O::sub(z13, z2);
     x[1 * S] = O::add(z11, z4);
     x[7 * S] = O::sub(z11, z4);
+}
+
+// x[k*S], k = 0..7, transformed in place (30 operations).
+template <typename T, int S>
+__device__ __forceinline__ void fdct8(T *x)
+{
+    using O = Ops<T>;
+    const T s07 = O::add(x[0 * S], x[7 * S]), d07 = O::sub(x[0 * S], x[7 * S]);
+    const T s16 = O::add(x[1 * S], x[6 * S]), d16 = O::sub(x[1 * S], x[6 * S]);
+    const T s25 = O::add(x[2 * S], x[5 * S]), d25 = O::sub(x[2 * S], x[5 * S]);
+    const T s34 = O::add(x[3 * S], x[4 * S]), d34 = O::sub(x[3 * S], x[4 * S]);
+    fdct8_tail<T, S>(x, s07, s16, s25, s34, d07, d16, d25, d34);
 }
 
 // v[k*S] pre-multiplied by a_k / sqrt(8); transformed in place to the 8 spatial samples.

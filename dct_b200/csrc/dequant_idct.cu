@@ -114,22 +114,28 @@ __global__ void __launch_bounds__(kThreads) k_dequant_idct_u8(const __grid_const
     const uint32_t by = bb / p.bw, bx = bb - by * p.bw;
     uint8_t *dst = p.px + (long long)by * 8 * p.pitch + (long long)bx * 8;
 
-    bool flag = false;
+    // t = x + (1.5*2^23 + 128): the low 16 mantissa bits of t are round(x) + 128 as an int16 (valid for
+    // |x| < 2^15 - 128, guaranteed below by the bound test); residual e = x - round(x) is exact.
+    // Clamp to [0, 255] on packed int16 pairs (VIMNMX.S16x2.RELU), then pack four bytes per word.
+    float emax = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        uint32_t tb[8];
+        uint32_t pr[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float x = fminf(fmaxf(v[8 * i + j], -128.0f), 127.0f);
-            const float t = __fadd_rn(x, kMagic128);            // low byte = round(x + 128)
-            const float e = __fsub_rn(x, __fsub_rn(t, kMagic128));   // x - round(x), exact
-            flag |= fabsf(e) >= thr;
-            tb[j] = __float_as_uint(t);
+        for (int h = 0; h < 4; ++h) {
+            const float x0 = v[8 * i + 2 * h], x1 = v[8 * i + 2 * h + 1];
+            const float t0 = __fadd_rn(x0, kMagic128), t1 = __fadd_rn(x1, kMagic128);
+            const float e0 = __fsub_rn(x0, __fsub_rn(t0, kMagic128)), e1 = __fsub_rn(x1, __fsub_rn(t1, kMagic128));
+            emax = fmaxf(fmaxf(emax, fabsf(e0)), fabsf(e1));                                   // FMNMX3
+            const uint32_t pair = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x5410);   // int16 x 2
+            asm("min.s16x2.relu %0, %1, %2;" : "=r"(pr[h]) : "r"(pair), "r"(0x00ff00ffu));
         }
-        const uint32_t lo = __byte_perm(__byte_perm(tb[0], tb[1], 0x0040), __byte_perm(tb[2], tb[3], 0x0040), 0x5410);
-        const uint32_t hi = __byte_perm(__byte_perm(tb[4], tb[5], 0x0040), __byte_perm(tb[6], tb[7], 0x0040), 0x5410);
+        const uint32_t lo = __byte_perm(pr[0], pr[1], 0x6420), hi = __byte_perm(pr[2], pr[3], 0x6420);
         if (valid) stg_stream_u2(dst + i * p.pitch, lo, hi);
     }
+    // |x| <= bound / 5 (every basis product is <= 1/4 and gain_k * prescale_k >= 1.25), so bound < 1.4e5
+    // keeps |x| far below 2^15; larger inputs go to the fp64 path
+    const bool flag = (emax >= thr) | !(bound < 1.4e5f);
 
     const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
     if (ballot != 0) {

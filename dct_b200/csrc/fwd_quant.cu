@@ -43,14 +43,33 @@ __device__ __forceinline__ void stg_stream_u4(void *p, const uint4 &v)
                  : "memory");
 }
 
-// byte `idx` of w -> float(byte) - 128, exactly: (0x4B000000 | byte) is 2^23 + byte
-template <int idx> __device__ __forceinline__ float byte_to_centered(uint32_t w)
+// byte `idx` of w -> 2^23 + byte as a float: (0x4B000000 | byte), one PRMT, no conversion instruction
+template <int idx> __device__ __forceinline__ float byte_to_magic(uint32_t w)
 {
-    const uint32_t m = __byte_perm(w, 0x4B000000u, 0x7440 + idx);
-    return __fadd_rn(__uint_as_float(m), -8388736.0f);   // -(2^23 + 128)
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + idx));
 }
 
-template <int LAYOUT, bool ADAPTIVE>
+// Row transform straight from the magic-biased bytes m_j = 2^23 + p_j.  The level shift and the
+// removal of the bias are folded into the first butterfly stage, every step exact:
+//   d = m_a - m_b                    = p_a - p_b
+//   s = (m_a - (2^24 + 256)) + m_b   = (p_a - 128) + (p_b - 128)      (|m_a - 2^24 - 256| < 2^24: exact)
+// i.e. the same integers the reference forms as (double)px - 128.0 (src/dct.c:115) summed pairwise.
+__device__ __forceinline__ void fdct8_row_from_bytes(float *x, uint2 raw)
+{
+    constexpr float kBias2 = 16777472.0f;   // 2 * (2^23 + 128)
+    const float m0 = byte_to_magic<0>(raw.x), m1 = byte_to_magic<1>(raw.x), m2 = byte_to_magic<2>(raw.x),
+                m3 = byte_to_magic<3>(raw.x), m4 = byte_to_magic<0>(raw.y), m5 = byte_to_magic<1>(raw.y),
+                m6 = byte_to_magic<2>(raw.y), m7 = byte_to_magic<3>(raw.y);
+    const float s07 = __fadd_rn(__fadd_rn(m0, -kBias2), m7), d07 = __fsub_rn(m0, m7);
+    const float s16 = __fadd_rn(__fadd_rn(m1, -kBias2), m6), d16 = __fsub_rn(m1, m6);
+    const float s25 = __fadd_rn(__fadd_rn(m2, -kBias2), m5), d25 = __fsub_rn(m2, m5);
+    const float s34 = __fadd_rn(__fadd_rn(m3, -kBias2), m4), d34 = __fsub_rn(m3, m4);
+    fdct8_tail<float, 1>(x, s07, s16, s25, s34, d07, d16, d25, d34);
+}
+
+// UNIFORM: one band for all 64 coefficients (the widest), tested with 3-input max -- half the
+// instructions of the per-coefficient compare; chosen by the host when the widest band is small.
+template <int LAYOUT, bool ADAPTIVE, bool UNIFORM>
 __global__ void __launch_bounds__(kThreads) k_fwd_quant_u8(const __grid_constant__ FwdParams p)
 {
     __shared__ uint4 stage[kWarps * kStageWordsPerWarp / 4];
@@ -68,31 +87,20 @@ __global__ void __launch_bounds__(kThreads) k_fwd_quant_u8(const __grid_constant
     for (int i = 0; i < 8; ++i) raw[i] = ldg_stream_u2(src + i * p.pitch);
 
     float v[64];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        v[8 * i + 0] = byte_to_centered<0>(raw[i].x);
-        v[8 * i + 1] = byte_to_centered<1>(raw[i].x);
-        v[8 * i + 2] = byte_to_centered<2>(raw[i].x);
-        v[8 * i + 3] = byte_to_centered<3>(raw[i].x);
-        v[8 * i + 4] = byte_to_centered<0>(raw[i].y);
-        v[8 * i + 5] = byte_to_centered<1>(raw[i].y);
-        v[8 * i + 6] = byte_to_centered<2>(raw[i].y);
-        v[8 * i + 7] = byte_to_centered<3>(raw[i].y);
-    }
-
     float inv_s = 1.0f;
     if constexpr (ADAPTIVE) {
-        // sum and sum of squares of the centred samples: integers below 2^24, exact in fp32
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        // Sum and sum of squares of the centred samples, as exact integers: packed byte dot products.
+        // 4096 * variance = 64 * sum(x^2) - sum(x)^2 is exact, so the side array equals
+        // calculate_block_variance (src/quantization.c:153-169) bit for bit.
+        int isum = 0, isq = 0;
 #pragma unroll
-        for (int k = 0; k < 64; k += 2) {
-            s0 = __fadd_rn(s0, v[k]);
-            s1 = __fadd_rn(s1, v[k + 1]);
-            q0 = __fmaf_rn(v[k], v[k], q0);
-            q1 = __fmaf_rn(v[k + 1], v[k + 1], q1);
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t wa = raw[i].x ^ 0x80808080u, wb = raw[i].y ^ 0x80808080u;   // p - 128 as int8
+            isum = __dp4a((int)wa, 0x01010101, isum);
+            isum = __dp4a((int)wb, 0x01010101, isum);
+            isq = __dp4a((int)wa, (int)wa, isq);
+            isq = __dp4a((int)wb, (int)wb, isq);
         }
-        const int isum = __float2int_rn(__fadd_rn(s0, s1));
-        const int isq = __float2int_rn(__fadd_rn(q0, q1));
         const int num = 64 * isq - isum * isum;   // 4096 * variance, exact (< 2^27)
         if (p.var_out != nullptr && valid) p.var_out[b] = (double)num * (1.0 / 4096.0);
         // s = 2 - clamp(var/1000, 0.1, 1)  (src/quantization.c:186-190), fp32 here, exact in K3
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(kThreads) k_fwd_quant_u8(const __grid_constant
 
     // rows (X * D^T), then columns (D * temp): same order as src/dct.c:57-74
 #pragma unroll
-    for (int i = 0; i < 8; ++i) fdct8<float, 1>(&v[8 * i]);
+    for (int i = 0; i < 8; ++i) fdct8_row_from_bytes(&v[8 * i], raw[i]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) fdct8<float, 8>(&v[j]);
 
@@ -110,6 +118,7 @@ __global__ void __launch_bounds__(kThreads) k_fwd_quant_u8(const __grid_constant
     // residual e = c*r - round(c*r) (one rounding); |e| >= 0.5 - band  => replay
     uint32_t w[32];
     bool flag = false;
+    float emax = 0.0f;
     static_for<0, 32>([&](auto M) {
         constexpr int m = decltype(M)::value;
         constexpr int k0 = storage_to_natural<LAYOUT>(2 * m), k1 = storage_to_natural<LAYOUT>(2 * m + 1);
@@ -121,9 +130,12 @@ __global__ void __launch_bounds__(kThreads) k_fwd_quant_u8(const __grid_constant
         const float t0 = __fmaf_rn(v[k0], r0, kMagic), t1 = __fmaf_rn(v[k1], r1, kMagic);
         const float e0 = __fmaf_rn(v[k0], r0, -__fsub_rn(t0, kMagic));
         const float e1 = __fmaf_rn(v[k1], r1, -__fsub_rn(t1, kMagic));
-        flag |= (fabsf(e0) >= p.thr[k0]) | (fabsf(e1) >= p.thr[k1]);
+        if constexpr (UNIFORM) emax = fmaxf(fmaxf(emax, fabsf(e0)), fabsf(e1));   // FMNMX3
+        else flag |= (fabsf(e0) >= p.thr[k0]) | (fabsf(e1) >= p.thr[k1]);
         w[m] = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x5410);   // lo16(t0) | lo16(t1) << 16
     });
+
+    if constexpr (UNIFORM) flag = emax >= p.thr_min;
 
     // stage: lane-major padded records in shared memory, then 512-byte contiguous warp stores
     uint32_t *wstage = reinterpret_cast<uint32_t *>(stage) + warp * kStageWordsPerWarp;
@@ -157,16 +169,22 @@ __global__ void __launch_bounds__(kThreads) k_fwd_quant_u8(const __grid_constant
 
 }  // namespace
 
+template <int LAYOUT, bool ADAPTIVE> static void launch_k1(const FwdParams &p, unsigned grid, cudaStream_t s)
+{
+    if (p.uniform_band) k_fwd_quant_u8<LAYOUT, ADAPTIVE, true><<<grid, kThreads, 0, s>>>(p);
+    else k_fwd_quant_u8<LAYOUT, ADAPTIVE, false><<<grid, kThreads, 0, s>>>(p);
+}
+
 cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s)
 {
     if (p.nblocks == 0) return cudaSuccess;
     const unsigned grid = (p.nblocks + kThreads - 1) / kThreads;
     if (layout == LAYOUT_ZIGZAG) {
-        if (adaptive) k_fwd_quant_u8<LAYOUT_ZIGZAG, true><<<grid, kThreads, 0, s>>>(p);
-        else          k_fwd_quant_u8<LAYOUT_ZIGZAG, false><<<grid, kThreads, 0, s>>>(p);
+        if (adaptive) launch_k1<LAYOUT_ZIGZAG, true>(p, grid, s);
+        else          launch_k1<LAYOUT_ZIGZAG, false>(p, grid, s);
     } else {
-        if (adaptive) k_fwd_quant_u8<LAYOUT_NATURAL, true><<<grid, kThreads, 0, s>>>(p);
-        else          k_fwd_quant_u8<LAYOUT_NATURAL, false><<<grid, kThreads, 0, s>>>(p);
+        if (adaptive) launch_k1<LAYOUT_NATURAL, true>(p, grid, s);
+        else          launch_k1<LAYOUT_NATURAL, false>(p, grid, s);
     }
     return cudaGetLastError();
 }

@@ -24,6 +24,12 @@ struct ExactTables {
     double D[64];   // dct_matrix, row-major
     double Q[64];   // quant_matrix
     double R[64];   // dequant_matrix
+    // derived, for phase 1 of the fp64 replay (K3): the fast butterfly in double precision
+    double rinv[64];    // 1 / (Q_k * 8 a_u a_v)
+    double band64[64];  // classification band of the fp64 butterfly's quantised value (incl. 1e-9 margin)
+    double mult64[64];  // dequantisation multiplier: R_k (non-adaptive) or 1/R_k (adaptive)
+    double pre64[64];   // a_u a_v / 8
+    double gain64[64];  // error gain of the inverse butterfly per unit |input|
 };
 
 // K1: forward DCT + quantise.  One thread per 8x8 block.
@@ -39,6 +45,8 @@ struct FwdParams {
     Counters *ctr;
     float r[64];           // natural index: 1 / (Q_k * 8 a_u a_v)
     float thr[64];         // natural index: 0.5 - band_k ; |residual| >= thr  => replay in fp64
+    float thr_min;         // min_k thr[k]: the single threshold of the uniform-band variant
+    int uniform_band;      // 1: test max_k |residual| >= thr_min (cheaper, slightly more replays)
 };
 
 // K2: dequantise + inverse DCT.  One thread per 8x8 block.

@@ -18,7 +18,16 @@ namespace dctb {
 
 namespace {
 
-__constant__ ZigZag cZigZag{};   // device copy of the scan order for run-time indexing
+// natural index -> zigzag position (inverse of the scan), for run-time indexing on the device
+struct ZigZagInv {
+    int pos[64];
+    constexpr ZigZagInv() : pos{}
+    {
+        ZigZag z{};
+        for (int p = 0; p < 64; ++p) pos[z.nat[p]] = p;
+    }
+};
+__constant__ ZigZagInv cZigZagInv{};
 
 // C99 round(): half away from zero.  (y - trunc(y)) is exact for |y| < 2^52.
 __device__ __forceinline__ double round_half_away(double y)
@@ -40,141 +49,169 @@ __device__ __forceinline__ double norm_variance(double variance)
     return fmin(1.0, fmax(0.1, __ddiv_rn(variance, 1000.0)));
 }
 
-constexpr int kReplayWarps = 8;   // one warp per 8x8 block, 8 independent warps per CTA
+constexpr int kReplayThreads = 256;                // 8 warps; a warp holds 4 blocks, 8 threads each
+constexpr double kMagic52 = 6755399441055744.0;    // 1.5 * 2^52: x + kMagic52 rounds x to an integer (RNE)
 
-// One warp replays one block: lane l owns elements l and l+32 (rows l/8 and l/8+4, column l%8).
-// Only __syncwarp() is needed, so the warps of a CTA never wait for each other and the long
-// dependent DMUL/DADD chains of different blocks overlap.
-template <bool FORWARD>
-__global__ void __launch_bounds__(32 * kReplayWarps) k_replay(const ReplayParams p)
+// K3 works on the flagged blocks only, 8 threads per block (thread r owns row r, then column r,
+// exchanged through a warp-private shared-memory tile), in two phases:
+//   1. the scaled butterfly of K1/K2 in fp64.  Its error is ~1e-11, so every value farther than
+//      band64 from a .5 boundary provably rounds like the reference's;
+//   2. the few that are not (mathematically exact ties) are recomputed one at a time
+//      in the reference's own operation order -- 64 + 8 non-contracted multiply-adds (each of the 8
+//      threads does one inner sum, one thread adds the 8 products in ascending order), true
+//      division, half-away rounding -- and patched into the output.
+
+__device__ __forceinline__ double shfl_double(double v, int src_lane)
 {
-    __shared__ double sD[64];
-    __shared__ double sM[64];                     // quant matrix (fwd) / dequant matrix (inv)
-    __shared__ double sX[kReplayWarps][64];
-    __shared__ double sT[kReplayWarps][64];
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src_lane),
+                            __shfl_sync(0xffffffffu, __double2loint(v), src_lane));
+}
 
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    if (tid < 64) {
-        sD[tid] = p.tab->D[tid];
-        sM[tid] = FORWARD ? p.tab->Q[tid] : p.tab->R[tid];
+// 64-bit OR across the 8 lanes of a group
+__device__ __forceinline__ unsigned long long group_or(unsigned long long m)
+{
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)m, d);
+        const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(m >> 32), d);
+        m |= ((unsigned long long)hi << 32) | lo;
+    }
+    return m;
+}
+
+__device__ __forceinline__ double byte_centered(uint2 raw, int m)
+{
+    const unsigned w = m < 4 ? raw.x : raw.y;
+    return __dsub_rn((double)((w >> (8 * (m & 3))) & 0xFFu), 128.0);   // src/dct.c:115
+}
+
+struct ReplayShared {
+    ExactTables tab;
+    double tile[kReplayThreads / 32][4][8][9];   // [warp][block][row][col + pad]
+};
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ReplayShared &sh = *reinterpret_cast<ReplayShared *>(smem_raw);
+    {
+        const double *src = reinterpret_cast<const double *>(p.tab);
+        double *dst = reinterpret_cast<double *>(&sh.tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(ExactTables) / sizeof(double)); i += kReplayThreads) dst[i] = src[i];
     }
     __syncthreads();
+    const ExactTables &tab = sh.tab;
 
     unsigned count = p.nblocks;
     if (p.worklist != nullptr) {
         count = p.ctr->wl_count;
         if (count > p.wl_cap) count = p.wl_cap;
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 3, r = lane & 7, gbase = lane & 24;
+    double(*T)[9] = sh.tile[warp][g];
     unsigned ties = 0, sat = 0;
-    double *X = sX[w], *T = sT[w];
-    const int j = lane & 7, i0 = lane >> 3;
+    const unsigned groups_per_grid = gridDim.x * (kReplayThreads / 8);
 
-    for (unsigned slot = blockIdx.x * kReplayWarps + w; slot < count; slot += gridDim.x * kReplayWarps) {
-        const unsigned b = p.worklist ? p.worklist[slot] : slot;
-        const unsigned by = b / p.bw, bx = b - by * p.bw;
-        double var = 0.0;
+    // Warp-uniform trip count so that the shuffles below always see the whole warp.  The worklist
+    // entry and the pixel row of the NEXT iteration are fetched before this iteration's arithmetic,
+    // which hides the two dependent global-memory latencies behind ~400 fp64 instructions.
+    auto fetch = [&](unsigned base_, bool &act_, unsigned &b_, uint2 &raw_) {
+        const unsigned slot = base_ + g;
+        act_ = slot < count;
+        b_ = act_ ? (p.worklist ? p.worklist[slot] : slot) : 0;
+        const unsigned by = b_ / p.bw, bx = b_ - by * p.bw;
+        raw_ = *reinterpret_cast<const uint2 *>(p.px_in + ((long long)by * 8 + r) * p.pitch + (long long)bx * 8);
+    };
+    unsigned base = (blockIdx.x * (kReplayThreads / 32) + warp) * 4;
+    bool active = false, active_n = false;
+    unsigned b = 0, b_n = 0;
+    uint2 raw = make_uint2(0, 0), raw_n = make_uint2(0, 0);
+    if (base < count) fetch(base, active, b, raw);
+    for (; base < count; base += groups_per_grid, active = active_n, b = b_n, raw = raw_n) {
+        if (base + groups_per_grid < count) fetch(base + groups_per_grid, active_n, b_n, raw_n);
 
-        if (FORWARD) {
-            int isum = 0, isq = 0;
+        // ---- phase 1: rows, then columns ---------------------------------------------------
+        double x[8];
+        int isum = 0, isq = 0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = i0 + 4 * h;
-                // src/dct.c:115  (double)px - 128.0
-                const int px = p.px_in[((long long)by * 8 + i) * p.pitch + (long long)bx * 8 + j];
-                X[i * 8 + j] = __dsub_rn((double)px, 128.0);
-                isum += px - 128;
-                isq += (px - 128) * (px - 128);
-            }
-            if (p.adaptive) {
-                // src/quantization.c:153-169.  Every partial sum there is an exactly representable
-                // integer, so the summation order does not matter; the three fp64 ops below see the
-                // same operands as the reference's.
-                isum = __reduce_add_sync(0xffffffffu, isum);
-                isq = __reduce_add_sync(0xffffffffu, isq);
-                const double mean = __ddiv_rn((double)isum, 64.0);
-                var = __dsub_rn(__ddiv_rn((double)isq, 64.0), __dmul_rn(mean, mean));
-                if (lane == 0 && p.var_out) p.var_out[b] = var;
-            }
-        } else {
-            if (p.adaptive) var = p.var_in ? p.var_in[b] : 0.0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int e = lane + 32 * h;   // record position
-                // position e holds natural index nat (zigzag: src/entropy.c:183-210)
-                const int nat = p.layout == LAYOUT_ZIGZAG ? cZigZag.nat[e] : e;
-                const int q = (int)p.coef_in[(size_t)b * 64 + e];
-                double m = sM[nat];
-                double val;
-                if (p.adaptive) {
-                    if (nat != 0) m = __dmul_rn(m, __ddiv_rn(1.0, __dsub_rn(2.0, norm_variance(var))));
-                    val = __dmul_rn((double)q, __ddiv_rn(1.0, m));
-                } else {
-                    val = __dmul_rn((double)q, m);
-                }
-                X[nat] = val;
-            }
+        for (int m = 0; m < 8; ++m) {
+            const int px = (int)(((m < 4 ? raw.x : raw.y) >> (8 * (m & 3))) & 0xFFu) - 128;
+            x[m] = (double)px;
+            isum += px;
+            isq += px * px;
         }
-        __syncwarp();
-
+        double scale = 1.0, inv_scale = 1.0;
+        if (p.adaptive) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int i = i0 + 4 * h;
-            double acc = 0.0;
-            if (FORWARD) {   // temp[i][j] = sum_k X[i][k] * D[j][k]
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(X[i * 8 + k], sD[j * 8 + k]));
-            } else {         // temp[i][j] = sum_k D[k][i] * in[k][j]
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(sD[k * 8 + i], X[k * 8 + j]));
+            for (int d = 1; d < 8; d <<= 1) {
+                isum += __shfl_xor_sync(0xffffffffu, isum, d);
+                isq += __shfl_xor_sync(0xffffffffu, isq, d);
             }
-            T[i * 8 + j] = acc;
+            // src/quantization.c:153-169: every partial sum there is an exact integer, so these three
+            // fp64 operations see the reference's operands
+            const double mean = __ddiv_rn((double)isum, 64.0);
+            const double var = __dsub_rn(__ddiv_rn((double)isq, 64.0), __dmul_rn(mean, mean));
+            if (r == 0 && active && p.var_out) p.var_out[b] = var;
+            scale = __dsub_rn(2.0, norm_variance(var));   // src/quantization.c:190
+            inv_scale = 1.0 / scale;
         }
+        fdct8<double, 1>(x);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) T[r][m] = x[m];
         __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = T[i][r];
+        __syncwarp();
+        fdct8<double, 1>(x);                              // x[u] = scaled coefficient (u, r)
 
-        int qv[2];
+        unsigned long long need = 0;
+        int16_t *rec16 = reinterpret_cast<int16_t *>(&T[0][0]);   // reuse the tile as a 64 x int16 record
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int i = i0 + 4 * h, e = i * 8 + j;
-            double acc = 0.0;
-            if (FORWARD) {   // out[i][j] = sum_k D[i][k] * temp[k][j]
+        for (int u = 0; u < 8; ++u) {
+            const int k = 8 * u + r;
+            double y = x[u] * tab.rinv[k];
+            if (k != 0) y *= inv_scale;
+            const double t = y + kMagic52, n = t - kMagic52;
+            const double band = tab.band64[k] + fabs(y) * 1e-15;
+            if (fabs(y - n) >= 0.5 - band || !(fabs(y) < 32000.0)) need |= 1ull << k;
+            const int pos = LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[k] : k;
+            rec16[pos] = (int16_t)__double2loint(t);
+        }
+        need = group_or(need);
+
+        // ---- phase 2: exact replay of single coefficients, cooperatively by the group ---------
+        while (__any_sync(0xffffffffu, need != 0)) {
+            const bool mine = need != 0;
+            const int k = mine ? __ffsll((long long)need) - 1 : 0;
+            need &= need - 1;
+            const int i = k >> 3, j = k & 7;
+            double temp = 0.0;   // temp[r][j] = sum_m X[r][m] * D[j][m]      (src/dct.c:57-64)
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(sD[i * 8 + k], T[k * 8 + j]));
-                double m = sM[e];
-                if (p.adaptive && e != 0) {
-                    m = __dmul_rn(m, __dsub_rn(2.0, norm_variance(var)));
-                    if (m < 1.0) m = 1.0;
+            for (int m = 0; m < 8; ++m) temp = __dadd_rn(temp, __dmul_rn(byte_centered(raw, m), tab.D[j * 8 + m]));
+            const double prod = __dmul_rn(tab.D[i * 8 + r], temp);
+            double out = 0.0;    // out[i][j] = sum_kk D[i][kk] * temp[kk][j]  (src/dct.c:67-74), kk ascending
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) out = __dadd_rn(out, shfl_double(prod, gbase + kk));
+            if (mine && r == 0 && active) {
+                double mq = tab.Q[k];
+                if (p.adaptive && k != 0) {
+                    mq = __dmul_rn(mq, scale);
+                    if (mq < 1.0) mq = 1.0;
                 }
-                const double y = __ddiv_rn(acc, m);
-                const double r = round_half_away(y);
-                int q = (int)r;
-                if (r > 32767.0) q = 32767, ++sat;
-                if (r < -32768.0) q = -32768, ++sat;
+                const double y = __ddiv_rn(out, mq);
+                const double rr = round_half_away(y);
+                int q = (int)rr;
+                if (rr > 32767.0) q = 32767, ++sat;
+                if (rr < -32768.0) q = -32768, ++sat;
                 ties += near_half(y);
-                qv[h] = q;
-            } else {         // out[i][j] = sum_k temp[i][k] * D[k][j]
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn(T[i * 8 + k], sD[k * 8 + j]));
-                const double v = __dadd_rn(acc, 128.0);
-                double r = round_half_away(v);
-                r = r < 0.0 ? 0.0 : (r > 255.0 ? 255.0 : r);
-                ties += near_half(v);
-                p.px_out[((long long)by * 8 + i) * p.pitch + (long long)bx * 8 + j] = (uint8_t)r;
+                const int pos = LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[k] : k;
+                rec16[pos] = (int16_t)q;
             }
         }
-        if (FORWARD) {
-            // re-order through shared memory: record position e <- natural index nat
-            int *Xi = reinterpret_cast<int *>(X);
-            __syncwarp();
-            Xi[i0 * 8 + j] = qv[0];
-            Xi[(i0 + 4) * 8 + j] = qv[1];
-            __syncwarp();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int e = lane + 32 * h;
-                const int nat = p.layout == LAYOUT_ZIGZAG ? cZigZag.nat[e] : e;
-                p.coef_out[(size_t)b * 64 + e] = (int16_t)Xi[nat];
-            }
-        }
+        __syncwarp();
+        if (active)
+            reinterpret_cast<uint4 *>(p.coef_out + (size_t)b * 64)[r] = reinterpret_cast<const uint4 *>(rec16)[r];
         __syncwarp();
     }
 
@@ -184,7 +221,139 @@ __global__ void __launch_bounds__(32 * kReplayWarps) k_replay(const ReplayParams
         if (ties) atomicAdd(&p.ctr->near_ties, (unsigned long long)ties);
         if (sat) atomicAdd(&p.ctr->saturated, (unsigned long long)sat);
     }
-    if (tid == 0 && blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
+}
+
+// the reference's dequantised value of natural index k (src/quantization.c:133-151)
+__device__ __forceinline__ double exact_dequant(const ExactTables &tab, int adaptive, double inv_two_minus_nv, int k, int q)
+{
+    double m = tab.R[k];
+    if (adaptive) {
+        if (k != 0) m = __dmul_rn(m, inv_two_minus_nv);
+        return __dmul_rn((double)q, __ddiv_rn(1.0, m));
+    }
+    return __dmul_rn((double)q, m);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kReplayThreads) k_replay_inv(const ReplayParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ReplayShared &sh = *reinterpret_cast<ReplayShared *>(smem_raw);
+    {
+        const double *src = reinterpret_cast<const double *>(p.tab);
+        double *dst = reinterpret_cast<double *>(&sh.tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(ExactTables) / sizeof(double)); i += kReplayThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    const ExactTables &tab = sh.tab;
+
+    unsigned count = p.nblocks;
+    if (p.worklist != nullptr) {
+        count = p.ctr->wl_count;
+        if (count > p.wl_cap) count = p.wl_cap;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 3, r = lane & 7, gbase = lane & 24;
+    double(*T)[9] = sh.tile[warp][g];
+    unsigned ties = 0;
+    const unsigned groups_per_grid = gridDim.x * (kReplayThreads / 8);
+
+    for (unsigned base = (blockIdx.x * (kReplayThreads / 32) + warp) * 4; base < count; base += groups_per_grid) {
+        const unsigned slot = base + g;
+        const bool active = slot < count;
+        const unsigned b = active ? (p.worklist ? p.worklist[slot] : slot) : 0;
+        const unsigned by = b / p.bw, bx = b - by * p.bw;
+        uint8_t *dst = p.px_out + (long long)by * 8 * p.pitch + (long long)bx * 8;
+
+        double two_minus_nv = 1.0, inv_two_minus_nv = 1.0;
+        if (p.adaptive) {
+            const double var = p.var_in ? p.var_in[b] : 0.0;
+            two_minus_nv = __dsub_rn(2.0, norm_variance(var));
+            inv_two_minus_nv = __ddiv_rn(1.0, two_minus_nv);   // src/quantization.c:193
+        }
+
+        // the record goes through the tile so that thread r can pick column r in any layout
+        int16_t *rec16 = reinterpret_cast<int16_t *>(&T[0][0]);
+        reinterpret_cast<uint4 *>(rec16)[r] = active ? reinterpret_cast<const uint4 *>(p.coef_in + (size_t)b * 64)[r]
+                                                     : make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        int q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = 8 * i + r;
+            q[i] = rec16[LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[k] : k];
+        }
+        __syncwarp();
+
+        // ---- phase 1: columns, then rows ---------------------------------------------------
+        double x[8];
+        double bound = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = 8 * i + r;
+            double dq = (double)q[i] * tab.mult64[k];     // a few ulps from the reference's reciprocal chain
+            if (k != 0) dq *= two_minus_nv;
+            x[i] = dq * tab.pre64[k];
+            bound = fma(fabs(x[i]), tab.gain64[k], bound);
+        }
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) bound += shfl_double(bound, lane ^ d);
+        idct8<double, 1>(x);                              // column r
+#pragma unroll
+        for (int i = 0; i < 8; ++i) T[i][r] = x[i];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = T[r][j];
+        __syncwarp();
+        idct8<double, 1>(x);                              // row r: x[j] = sample (r, j)
+
+        const double band = 2e-9 + bound * 1.25e-16;      // 1e-9 classification margin + 1.1 * 2^-53 * bound
+        unsigned long long need = 0;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double val = x[j] + 128.0;
+            const double t = val + kMagic52, n = t - kMagic52;
+            if (fabs(val - n) >= 0.5 - band || !(fabs(val) < 1e9)) need |= 1ull << (8 * r + j);
+            const uint32_t byte = (uint32_t)(int)fmin(fmax(n, 0.0), 255.0);
+            if (j < 4) lo |= byte << (8 * j);
+            else hi |= byte << (8 * (j - 4));
+        }
+        if (active) *reinterpret_cast<uint2 *>(dst + r * p.pitch) = make_uint2(lo, hi);
+        need = group_or(need);
+
+        // ---- phase 2: exact replay of single pixels ------------------------------------------
+        if (__any_sync(0xffffffffu, need != 0)) {
+            double in[8];                                 // exact dequantised column r
+#pragma unroll
+            for (int m = 0; m < 8; ++m) in[m] = exact_dequant(tab, p.adaptive, inv_two_minus_nv, 8 * m + r, q[m]);
+            while (__any_sync(0xffffffffu, need != 0)) {
+                const bool mine = need != 0;
+                const int e = mine ? __ffsll((long long)need) - 1 : 0;
+                need &= need - 1;
+                const int i = e >> 3, j = e & 7;
+                double temp = 0.0;   // temp[i][r] = sum_m D[m][i] * in[m][r]     (src/dct.c:85-92)
+#pragma unroll
+                for (int m = 0; m < 8; ++m) temp = __dadd_rn(temp, __dmul_rn(tab.D[m * 8 + i], in[m]));
+                const double prod = __dmul_rn(temp, tab.D[r * 8 + j]);
+                double out = 0.0;    // out[i][j] = sum_k temp[i][k] * D[k][j]  (src/dct.c:95-102), k ascending
+#pragma unroll
+                for (int k = 0; k < 8; ++k) out = __dadd_rn(out, shfl_double(prod, gbase + k));
+                if (mine && r == 0 && active) {
+                    const double val = __dadd_rn(out, 128.0);
+                    double rr = round_half_away(val);
+                    rr = rr < 0.0 ? 0.0 : (rr > 255.0 ? 255.0 : rr);
+                    ties += near_half(val);
+                    dst[i * p.pitch + j] = (uint8_t)rr;
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    ties = __reduce_add_sync(0xffffffffu, ties);
+    if (lane == 0 && ties) atomicAdd(&p.ctr->near_ties, (unsigned long long)ties);
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
 }
 
 // ---- generic n x n single-block kernels (n <= 32): the per-block drop-in API -------------
@@ -243,22 +412,28 @@ __global__ void k_block_dequantize_f64(int n, const double *R, int adaptive, dou
 
 static unsigned replay_grid(const ReplayParams &p)
 {
-    // worklist mode: the count lives on the device; a fixed grid (8 CTAs per SM) strides over it
-    if (p.worklist != nullptr) return 148 * 8;
-    const unsigned ctas = (p.nblocks + kReplayWarps - 1) / kReplayWarps;
+    // worklist mode: the count lives on the device; a fixed grid (4 CTAs per SM) strides over it
+    if (p.worklist != nullptr) return 148 * 4;
+    const unsigned ctas = (p.nblocks + kReplayThreads / 8 - 1) / (kReplayThreads / 8);
     return ctas < 148u * 8u ? (ctas ? ctas : 1u) : 148u * 8u;
+}
+
+template <typename K> static cudaError_t launch_replay(K kernel, const ReplayParams &p, cudaStream_t s)
+{
+    kernel<<<replay_grid(p), kReplayThreads, sizeof(ReplayShared), s>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s)
 {
-    k_replay<true><<<replay_grid(p), 32 * kReplayWarps, 0, s>>>(p);
-    return cudaGetLastError();
+    return p.layout == LAYOUT_ZIGZAG ? launch_replay(k_replay_fwd<LAYOUT_ZIGZAG>, p, s)
+                                     : launch_replay(k_replay_fwd<LAYOUT_NATURAL>, p, s);
 }
 
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s)
 {
-    k_replay<false><<<replay_grid(p), 32 * kReplayWarps, 0, s>>>(p);
-    return cudaGetLastError();
+    return p.layout == LAYOUT_ZIGZAG ? launch_replay(k_replay_inv<LAYOUT_ZIGZAG>, p, s)
+                                     : launch_replay(k_replay_inv<LAYOUT_NATURAL>, p, s);
 }
 
 cudaError_t launch_block_dct_f64(int n, const double *d_D, const double *d_in, double *d_out, int inverse,

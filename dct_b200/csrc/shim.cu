@@ -93,7 +93,8 @@ struct dct_cuda_plan {
     bool exotic = false;                        // tables outside the fast path's proven domain
     ExactTables h_tab;
     ExactTables *d_tab = nullptr;
-    float r[64], thr[64];                       // K1
+    float r[64], thr[64], thr_min;              // K1
+    int uniform_band;
     float rs[64], gain[64], band_floor;         // K2
     Lane lane[kLanes];
     Counters *h_ctr = nullptr;                  // pinned, kLanes entries
@@ -155,8 +156,24 @@ int read_tables(dct_cuda_plan *p)
         const double mult = p->adaptive ? 1.0 / R : R;
         p->rs[k] = (float)(mult * kInvPrescale[k]);
         p->gain[k] = exotic ? 1e30f : kInvGain[k] * 1.02f;
+        // phase 1 of K3 (fp64 butterfly): the fp32 bounds scale with the unit roundoff, 2^-53 / 2^-24 = 2^-29
+        const double b64 = ((double)kFwdBeta[k] * 1.1 + 16.0 * u * kFwdCmax[k]) * std::ldexp(1.0, -29) / Q;
+        p->h_tab.rinv[k] = 1.0 / (Q * kFwdScale[k]);
+        p->h_tab.band64[k] = (std::isfinite(b64) && b64 < 0.25) ? 2e-9 + b64 : 1.0;   // 1.0: always exact
+        // adjust_matrix_for_block floors Q*(2-nv) at 1.0 (src/quantization.c:203-205); phase 1 does not
+        // model that floor, so entries that could hit it always take the exact path
+        if (p->adaptive && k != 0 && !(Q >= 1.0)) p->h_tab.band64[k] = 1.0;
+        p->h_tab.mult64[k] = mult;
+        p->h_tab.pre64[k] = kInvPrescale[k];
+        p->h_tab.gain64[k] = (double)kInvGain[k] * 1.1;
     }
     p->band_floor = 1.0e-6f;
+    // One band for all coefficients costs half the instructions of 64 separate compares but replays
+    // a block whenever ANY coefficient is within the WIDEST band of a boundary: about
+    // 2 * 64 * max_band of all blocks.  Worth it while that stays below ~1 %.
+    p->thr_min = p->thr[0];
+    for (int k = 1; k < 64; ++k) p->thr_min = std::min(p->thr_min, p->thr[k]);
+    p->uniform_band = (!exotic && (0.5 - (double)p->thr_min) * 128.0 < 0.01) ? 1 : 0;
     return DCT_CUDA_OK;
 }
 
@@ -225,6 +242,8 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
         fp.ctr = ln.d_ctr;
         memcpy(fp.r, p->r, sizeof fp.r);
         memcpy(fp.thr, p->thr, sizeof fp.thr);
+        fp.thr_min = p->thr_min;
+        fp.uniform_band = p->uniform_band;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (p->profile) {
             CU_TRY(cudaEventCreate(&e0));
