@@ -7,14 +7,19 @@
 //   (src/entropy.c:158-178)
 // into one pass: each block is read once (64 B) and written once (128 B).
 //
-// Mapping: one thread owns one block; a warp owns 32 consecutive records, i.e. a 256-pixel
-// wide, 8-row tile.  A lane reads its 8-byte block rows with 8 independent LDG.64 (a warp
-// instruction covers 256 contiguous bytes), keeps the block in 64 registers through both
-// butterfly passes (no transpose, no shuffles), quantises with one FFMA per coefficient
-// (round-to-nearest via the 1.5*2^23 trick), checks the fp32 residual against the
-// per-coefficient band, and stores through a padded per-warp shared-memory stage so that
-// every STG.128 of the warp covers 512 contiguous bytes of the record array.
+// Mapping: one thread owns one block; a warp owns a TILE of 32 consecutive records, i.e. a
+// 256-pixel wide, 8-row strip.  The kernel is persistent (one CTA per SM slot, grid-stride over
+// tiles) and every warp runs its own two-stage cp.async pipeline, with no CTA-wide barrier:
+// while a warp transforms tile t, the 2 KB of tile t+1 are already in flight into its second
+// shared-memory stage (a warp LDGSTS instruction covers 256 contiguous bytes).  A lane keeps its
+// block in 64 registers through both butterfly passes (no transpose, no shuffles), quantises with
+// one FFMA per coefficient (round-to-nearest via the 1.5*2^23 trick), checks the fp32 residual
+// against the band, and stores through a padded per-warp stage so that every STG.128 of the warp
+// covers 512 contiguous bytes of the record array.
 // Blocks with a coefficient inside the band go to the worklist and are replayed in fp64 (K3).
+#include <cstdio>
+#include <cstdlib>
+
 #include "butterfly.cuh"
 #include "kernels.cuh"
 
@@ -29,12 +34,17 @@ constexpr int kStageWordsPerWarp = 32 * kStageWordsPerBlock;
 
 constexpr float kMagic = 12582912.0f;     // 1.5 * 2^23: x + kMagic rounds x to an integer (RNE)
 
-__device__ __forceinline__ uint2 ldg_stream_u2(const uint8_t *p)
+constexpr int kInStages = 2;                          // tiles in flight per warp
+constexpr int kInWordsPerStage = 8 * 64;              // 8 rows x 256 B
+constexpr int kSmemWordsPerWarp = kInStages * kInWordsPerStage + kStageWordsPerWarp;
+constexpr int kSmemBytes = kWarps * kSmemWordsPerWarp * 4;   // 69 632 B per CTA -> 3 CTAs per SM
+
+__device__ __forceinline__ void cp_async_8(uint32_t smem_addr, const void *gptr)
 {
-    uint2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void stg_stream_u4(void *p, const uint4 &v)
 {
@@ -70,21 +80,62 @@ __device__ __forceinline__ void fdct8_row_from_bytes(float *x, uint2 raw)
 // UNIFORM: one band for all 64 coefficients (the widest), tested with 3-input max -- half the
 // instructions of the per-coefficient compare; chosen by the host when the widest band is small.
 template <int LAYOUT, bool ADAPTIVE, bool UNIFORM>
-__global__ void __launch_bounds__(kThreads) k_fwd_quant_u8(const __grid_constant__ FwdParams p)
+__global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_constant__ FwdParams p)
 {
-    __shared__ uint4 stage[kWarps * kStageWordsPerWarp / 4];
-
+    extern __shared__ uint4 smem_dyn[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t warp_base = (blockIdx.x * kThreads + warp * 32);   // first record of this warp
+    uint32_t *wsm = reinterpret_cast<uint32_t *>(smem_dyn) + warp * kSmemWordsPerWarp;
+    uint32_t *wstage = wsm + kInStages * kInWordsPerStage;                       // output stage
+    const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(wsm) + lane * 8;   // + stage*2048 + row*256
+
+    const uint32_t ntiles = (p.nblocks + 31) >> 5;
+    const uint32_t tile_stride = gridDim.x * kWarps;
+    uint32_t tile = blockIdx.x * kWarps + warp;
+
+    // Each lane copies the 8 rows of its own block (lane-private data: no cross-lane hazard on the
+    // input).  The lane's block coordinates advance by a fixed step from tile to tile, so the only
+    // integer divisions of the kernel are the two below.
+    const uint32_t step = tile_stride * 32;                     // blocks between consecutive tiles of a warp
+    const uint32_t step_q = step / p.bw, step_r = step - step_q * p.bw;
+    const long long step_bytes = ((long long)step_q * p.pitch + step_r) * 8;
+    const long long wrap_bytes = (p.pitch - (long long)p.bw) * 8;   // bx -= bw, by += 1
+    uint32_t nb = tile * 32 + lane;                             // block the next issue() fetches
+    uint32_t nbx;
+    const uint8_t *nsrc;
+    {
+        const uint32_t by = nb / p.bw;
+        nbx = nb - by * p.bw;
+        nsrc = p.px + ((long long)by * p.pitch + nbx) * 8;
+    }
+    auto issue = [&](int stage) {
+        if (nb < p.nblocks) {   // lanes past the end keep stale (but valid u8) data and store nothing
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cp_async_8(in_addr + stage * (kInWordsPerStage * 4) + i * 256, nsrc + i * p.pitch);
+        }
+        cp_async_commit();
+        nb += step;
+        nbx += step_r;
+        nsrc += step_bytes;
+        if (nbx >= p.bw) nbx -= p.bw, nsrc += wrap_bytes;
+    };
+
+    int stage = 0;
+    if (tile < ntiles) issue(0);
+    for (; tile < ntiles; tile += tile_stride, stage ^= 1) {
+    if (tile + tile_stride < ntiles) {
+        issue(stage ^ 1);
+        cp_async_wait<1>();
+    } else {
+        cp_async_wait<0>();
+    }
+    const uint32_t warp_base = tile * 32;
     const uint32_t b = warp_base + lane;
     const bool valid = b < p.nblocks;
-    const uint32_t bb = valid ? b : p.nblocks - 1;
-    const uint32_t by = bb / p.bw, bx = bb - by * p.bw;
-    const uint8_t *src = p.px + (long long)by * 8 * p.pitch + (long long)bx * 8;
 
     uint2 raw[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) raw[i] = ldg_stream_u2(src + i * p.pitch);
+    for (int i = 0; i < 8; ++i)
+        raw[i] = *reinterpret_cast<const uint2 *>(wsm + stage * kInWordsPerStage + i * 64 + lane * 2);
 
     float v[64];
     float inv_s = 1.0f;
@@ -138,19 +189,23 @@ __global__ void __launch_bounds__(kThreads) k_fwd_quant_u8(const __grid_constant
     if constexpr (UNIFORM) flag = emax >= p.thr_min;
 
     // stage: lane-major padded records in shared memory, then 512-byte contiguous warp stores
-    uint32_t *wstage = reinterpret_cast<uint32_t *>(stage) + warp * kStageWordsPerWarp;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         *reinterpret_cast<uint4 *>(wstage + lane * kStageWordsPerBlock + 4 * j) =
             make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
     __syncwarp();
-    uint4 *dst = reinterpret_cast<uint4 *>(p.coef) + (size_t)warp_base * 8;
+    uint4 *dst = reinterpret_cast<uint4 *>(p.coef) + (size_t)warp_base * 8 + lane;
+    const uint32_t *rd = wstage + (lane >> 3) * kStageWordsPerBlock + 4 * (lane & 7);   // chunk c = j*32 + lane
+    const uint32_t full = p.nblocks - warp_base;      // records in this tile
+    if (full >= 32) {                                 // warp-uniform: every tile but possibly the last
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t c = j * 32 + lane;             // 16-byte chunk of the warp's 4 KB
-        const uint32_t blk = c >> 3, part = c & 7;
-        const uint4 val = *reinterpret_cast<const uint4 *>(wstage + blk * kStageWordsPerBlock + 4 * part);
-        if (warp_base + blk < p.nblocks) stg_stream_u4(dst + c, val);
+        for (int j = 0; j < 8; ++j)
+            stg_stream_u4(dst + j * 32, *reinterpret_cast<const uint4 *>(rd + j * 4 * kStageWordsPerBlock));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j * 4 + (lane >> 3) < full)
+                stg_stream_u4(dst + j * 32, *reinterpret_cast<const uint4 *>(rd + j * 4 * kStageWordsPerBlock));
     }
 
     // warp-aggregated append to the replay worklist
@@ -165,28 +220,58 @@ __global__ void __launch_bounds__(kThreads) k_fwd_quant_u8(const __grid_constant
             if (pos < p.wl_cap) p.worklist[pos] = b;
         }
     }
+    __syncwarp();   // the output stage is rewritten by the next tile
+    }   // tile loop
 }
 
 }  // namespace
 
-template <int LAYOUT, bool ADAPTIVE> static void launch_k1(const FwdParams &p, unsigned grid, cudaStream_t s)
+static int sm_count()
 {
-    if (p.uniform_band) k_fwd_quant_u8<LAYOUT, ADAPTIVE, true><<<grid, kThreads, 0, s>>>(p);
-    else k_fwd_quant_u8<LAYOUT, ADAPTIVE, false><<<grid, kThreads, 0, s>>>(p);
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+template <typename K> static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    const unsigned ntiles = (p.nblocks + 31) / 32;
+    const unsigned want = (ntiles + kWarps - 1) / kWarps;
+    static int per_sm = 0;   // resident CTAs per SM for this instantiation (3 by design: registers and shared memory)
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, kSmemBytes) != cudaSuccess || n < 1) n = 1;
+        per_sm = n;
+        if (getenv("DCT_CUDA_DEBUG")) fprintf(stderr, "libdct_cuda: %s: %d CTAs/SM, %d B smem\n", __FILE__, n, kSmemBytes);
+    }
+    const unsigned resident = (unsigned)sm_count() * (unsigned)per_sm;
+    kernel<<<want < resident ? want : resident, kThreads, kSmemBytes, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int LAYOUT, bool ADAPTIVE> static cudaError_t launch_k1(const FwdParams &p, cudaStream_t s)
+{
+    return p.uniform_band ? launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, true>, p, s)
+                          : launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, false>, p, s);
 }
 
 cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s)
 {
     if (p.nblocks == 0) return cudaSuccess;
-    const unsigned grid = (p.nblocks + kThreads - 1) / kThreads;
-    if (layout == LAYOUT_ZIGZAG) {
-        if (adaptive) launch_k1<LAYOUT_ZIGZAG, true>(p, grid, s);
-        else          launch_k1<LAYOUT_ZIGZAG, false>(p, grid, s);
-    } else {
-        if (adaptive) launch_k1<LAYOUT_NATURAL, true>(p, grid, s);
-        else          launch_k1<LAYOUT_NATURAL, false>(p, grid, s);
-    }
-    return cudaGetLastError();
+    if (layout == LAYOUT_ZIGZAG)
+        return adaptive ? launch_k1<LAYOUT_ZIGZAG, true>(p, s) : launch_k1<LAYOUT_ZIGZAG, false>(p, s);
+    return adaptive ? launch_k1<LAYOUT_NATURAL, true>(p, s) : launch_k1<LAYOUT_NATURAL, false>(p, s);
 }
 
 }  // namespace dctb
