@@ -99,6 +99,11 @@ _fwd_host = _sig("dct_cuda_fwd_quant_u8", C.c_int, C.c_void_p, C.c_void_p, C.c_s
                  C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Stats))
 _inv_host = _sig("dct_cuda_dequant_idct_u8", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                  C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Stats))
+_fwd_host_async = _sig("dct_cuda_fwd_quant_u8_async", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                       C.c_void_p, C.c_int, C.c_void_p)
+_inv_host_async = _sig("dct_cuda_dequant_idct_u8_async", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                       C.c_void_p, C.c_void_p, C.c_size_t)
+_plan_wait = _sig("dct_cuda_plan_wait", C.c_int, C.c_void_p, C.POINTER(Stats))
 _fwd_multi = _sig("dct_cuda_fwd_quant_u8_multi", C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t,
                   C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Stats))
 _inv_multi = _sig("dct_cuda_dequant_idct_u8_multi", C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int,
@@ -340,6 +345,18 @@ class Plan:
     def dequant_idct_ptr(self, coef_ptr, W, H, px_ptr, pitch, layout=NATURAL, var_ptr=None):
         _check(_inv_host(self._h, coef_ptr, W, H, layout, var_ptr, px_ptr, pitch, None))
 
+    # -- the same, asynchronous: returns at once; wait() blocks until the host buffers hold the result
+    def fwd_quant_ptr_async(self, px_ptr, pitch, W, H, coef_ptr, layout=NATURAL, var_ptr=None):
+        _check(_fwd_host_async(self._h, px_ptr, pitch, W, H, coef_ptr, layout, var_ptr))
+
+    def dequant_idct_ptr_async(self, coef_ptr, W, H, px_ptr, pitch, layout=NATURAL, var_ptr=None):
+        _check(_inv_host_async(self._h, coef_ptr, W, H, layout, var_ptr, px_ptr, pitch))
+
+    def wait(self, want_stats=False):
+        st = Stats()
+        _check(_plan_wait(self._h, C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
     # -- device tensors (torch, cuda): asynchronous on the current / given stream -----------
     def fwd_quant_dev(self, pixels, layout=NATURAL, coef_out=None, var_out=None, stream=None):
         import torch
@@ -408,7 +425,8 @@ def exported_symbols():
             "adjust_matrix_for_block", "dct_cuda_last_error", "dct_cuda_device_count", "dct_cuda_plan_create",
             "dct_cuda_plan_refresh", "dct_cuda_plan_destroy", "dct_cuda_plan_device", "dct_cuda_fwd_quant_u8_dev",
             "dct_cuda_dequant_idct_u8_dev", "dct_cuda_fwd_quant_planes_dev", "dct_cuda_dequant_idct_planes_dev",
-            "dct_cuda_fwd_quant_u8", "dct_cuda_dequant_idct_u8", "dct_cuda_fwd_quant_u8_multi",
+            "dct_cuda_fwd_quant_u8", "dct_cuda_dequant_idct_u8", "dct_cuda_fwd_quant_u8_async",
+            "dct_cuda_dequant_idct_u8_async", "dct_cuda_plan_wait", "dct_cuda_fwd_quant_u8_multi",
             "dct_cuda_dequant_idct_u8_multi", "dct_cuda_stats_fetch", "dct_cuda_plan_profile",
             "dct_cuda_profile_fetch", "dct_cuda_record_to_block",
             "dct_cuda_block_to_record", "dct_cuda_host_alloc", "dct_cuda_host_free"]

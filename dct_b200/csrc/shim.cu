@@ -535,8 +535,8 @@ static int strip_rows(int W, int H)
     return (int)std::min(rows, total);
 }
 
-extern "C" int dct_cuda_fwd_quant_u8(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H,
-                                     int16_t *coef, int layout, double *var, dct_cuda_stats *stats)
+extern "C" int dct_cuda_fwd_quant_u8_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H,
+                                           int16_t *coef, int layout, double *var)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     int rc = check_plane(px, coef, pitch, W, H, false);
@@ -560,13 +560,28 @@ extern "C" int dct_cuda_fwd_quant_u8(dct_cuda_plan *p, const uint8_t *px, size_t
                 CU_TRY(cudaMemcpyAsync(var + b0, ln.d_var, nb * sizeof(double), cudaMemcpyDeviceToHost, ln.stream));
         }
     }
+    return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_plan_wait(dct_cuda_plan *p, dct_cuda_stats *stats)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    DeviceGuard g(p->device);
     for (int l = 0; l < kLanes; ++l) CU_TRY(cudaStreamSynchronize(p->lane[l].stream));
     if (stats) return collect_stats(p, stats, nullptr);
     return DCT_CUDA_OK;
 }
 
-extern "C" int dct_cuda_dequant_idct_u8(dct_cuda_plan *p, const int16_t *coef, int W, int H, int layout,
-                                        const double *var, uint8_t *px, size_t pitch, dct_cuda_stats *stats)
+extern "C" int dct_cuda_fwd_quant_u8(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H,
+                                     int16_t *coef, int layout, double *var, dct_cuda_stats *stats)
+{
+    int rc = dct_cuda_fwd_quant_u8_async(p, px, pitch, W, H, coef, layout, var);
+    if (rc) return rc;
+    return dct_cuda_plan_wait(p, stats);
+}
+
+extern "C" int dct_cuda_dequant_idct_u8_async(dct_cuda_plan *p, const int16_t *coef, int W, int H, int layout,
+                                              const double *var, uint8_t *px, size_t pitch)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     int rc = check_plane(px, coef, pitch, W, H, false);
@@ -591,9 +606,15 @@ extern "C" int dct_cuda_dequant_idct_u8(dct_cuda_plan *p, const int16_t *coef, i
                                      cudaMemcpyDeviceToHost, ln.stream));
         }
     }
-    for (int l = 0; l < kLanes; ++l) CU_TRY(cudaStreamSynchronize(p->lane[l].stream));
-    if (stats) return collect_stats(p, stats, nullptr);
     return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_dequant_idct_u8(dct_cuda_plan *p, const int16_t *coef, int W, int H, int layout,
+                                        const double *var, uint8_t *px, size_t pitch, dct_cuda_stats *stats)
+{
+    int rc = dct_cuda_dequant_idct_u8_async(p, coef, W, H, layout, var, px, pitch);
+    if (rc) return rc;
+    return dct_cuda_plan_wait(p, stats);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -105,6 +105,16 @@ int dct_cuda_fwd_quant_u8(dct_cuda_plan *plan, const uint8_t *pixels, size_t pit
 int dct_cuda_dequant_idct_u8(dct_cuda_plan *plan, const int16_t *coef, int width, int height, int layout,
                              const double *variance, uint8_t *pixels, size_t pitch, dct_cuda_stats *stats);
 
+/* Asynchronous forms: queue the whole strip pipeline on the plan's own streams and return at once.
+ * The host buffers must be PINNED and stay untouched until dct_cuda_plan_wait(plan, stats) returns.
+ * Two plans (e.g. an encoder and a decoder) driven this way overlap each other's H2D and D2H
+ * traffic, which the synchronous calls cannot (forward is D2H-heavy, inverse is H2D-heavy). */
+int dct_cuda_fwd_quant_u8_async(dct_cuda_plan *plan, const uint8_t *pixels, size_t pitch, int width, int height,
+                                int16_t *coef, int layout, double *variance);
+int dct_cuda_dequant_idct_u8_async(dct_cuda_plan *plan, const int16_t *coef, int width, int height, int layout,
+                                   const double *variance, uint8_t *pixels, size_t pitch);
+int dct_cuda_plan_wait(dct_cuda_plan *plan, dct_cuda_stats *stats);
+
 /* ---- several GPUs, one host plane: block-row ranges are dealt to the plans (one per GPU, same
  * tables) and run concurrently, one host thread per GPU; no inter-GPU traffic. ---- */
 int dct_cuda_fwd_quant_u8_multi(dct_cuda_plan *const *plans, int n_plans, const uint8_t *pixels, size_t pitch,
