@@ -38,11 +38,14 @@ __device__ __forceinline__ void stg_stream_u2(void *p, uint32_t a, uint32_t b)
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
 
-// halves of a word of two int16 (already XORed with 0x8000 each) -> float(int16), exactly
-template <int hi> __device__ __forceinline__ float biased_half_to_float(uint32_t wx)
+// one int16 half of a packed word -> float, exactly: PRMT with sign replication widens it to int32,
+// then the full-width conversion (I2FP.F32.S32 runs at 64 lanes/clk/SM; the 16-bit form I2F.S16 at 16)
+template <int hi> __device__ __forceinline__ float half_to_float(uint32_t w)
 {
-    const uint32_t m = __byte_perm(wx, 0x4B000000u, hi ? 0x7432 : 0x7410);   // 2^23 + (q + 32768)
-    return __fadd_rn(__uint_as_float(m), -8421376.0f);                        // -(2^23 + 32768)
+    const uint32_t x = __byte_perm(w, 0u, hi ? 0xBB32 : 0x9910);
+    float f;
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(x));
+    return f;
 }
 
 template <int LAYOUT, bool ADAPTIVE>
@@ -59,10 +62,14 @@ __global__ void __launch_bounds__(kThreads) k_dequant_idct_u8(const __grid_const
     uint32_t *wstage = reinterpret_cast<uint32_t *>(stage) + warp * kStageWordsPerWarp;
     const uint4 *srcv = reinterpret_cast<const uint4 *>(p.coef) + (size_t)warp_base * 8;
     uint4 chunk[8];
+    const uint32_t full = warp_base < p.nblocks ? p.nblocks - warp_base : 0;   // records in this tile
+    if (full >= 32) {                                   // warp-uniform: every tile but possibly the last
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t c = j * 32 + lane;
-        chunk[j] = (warp_base + (c >> 3) < p.nblocks) ? ldg_stream_u4(srcv + c) : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < 8; ++j) chunk[j] = ldg_stream_u4(srcv + j * 32 + lane);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            chunk[j] = (j * 4 + (lane >> 3) < full) ? ldg_stream_u4(srcv + j * 32 + lane) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -90,8 +97,7 @@ __global__ void __launch_bounds__(kThreads) k_dequant_idct_u8(const __grid_const
     static_for<0, 32>([&](auto M) {
         constexpr int m = decltype(M)::value;
         constexpr int k0 = storage_to_natural<LAYOUT>(2 * m), k1 = storage_to_natural<LAYOUT>(2 * m + 1);
-        const uint32_t wx = w[m] ^ 0x80008000u;
-        float f0 = biased_half_to_float<0>(wx), f1 = biased_half_to_float<1>(wx);
+        float f0 = half_to_float<0>(w[m]), f1 = half_to_float<1>(w[m]);
         if constexpr (ADAPTIVE) {
             if (k0 != 0) f0 = __fmul_rn(f0, s);
             f1 = __fmul_rn(f1, s);
