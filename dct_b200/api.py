@@ -109,6 +109,7 @@ _fwd_multi = _sig("dct_cuda_fwd_quant_u8_multi", C.c_int, C.POINTER(C.c_void_p),
 _inv_multi = _sig("dct_cuda_dequant_idct_u8_multi", C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int,
                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Stats))
 _stats_fetch = _sig("dct_cuda_stats_fetch", C.c_int, C.c_void_p, C.POINTER(Stats), C.c_void_p)
+_skip_replay = _sig("dct_cuda_plan_debug_skip_replay", C.c_int, C.c_void_p, C.c_int)
 _profile = _sig("dct_cuda_plan_profile", C.c_int, C.c_void_p, C.c_int)
 _profile_fetch = _sig("dct_cuda_profile_fetch", C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int),
                       C.POINTER(C.c_double), C.POINTER(C.c_int))
@@ -379,6 +380,9 @@ class Plan:
                         px.data_ptr(), px.stride(0), _stream_ptr(stream)))
         return px
 
+    def debug_skip_replay(self, skip=True):
+        _check(_skip_replay(self._h, int(skip)))
+
     def profile(self, enable=True):
         _check(_profile(self._h, int(enable)))
 
@@ -427,6 +431,6 @@ def exported_symbols():
             "dct_cuda_dequant_idct_u8_dev", "dct_cuda_fwd_quant_planes_dev", "dct_cuda_dequant_idct_planes_dev",
             "dct_cuda_fwd_quant_u8", "dct_cuda_dequant_idct_u8", "dct_cuda_fwd_quant_u8_async",
             "dct_cuda_dequant_idct_u8_async", "dct_cuda_plan_wait", "dct_cuda_fwd_quant_u8_multi",
-            "dct_cuda_dequant_idct_u8_multi", "dct_cuda_stats_fetch", "dct_cuda_plan_profile",
+            "dct_cuda_dequant_idct_u8_multi", "dct_cuda_stats_fetch", "dct_cuda_plan_profile", "dct_cuda_plan_debug_skip_replay",
             "dct_cuda_profile_fetch", "dct_cuda_record_to_block",
             "dct_cuda_block_to_record", "dct_cuda_host_alloc", "dct_cuda_host_free"]

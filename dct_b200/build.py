@@ -23,7 +23,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CU_SOURCES = ["fwd_quant.cu", "dequant_idct.cu", "replay_f64.cu", "shim.cu"]
 C_SOURCES = ["host_context.c"]
-HEADERS = ["butterfly.cuh", "kernels.cuh", "band_tables.h"]
+HEADERS = ["butterfly.cuh", "fast_core.cuh", "kernels.cuh", "band_tables.h"]
 
 
 def _newer(target: str, deps: list[str]) -> bool:

@@ -10,7 +10,7 @@
 // with 512-byte contiguous LDG.128 through a padded shared-memory stage) and writes a
 // 256-pixel x 8-row tile with 8 STG.64 per lane (256 contiguous bytes per warp instruction).
 // The fp32 error bound is dynamic here (inputs are arbitrary int16): 2^-24 * sum gain_k |v_k|.
-#include "butterfly.cuh"
+#include "fast_core.cuh"
 #include "kernels.cuh"
 
 namespace dctb {
@@ -22,7 +22,6 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kStageWordsPerBlock = 36;
 constexpr int kStageWordsPerWarp = 32 * kStageWordsPerBlock;
 
-constexpr float kMagic128 = 12583040.0f;   // 1.5 * 2^23 + 128
 
 __device__ __forceinline__ uint4 ldg_stream_u4(const void *p)
 {
@@ -36,16 +35,6 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void *p)
 __device__ __forceinline__ void stg_stream_u2(void *p, uint32_t a, uint32_t b)
 {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
-}
-
-// one int16 half of a packed word -> float, exactly: PRMT with sign replication widens it to int32,
-// then the full-width conversion (I2FP.F32.S32 runs at 64 lanes/clk/SM; the 16-bit form I2F.S16 at 16)
-template <int hi> __device__ __forceinline__ float half_to_float(uint32_t w)
-{
-    const uint32_t x = __byte_perm(w, 0u, hi ? 0xBB32 : 0x9910);
-    float f;
-    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(x));
-    return f;
 }
 
 template <int LAYOUT, bool ADAPTIVE>
@@ -88,8 +77,7 @@ __global__ void __launch_bounds__(kThreads) k_dequant_idct_u8(const __grid_const
     if constexpr (ADAPTIVE) {
         // multiplier 1/((1/Q)*(1/(2-nv))) = Q*(2-nv) up to fp64 rounding; exact form in K3
         const double var = (p.var_in != nullptr && valid) ? p.var_in[b] : 0.0;
-        const float nv = fminf(1.0f, fmaxf(0.1f, __fmul_rn((float)var, 1.0f / 1000.0f)));
-        s = __fsub_rn(2.0f, nv);
+        s = adaptive_scale(var);
     }
 
     float v[64];
@@ -108,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) k_dequant_idct_u8(const __grid_const
         bound = __fmaf_rn(fabsf(v[k1]), p.gain[k1], bound);
     });
     // |fp32 pixel - exact pixel| <= 2^-24 * bound (derive_bands.py) ; + floor for the residual's own rounding
-    const float thr = __fsub_rn(0.5f, __fmaf_rn(bound, 5.9604645e-8f * 1.0625f, p.band_floor));
+    const float thr = pixel_threshold(bound, p.band_floor);
 
     // columns (D^T * in), then rows (temp * D): same order as src/dct.c:85-102
 #pragma unroll
@@ -130,8 +118,9 @@ __global__ void __launch_bounds__(kThreads) k_dequant_idct_u8(const __grid_const
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
             const float x0 = v[8 * i + 2 * h], x1 = v[8 * i + 2 * h + 1];
-            const float t0 = __fadd_rn(x0, kMagic128), t1 = __fadd_rn(x1, kMagic128);
-            const float e0 = __fsub_rn(x0, __fsub_rn(t0, kMagic128)), e1 = __fsub_rn(x1, __fsub_rn(t1, kMagic128));
+            float t0, t1, e0, e1;
+            pixel_residual(x0, t0, e0);
+            pixel_residual(x1, t1, e1);
             emax = fmaxf(fmaxf(emax, fabsf(e0)), fabsf(e1));                                   // FMNMX3
             const uint32_t pair = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x5410);   // int16 x 2
             asm("min.s16x2.relu %0, %1, %2;" : "=r"(pr[h]) : "r"(pair), "r"(0x00ff00ffu));

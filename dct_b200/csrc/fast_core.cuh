@@ -1,0 +1,97 @@
+// fast_core.cuh -- the fp32 building blocks shared by the fused kernels (K1/K2) and by K3's
+// re-flagging phase.  K3 must reproduce K1's / K2's fp32 values BIT FOR BIT (same operations in
+// the same order on the same inputs) to find out which single values fell inside the error band,
+// so both sides call these functions and nothing else.
+#pragma once
+#include <stdint.h>
+
+#include "butterfly.cuh"
+
+namespace dctb {
+
+constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: x + kMagic rounds x to an integer (RNE)
+constexpr float kMagic128 = 12583040.0f;   // 1.5 * 2^23 + 128
+
+// byte `idx` of w -> 2^23 + byte as a float: (0x4B000000 | byte), one PRMT, no conversion instruction
+template <int idx> __device__ __forceinline__ float byte_to_magic(uint32_t w)
+{
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + idx));
+}
+
+// Row transform straight from the magic-biased bytes m_j = 2^23 + p_j.  The level shift and the
+// removal of the bias are folded into the first butterfly stage, every step exact:
+//   d = m_a - m_b                    = p_a - p_b
+//   s = (m_a - (2^24 + 256)) + m_b   = (p_a - 128) + (p_b - 128)      (|m_a - 2^24 - 256| < 2^24: exact)
+// i.e. the same integers the reference forms as (double)px - 128.0 (src/dct.c:115) summed pairwise.
+__device__ __forceinline__ void fdct8_row_from_bytes(float *x, uint2 raw)
+{
+    constexpr float kBias2 = 16777472.0f;   // 2 * (2^23 + 128)
+    const float m0 = byte_to_magic<0>(raw.x), m1 = byte_to_magic<1>(raw.x), m2 = byte_to_magic<2>(raw.x),
+                m3 = byte_to_magic<3>(raw.x), m4 = byte_to_magic<0>(raw.y), m5 = byte_to_magic<1>(raw.y),
+                m6 = byte_to_magic<2>(raw.y), m7 = byte_to_magic<3>(raw.y);
+    const float s07 = __fadd_rn(__fadd_rn(m0, -kBias2), m7), d07 = __fsub_rn(m0, m7);
+    const float s16 = __fadd_rn(__fadd_rn(m1, -kBias2), m6), d16 = __fsub_rn(m1, m6);
+    const float s25 = __fadd_rn(__fadd_rn(m2, -kBias2), m5), d25 = __fsub_rn(m2, m5);
+    const float s34 = __fadd_rn(__fadd_rn(m3, -kBias2), m4), d34 = __fsub_rn(m3, m4);
+    fdct8_tail<float, 1>(x, s07, s16, s25, s34, d07, d16, d25, d34);
+}
+
+// sum and sum of squares of the centred samples of one 8-pixel row, exact (packed byte dot products)
+__device__ __forceinline__ void row_moments(uint2 raw, int &isum, int &isq)
+{
+    const uint32_t wa = raw.x ^ 0x80808080u, wb = raw.y ^ 0x80808080u;   // p - 128 as int8
+    isum = __dp4a((int)wa, 0x01010101, isum);
+    isum = __dp4a((int)wb, 0x01010101, isum);
+    isq = __dp4a((int)wa, (int)wa, isq);
+    isq = __dp4a((int)wb, (int)wb, isq);
+}
+
+// fast-path 1/(2 - nv) from num = 4096 * variance (src/quantization.c:186-190 in fp32; exact in K3)
+__device__ __forceinline__ float adaptive_inv_scale(int num)
+{
+    const float nv = fminf(1.0f, fmaxf(0.1f, __fmul_rn((float)num, 1.0f / 4096000.0f)));
+    return __frcp_rn(__fsub_rn(2.0f, nv));
+}
+
+// fast-path (2 - nv) for the decoder, from the variance side information
+__device__ __forceinline__ float adaptive_scale(double var)
+{
+    const float nv = fminf(1.0f, fmaxf(0.1f, __fmul_rn((float)var, 1.0f / 1000.0f)));
+    return __fsub_rn(2.0f, nv);
+}
+
+// quantise one coefficient: t holds round(c*r) in its low mantissa bits, e = c*r - round(c*r)
+__device__ __forceinline__ void quant_residual(float c, float r, float &t, float &e)
+{
+    t = __fmaf_rn(c, r, kMagic);
+    e = __fmaf_rn(c, r, -__fsub_rn(t, kMagic));
+}
+
+// one int16 half of a packed word -> float, exactly: PRMT with sign replication widens it to int32,
+// then the full-width conversion (I2FP.F32.S32 runs at 64 lanes/clk/SM; the 16-bit form I2F.S16 at 16)
+template <int hi> __device__ __forceinline__ float half_to_float(uint32_t w)
+{
+    // PTX prmt (not __byte_perm, which ignores bit 3 of a selector nibble): nibble 8|n replicates the
+    // sign bit of byte n, so {b0, b1, sign(b1), sign(b1)} is the sign-extended low half
+    uint32_t x;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(x) : "r"(w), "r"(0u), "r"(hi ? 0xBB32u : 0x9910u));
+    float f;
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(x));
+    return f;
+}
+
+// pixel from an inverse-transform sample: t holds round(x) + 128 in its low 16 mantissa bits, e = x - round(x)
+__device__ __forceinline__ void pixel_residual(float x, float &t, float &e)
+{
+    t = __fadd_rn(x, kMagic128);
+    e = __fsub_rn(x, __fsub_rn(t, kMagic128));
+}
+
+// K2's threshold from the accumulated bound: |fp32 pixel - exact pixel| <= 2^-24 * bound (derive_bands.py);
+// 1.0625 covers the rounding of the bound's own accumulation (any summation order)
+__device__ __forceinline__ float pixel_threshold(float bound, float band_floor)
+{
+    return __fsub_rn(0.5f, __fmaf_rn(bound, 5.9604645e-8f * 1.0625f, band_floor));
+}
+
+}  // namespace dctb

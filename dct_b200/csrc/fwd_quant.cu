@@ -20,7 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "butterfly.cuh"
+#include "fast_core.cuh"
 #include "kernels.cuh"
 
 namespace dctb {
@@ -32,7 +32,6 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kStageWordsPerBlock = 36;   // 128 B record + 16 B pad: conflict-free STS.128 / LDS.128
 constexpr int kStageWordsPerWarp = 32 * kStageWordsPerBlock;
 
-constexpr float kMagic = 12582912.0f;     // 1.5 * 2^23: x + kMagic rounds x to an integer (RNE)
 
 constexpr int kInStages = 2;                          // tiles in flight per warp
 constexpr int kInWordsPerStage = 8 * 64;              // 8 rows x 256 B
@@ -51,30 +50,6 @@ __device__ __forceinline__ void stg_stream_u4(void *p, const uint4 &v)
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
                  "r"(v.z), "r"(v.w)
                  : "memory");
-}
-
-// byte `idx` of w -> 2^23 + byte as a float: (0x4B000000 | byte), one PRMT, no conversion instruction
-template <int idx> __device__ __forceinline__ float byte_to_magic(uint32_t w)
-{
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + idx));
-}
-
-// Row transform straight from the magic-biased bytes m_j = 2^23 + p_j.  The level shift and the
-// removal of the bias are folded into the first butterfly stage, every step exact:
-//   d = m_a - m_b                    = p_a - p_b
-//   s = (m_a - (2^24 + 256)) + m_b   = (p_a - 128) + (p_b - 128)      (|m_a - 2^24 - 256| < 2^24: exact)
-// i.e. the same integers the reference forms as (double)px - 128.0 (src/dct.c:115) summed pairwise.
-__device__ __forceinline__ void fdct8_row_from_bytes(float *x, uint2 raw)
-{
-    constexpr float kBias2 = 16777472.0f;   // 2 * (2^23 + 128)
-    const float m0 = byte_to_magic<0>(raw.x), m1 = byte_to_magic<1>(raw.x), m2 = byte_to_magic<2>(raw.x),
-                m3 = byte_to_magic<3>(raw.x), m4 = byte_to_magic<0>(raw.y), m5 = byte_to_magic<1>(raw.y),
-                m6 = byte_to_magic<2>(raw.y), m7 = byte_to_magic<3>(raw.y);
-    const float s07 = __fadd_rn(__fadd_rn(m0, -kBias2), m7), d07 = __fsub_rn(m0, m7);
-    const float s16 = __fadd_rn(__fadd_rn(m1, -kBias2), m6), d16 = __fsub_rn(m1, m6);
-    const float s25 = __fadd_rn(__fadd_rn(m2, -kBias2), m5), d25 = __fsub_rn(m2, m5);
-    const float s34 = __fadd_rn(__fadd_rn(m3, -kBias2), m4), d34 = __fsub_rn(m3, m4);
-    fdct8_tail<float, 1>(x, s07, s16, s25, s34, d07, d16, d25, d34);
 }
 
 // UNIFORM: one band for all 64 coefficients (the widest), tested with 3-input max -- half the
@@ -145,18 +120,11 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
         // calculate_block_variance (src/quantization.c:153-169) bit for bit.
         int isum = 0, isq = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t wa = raw[i].x ^ 0x80808080u, wb = raw[i].y ^ 0x80808080u;   // p - 128 as int8
-            isum = __dp4a((int)wa, 0x01010101, isum);
-            isum = __dp4a((int)wb, 0x01010101, isum);
-            isq = __dp4a((int)wa, (int)wa, isq);
-            isq = __dp4a((int)wb, (int)wb, isq);
-        }
+        for (int i = 0; i < 8; ++i) row_moments(raw[i], isum, isq);
         const int num = 64 * isq - isum * isum;   // 4096 * variance, exact (< 2^27)
         if (p.var_out != nullptr && valid) p.var_out[b] = (double)num * (1.0 / 4096.0);
         // s = 2 - clamp(var/1000, 0.1, 1)  (src/quantization.c:186-190), fp32 here, exact in K3
-        const float nv = fminf(1.0f, fmaxf(0.1f, __fmul_rn((float)num, 1.0f / 4096000.0f)));
-        inv_s = __frcp_rn(__fsub_rn(2.0f, nv));
+        inv_s = adaptive_inv_scale(num);
     }
 
     // rows (X * D^T), then columns (D * temp): same order as src/dct.c:57-74
@@ -178,9 +146,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
             if (k0 != 0) r0 = __fmul_rn(r0, inv_s);   // DC keeps the unscaled table entry
             r1 = __fmul_rn(r1, inv_s);
         }
-        const float t0 = __fmaf_rn(v[k0], r0, kMagic), t1 = __fmaf_rn(v[k1], r1, kMagic);
-        const float e0 = __fmaf_rn(v[k0], r0, -__fsub_rn(t0, kMagic));
-        const float e1 = __fmaf_rn(v[k1], r1, -__fsub_rn(t1, kMagic));
+        float t0, t1, e0, e1;
+        quant_residual(v[k0], r0, t0, e0);
+        quant_residual(v[k1], r1, t1, e1);
         if constexpr (UNIFORM) emax = fmaxf(fmaxf(emax, fabsf(e0)), fabsf(e1));   // FMNMX3
         else flag |= (fabsf(e0) >= p.thr[k0]) | (fabsf(e1) >= p.thr[k1]);
         w[m] = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x5410);   // lo16(t0) | lo16(t1) << 16

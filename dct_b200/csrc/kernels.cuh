@@ -24,12 +24,13 @@ struct ExactTables {
     double D[64];   // dct_matrix, row-major
     double Q[64];   // quant_matrix
     double R[64];   // dequant_matrix
-    // derived, for phase 1 of the fp64 replay (K3): the fast butterfly in double precision
-    double rinv[64];    // 1 / (Q_k * 8 a_u a_v)
-    double band64[64];  // classification band of the fp64 butterfly's quantised value (incl. 1e-9 margin)
-    double mult64[64];  // dequantisation multiplier: R_k (non-adaptive) or 1/R_k (adaptive)
-    double pre64[64];   // a_u a_v / 8
-    double gain64[64];  // error gain of the inverse butterfly per unit |input|
+    // the fused kernels' fp32 tables, so that K3 can repeat their arithmetic bit for bit
+    float r32[64];      // K1: 1 / (Q_k * 8 a_u a_v)
+    float thr32[64];    // K1: 0.5 - band_k
+    float rs32[64];     // K2: dequantisation multiplier * a_u a_v / 8
+    float gain32[64];   // K2: error gain per unit |input|
+    float band_floor;   // K2
+    float pad_;
 };
 
 // K1: forward DCT + quantise.  One thread per 8x8 block.

@@ -11,7 +11,7 @@
 // and non-contracted __dmul_rn/__dadd_rn/__ddiv_rn, so the integers are bit-identical to
 // the reference's, exact ties included.  The same code, generalised to n x n, backs the
 // per-block drop-in entry points dct_forward/dct_inverse/quantize/dequantize.
-#include "butterfly.cuh"
+#include "fast_core.cuh"
 #include "kernels.cuh"
 
 namespace dctb {
@@ -50,16 +50,18 @@ __device__ __forceinline__ double norm_variance(double variance)
 }
 
 constexpr int kReplayThreads = 256;                // 8 warps; a warp holds 4 blocks, 8 threads each
-constexpr double kMagic52 = 6755399441055744.0;    // 1.5 * 2^52: x + kMagic52 rounds x to an integer (RNE)
 
-// K3 works on the flagged blocks only, 8 threads per block (thread r owns row r, then column r,
+// K3 visits the flagged blocks only, 8 threads per block (thread r owns row r, then column r,
 // exchanged through a warp-private shared-memory tile), in two phases:
-//   1. the scaled butterfly of K1/K2 in fp64.  Its error is ~1e-11, so every value farther than
-//      band64 from a .5 boundary provably rounds like the reference's;
-//   2. the few that are not (mathematically exact ties) are recomputed one at a time
-//      in the reference's own operation order -- 64 + 8 non-contracted multiply-adds (each of the 8
-//      threads does one inner sum, one thread adds the 8 products in ascending order), true
-//      division, half-away rounding -- and patched into the output.
+//   1. RE-FLAG: repeat K1's / K2's fp32 arithmetic bit for bit (same functions from fast_core.cuh,
+//      same inputs) to find WHICH values of the block sit inside the error band.  Everything else
+//      in the block was already written correctly by K1 / K2 and is left alone.
+//   2. REPLAY each such value -- typically one per block, a mathematically exact tie (SURVEY.md
+//      S6) -- in the reference's own operation order: 64 + 8 non-contracted fp64 multiply-adds
+//      (each of the 8 threads does one inner sum, one thread adds the 8 products in ascending
+//      order), true division, half-away rounding; patch it into the output.
+// With worklist == null (tables outside the fast path's domain; K1/K2 skipped) every value of
+// every block is replayed.
 
 __device__ __forceinline__ double shfl_double(double v, int src_lane)
 {
@@ -87,7 +89,7 @@ __device__ __forceinline__ double byte_centered(uint2 raw, int m)
 
 struct ReplayShared {
     ExactTables tab;
-    double tile[kReplayThreads / 32][4][8][9];   // [warp][block][row][col + pad]
+    alignas(16) float tile[kReplayThreads / 32][4][8][9];   // [warp][block][row][col + pad]; 288 B per block
 };
 
 template <int LAYOUT>
@@ -96,9 +98,9 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ReplayShared &sh = *reinterpret_cast<ReplayShared *>(smem_raw);
     {
-        const double *src = reinterpret_cast<const double *>(p.tab);
-        double *dst = reinterpret_cast<double *>(&sh.tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(ExactTables) / sizeof(double)); i += kReplayThreads) dst[i] = src[i];
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.tab);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(ExactTables) / 4); i += kReplayThreads) dst[i] = src[i];
     }
     __syncthreads();
     const ExactTables &tab = sh.tab;
@@ -108,14 +110,14 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
         count = p.ctr->wl_count;
         if (count > p.wl_cap) count = p.wl_cap;
     }
+    const bool replay_all = p.worklist == nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 3, r = lane & 7, gbase = lane & 24;
-    double(*T)[9] = sh.tile[warp][g];
+    float(*T)[9] = sh.tile[warp][g];
     unsigned ties = 0, sat = 0;
     const unsigned groups_per_grid = gridDim.x * (kReplayThreads / 8);
 
     // Warp-uniform trip count so that the shuffles below always see the whole warp.  The worklist
-    // entry and the pixel row of the NEXT iteration are fetched before this iteration's arithmetic,
-    // which hides the two dependent global-memory latencies behind ~400 fp64 instructions.
+    // entry and the pixel row of the NEXT iteration are fetched before this iteration's arithmetic.
     auto fetch = [&](unsigned base_, bool &act_, unsigned &b_, uint2 &raw_) {
         const unsigned slot = base_ + g;
         act_ = slot < count;
@@ -131,18 +133,12 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
     for (; base < count; base += groups_per_grid, active = active_n, b = b_n, raw = raw_n) {
         if (base + groups_per_grid < count) fetch(base + groups_per_grid, active_n, b_n, raw_n);
 
-        // ---- phase 1: rows, then columns ---------------------------------------------------
-        double x[8];
-        int isum = 0, isq = 0;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int px = (int)(((m < 4 ? raw.x : raw.y) >> (8 * (m & 3))) & 0xFFu) - 128;
-            x[m] = (double)px;
-            isum += px;
-            isq += px * px;
-        }
-        double scale = 1.0, inv_scale = 1.0;
+        // per-block variance (adaptive): exact integers, reduced over the 8 rows
+        double scale = 1.0;
+        float inv_s = 1.0f;
         if (p.adaptive) {
+            int isum = 0, isq = 0;
+            row_moments(raw, isum, isq);
 #pragma unroll
             for (int d = 1; d < 8; d <<= 1) {
                 isum += __shfl_xor_sync(0xffffffffu, isum, d);
@@ -154,31 +150,33 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
             const double var = __dsub_rn(__ddiv_rn((double)isq, 64.0), __dmul_rn(mean, mean));
             if (r == 0 && active && p.var_out) p.var_out[b] = var;
             scale = __dsub_rn(2.0, norm_variance(var));   // src/quantization.c:190
-            inv_scale = 1.0 / scale;
+            inv_s = adaptive_inv_scale(64 * isq - isum * isum);
         }
-        fdct8<double, 1>(x);
-#pragma unroll
-        for (int m = 0; m < 8; ++m) T[r][m] = x[m];
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = T[i][r];
-        __syncwarp();
-        fdct8<double, 1>(x);                              // x[u] = scaled coefficient (u, r)
 
-        unsigned long long need = 0;
-        int16_t *rec16 = reinterpret_cast<int16_t *>(&T[0][0]);   // reuse the tile as a 64 x int16 record
+        // ---- phase 1: K1's fp32 arithmetic again (rows, then columns), to find the flagged coefficients
+        unsigned long long need = ~0ull;
+        if (!replay_all) {
+            float x[8];
+            fdct8_row_from_bytes(x, raw);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int k = 8 * u + r;
-            double y = x[u] * tab.rinv[k];
-            if (k != 0) y *= inv_scale;
-            const double t = y + kMagic52, n = t - kMagic52;
-            const double band = tab.band64[k] + fabs(y) * 1e-15;
-            if (fabs(y - n) >= 0.5 - band || !(fabs(y) < 32000.0)) need |= 1ull << k;
-            const int pos = LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[k] : k;
-            rec16[pos] = (int16_t)__double2loint(t);
+            for (int m = 0; m < 8; ++m) T[r][m] = x[m];
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = T[i][r];
+            __syncwarp();
+            fdct8<float, 1>(x);                           // x[u] = scaled coefficient (u, r)
+            need = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = 8 * u + r;
+                float rk = tab.r32[k];
+                if (p.adaptive && k != 0) rk = __fmul_rn(rk, inv_s);
+                float t, e;
+                quant_residual(x[u], rk, t, e);
+                if (fabsf(e) >= tab.thr32[k]) need |= 1ull << k;
+            }
+            need = group_or(need);
         }
-        need = group_or(need);
 
         // ---- phase 2: exact replay of single coefficients, cooperatively by the group ---------
         while (__any_sync(0xffffffffu, need != 0)) {
@@ -206,13 +204,9 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
                 if (rr < -32768.0) q = -32768, ++sat;
                 ties += near_half(y);
                 const int pos = LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[k] : k;
-                rec16[pos] = (int16_t)q;
+                p.coef_out[(size_t)b * 64 + pos] = (int16_t)q;
             }
         }
-        __syncwarp();
-        if (active)
-            reinterpret_cast<uint4 *>(p.coef_out + (size_t)b * 64)[r] = reinterpret_cast<const uint4 *>(rec16)[r];
-        __syncwarp();
     }
 
     ties = __reduce_add_sync(0xffffffffu, ties);
@@ -236,14 +230,14 @@ __device__ __forceinline__ double exact_dequant(const ExactTables &tab, int adap
 }
 
 template <int LAYOUT>
-__global__ void __launch_bounds__(kReplayThreads) k_replay_inv(const ReplayParams p)
+__global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ReplayShared &sh = *reinterpret_cast<ReplayShared *>(smem_raw);
     {
-        const double *src = reinterpret_cast<const double *>(p.tab);
-        double *dst = reinterpret_cast<double *>(&sh.tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(ExactTables) / sizeof(double)); i += kReplayThreads) dst[i] = src[i];
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.tab);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(ExactTables) / 4); i += kReplayThreads) dst[i] = src[i];
     }
     __syncthreads();
     const ExactTables &tab = sh.tab;
@@ -253,8 +247,9 @@ __global__ void __launch_bounds__(kReplayThreads) k_replay_inv(const ReplayParam
         count = p.ctr->wl_count;
         if (count > p.wl_cap) count = p.wl_cap;
     }
+    const bool replay_all = p.worklist == nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 3, r = lane & 7, gbase = lane & 24;
-    double(*T)[9] = sh.tile[warp][g];
+    float(*T)[9] = sh.tile[warp][g];
     unsigned ties = 0;
     const unsigned groups_per_grid = gridDim.x * (kReplayThreads / 8);
 
@@ -265,11 +260,12 @@ __global__ void __launch_bounds__(kReplayThreads) k_replay_inv(const ReplayParam
         const unsigned by = b / p.bw, bx = b - by * p.bw;
         uint8_t *dst = p.px_out + (long long)by * 8 * p.pitch + (long long)bx * 8;
 
-        double two_minus_nv = 1.0, inv_two_minus_nv = 1.0;
+        double inv_two_minus_nv = 1.0;
+        float s32 = 1.0f;
         if (p.adaptive) {
             const double var = p.var_in ? p.var_in[b] : 0.0;
-            two_minus_nv = __dsub_rn(2.0, norm_variance(var));
-            inv_two_minus_nv = __ddiv_rn(1.0, two_minus_nv);   // src/quantization.c:193
+            inv_two_minus_nv = __ddiv_rn(1.0, __dsub_rn(2.0, norm_variance(var)));   // src/quantization.c:193
+            s32 = adaptive_scale(var);
         }
 
         // the record goes through the tile so that thread r can pick column r in any layout
@@ -285,42 +281,47 @@ __global__ void __launch_bounds__(kReplayThreads) k_replay_inv(const ReplayParam
         }
         __syncwarp();
 
-        // ---- phase 1: columns, then rows ---------------------------------------------------
-        double x[8];
-        double bound = 0.0;
+        // ---- phase 1: K2's fp32 arithmetic again (columns, then rows), to find the flagged pixels ----
+        unsigned long long need = ~0ull;
+        if (!replay_all) {
+            float x[8];
+            float bound = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int k = 8 * i + r;
-            double dq = (double)q[i] * tab.mult64[k];     // a few ulps from the reference's reciprocal chain
-            if (k != 0) dq *= two_minus_nv;
-            x[i] = dq * tab.pre64[k];
-            bound = fma(fabs(x[i]), tab.gain64[k], bound);
+            for (int i = 0; i < 8; ++i) {
+                const int k = 8 * i + r;
+                float f;
+                asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(q[i]));
+                if (p.adaptive && k != 0) f = __fmul_rn(f, s32);
+                x[i] = __fmul_rn(f, tab.rs32[k]);
+                bound = __fmaf_rn(fabsf(x[i]), tab.gain32[k], bound);
+            }
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) bound += __shfl_xor_sync(0xffffffffu, bound, d);
+            idct8<float, 1>(x);                           // column r
+#pragma unroll
+            for (int i = 0; i < 8; ++i) T[i][r] = x[i];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = T[r][j];
+            __syncwarp();
+            idct8<float, 1>(x);                           // row r: x[j] = sample (r, j)
+            // K2 and this sum the bound in different orders; both are valid bounds (the 1.0625 in
+            // pixel_threshold covers the accumulation's own rounding), so a pixel unflagged here is
+            // provably right even if K2 flagged it.
+            const float thr = pixel_threshold(bound, tab.band_floor);
+            need = 0;
+            if (!(bound < 1.4e5f)) {
+                need = 0xFFull << (8 * r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float t, e;
+                    pixel_residual(x[j], t, e);
+                    if (fabsf(e) >= thr) need |= 1ull << (8 * r + j);
+                }
+            }
+            need = group_or(need);
         }
-#pragma unroll
-        for (int d = 1; d < 8; d <<= 1) bound += shfl_double(bound, lane ^ d);
-        idct8<double, 1>(x);                              // column r
-#pragma unroll
-        for (int i = 0; i < 8; ++i) T[i][r] = x[i];
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = T[r][j];
-        __syncwarp();
-        idct8<double, 1>(x);                              // row r: x[j] = sample (r, j)
-
-        const double band = 2e-9 + bound * 1.25e-16;      // 1e-9 classification margin + 1.1 * 2^-53 * bound
-        unsigned long long need = 0;
-        uint32_t lo = 0, hi = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const double val = x[j] + 128.0;
-            const double t = val + kMagic52, n = t - kMagic52;
-            if (fabs(val - n) >= 0.5 - band || !(fabs(val) < 1e9)) need |= 1ull << (8 * r + j);
-            const uint32_t byte = (uint32_t)(int)fmin(fmax(n, 0.0), 255.0);
-            if (j < 4) lo |= byte << (8 * j);
-            else hi |= byte << (8 * (j - 4));
-        }
-        if (active) *reinterpret_cast<uint2 *>(dst + r * p.pitch) = make_uint2(lo, hi);
-        need = group_or(need);
 
         // ---- phase 2: exact replay of single pixels ------------------------------------------
         if (__any_sync(0xffffffffu, need != 0)) {

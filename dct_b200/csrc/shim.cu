@@ -99,6 +99,7 @@ struct dct_cuda_plan {
     Lane lane[kLanes];
     Counters *h_ctr = nullptr;                  // pinned, kLanes entries
     bool profile = false;
+    bool skip_replay = false;                   // test hook: leave K1/K2's fast-path values unpatched
 };
 
 namespace {
@@ -156,16 +157,6 @@ int read_tables(dct_cuda_plan *p)
         const double mult = p->adaptive ? 1.0 / R : R;
         p->rs[k] = (float)(mult * kInvPrescale[k]);
         p->gain[k] = exotic ? 1e30f : kInvGain[k] * 1.02f;
-        // phase 1 of K3 (fp64 butterfly): the fp32 bounds scale with the unit roundoff, 2^-53 / 2^-24 = 2^-29
-        const double b64 = ((double)kFwdBeta[k] * 1.1 + 16.0 * u * kFwdCmax[k]) * std::ldexp(1.0, -29) / Q;
-        p->h_tab.rinv[k] = 1.0 / (Q * kFwdScale[k]);
-        p->h_tab.band64[k] = (std::isfinite(b64) && b64 < 0.25) ? 2e-9 + b64 : 1.0;   // 1.0: always exact
-        // adjust_matrix_for_block floors Q*(2-nv) at 1.0 (src/quantization.c:203-205); phase 1 does not
-        // model that floor, so entries that could hit it always take the exact path
-        if (p->adaptive && k != 0 && !(Q >= 1.0)) p->h_tab.band64[k] = 1.0;
-        p->h_tab.mult64[k] = mult;
-        p->h_tab.pre64[k] = kInvPrescale[k];
-        p->h_tab.gain64[k] = (double)kInvGain[k] * 1.1;
     }
     p->band_floor = 1.0e-6f;
     // One band for all coefficients costs half the instructions of 64 separate compares but replays
@@ -174,6 +165,12 @@ int read_tables(dct_cuda_plan *p)
     p->thr_min = p->thr[0];
     for (int k = 1; k < 64; ++k) p->thr_min = std::min(p->thr_min, p->thr[k]);
     p->uniform_band = (!exotic && (0.5 - (double)p->thr_min) * 128.0 < 0.01) ? 1 : 0;
+    memcpy(p->h_tab.r32, p->r, sizeof p->r);
+    memcpy(p->h_tab.thr32, p->thr, sizeof p->thr);
+    memcpy(p->h_tab.rs32, p->rs, sizeof p->rs);
+    memcpy(p->h_tab.gain32, p->gain, sizeof p->gain);
+    p->h_tab.band_floor = p->band_floor;
+    p->h_tab.pad_ = 0.f;
     return DCT_CUDA_OK;
 }
 
@@ -257,7 +254,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
         }
         rp.worklist = ln.d_wl;
     }
-    CU_TRY(launch_replay_fwd(rp, s));
+    if (!p->skip_replay || p->exotic) CU_TRY(launch_replay_fwd(rp, s));
     ln.blocks += nblocks;
     return DCT_CUDA_OK;
 }
@@ -314,7 +311,7 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
         }
         rp.worklist = ln.d_wl;
     }
-    CU_TRY(launch_replay_inv(rp, s));
+    if (!p->skip_replay || p->exotic) CU_TRY(launch_replay_inv(rp, s));
     ln.blocks += nblocks;
     return DCT_CUDA_OK;
 }
@@ -483,6 +480,13 @@ extern "C" int dct_cuda_stats_fetch(dct_cuda_plan *p, dct_cuda_stats *stats, voi
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     DeviceGuard g(p->device);
     return collect_stats(p, stats, (cudaStream_t)stream);
+}
+
+extern "C" int dct_cuda_plan_debug_skip_replay(dct_cuda_plan *p, int skip)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    p->skip_replay = skip != 0;
+    return DCT_CUDA_OK;
 }
 
 extern "C" int dct_cuda_plan_profile(dct_cuda_plan *p, int enable)

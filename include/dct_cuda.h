@@ -135,6 +135,11 @@ int dct_cuda_plan_profile(dct_cuda_plan *plan, int enable);
 int dct_cuda_profile_fetch(dct_cuda_plan *plan, double *fwd_ms, int *fwd_launches, double *inv_ms,
                            int *inv_launches);
 
+/* Test hook: with skip != 0 the fp64 replay (K3) is not queued, so the output holds the fused kernels'
+ * own fp32-path values.  Used by the tests to prove that every value outside a replayed block is
+ * already bit-exact, i.e. that the replay hides nothing.  Never set this in production. */
+int dct_cuda_plan_debug_skip_replay(dct_cuda_plan *plan, int skip);
+
 /* ---- adapters for the untouched host consumer (src/entropy.c) ---- */
 /* widen one 128-byte record into a ragged 8x8 int block in NATURAL order */
 void dct_cuda_record_to_block(const int16_t *record, int layout, int **block);

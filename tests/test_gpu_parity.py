@@ -247,6 +247,42 @@ def test_inverse_on_arbitrary_coefficients(api, oracle):
         assert np.array_equal(got, want), (quality, adaptive, span, np.count_nonzero(got != want))
 
 
+@pytest.mark.parametrize("quality,adaptive", [(50, 0), (95, 0), (100, 0), (75, 1), (100, 1)])
+def test_fast_path_alone_is_exact_outside_the_band(api, oracle, quality, adaptive):
+    """With the fp64 replay switched off, the fused kernels' own values may differ from the oracle only
+    in a handful of places (the values the replay exists for): the replay must not be hiding errors of
+    the fp32 path.  Large coefficients (q95-100: |q| up to 1024) go through the fast conversions here."""
+    rng = np.random.default_rng(1000 + quality + adaptive)
+    px = rng.integers(0, 256, size=(256, 512), dtype=np.uint8)
+    H, W = px.shape
+    nb = (H // 8) * (W // 8)
+    Q = oracle.quant_table(quality)
+    want_c, want_v, _ = oracle.fwd_quant_plane(px, Q, adaptive, 0, nthreads=8)
+    want_p, _ = oracle.dequant_idct_plane(want_c, W, H, Q, adaptive, 0, want_v, nthreads=8)
+    with Ctx(api, quality, adaptive) as cx:
+        ref_c, st = cx.plan.fwd_quant(px, want_stats=True)
+        ref_c = ref_c[0] if adaptive else ref_c
+        flagged_fwd = st["replayed_blocks"]
+        _, st = cx.plan.dequant_idct(want_c, W, H, var=want_v if adaptive else None, want_stats=True)
+        flagged_inv = st["replayed_blocks"]
+        cx.plan.debug_skip_replay(True)
+        out = cx.plan.fwd_quant(px)
+        fast_c = out[0] if adaptive else out
+        fast_p = cx.plan.dequant_idct(want_c, W, H, var=want_v if adaptive else None)
+        cx.plan.debug_skip_replay(False)
+    assert np.array_equal(ref_c, want_c)
+    bad_blocks = np.count_nonzero((fast_c != want_c).any(axis=1))
+    bad_vals = np.count_nonzero(fast_c != want_c)
+    assert bad_blocks <= flagged_fwd and bad_vals <= 2 * max(flagged_fwd, 1), (bad_blocks, bad_vals, flagged_fwd)
+    assert np.abs(fast_c.astype(np.int32) - want_c).max() <= 1          # a missed tie is off by one, never more
+    diff = fast_p != want_p
+    bad_px = np.count_nonzero(diff)
+    bad_pblocks = np.count_nonzero(diff.reshape(H // 8, 8, W // 8, 8).any(axis=(1, 3)))
+    assert bad_pblocks <= flagged_inv and bad_px <= 2 * max(flagged_inv, 1), (bad_pblocks, bad_px, flagged_inv)
+    assert np.abs(fast_p.astype(np.int32) - want_p).max() <= 1
+    assert flagged_fwd < nb and flagged_inv <= nb
+
+
 def test_custom_and_exotic_tables(api, oracle):
     rng = np.random.default_rng(23)
     px = rng.integers(0, 256, size=(64, 256), dtype=np.uint8)
