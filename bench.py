@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--layout", type=int, default=0)
     ap.add_argument("--adaptive", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quality", type=int, default=QUALITY, help="non-default values are exploratory, not the headline config")
     return ap.parse_args()
 
 
@@ -218,7 +219,7 @@ def main():
     rec = torch.empty_like(px)
     var = torch.empty(nblocks, dtype=torch.float64, device=dev) if args.adaptive else None
 
-    dctx, qctx = api.dct_init(8), api.quant_init(8, QUALITY, args.adaptive)
+    dctx, qctx = api.dct_init(8), api.quant_init(8, args.quality, args.adaptive)
     plan = api.Plan(dctx, qctx, local_rank)
 
     def step():
@@ -347,7 +348,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 butterfly, f64 replay of near-ties (bit-exact int16/u8 results)", "data": "synthetic",
-        "config": {"workload": f"{W}x{H} 8-bit grayscale frames, q{QUALITY}, adaptive {'on' if args.adaptive else 'off'}: "
+        "config": {"workload": f"{W}x{H} 8-bit grayscale frames, q{args.quality}, adaptive {'on' if args.adaptive else 'off'}: "
                                f"forward DCT+quantise then dequantise+IDCT (BASELINE configs[1])",
                    "frames_per_step_per_gpu": frames, "layout": "zigzag" if args.layout else "natural",
                    "l2": "inputs larger than L2 (531 MB pixels + 1062 MB records per direction), no flush",

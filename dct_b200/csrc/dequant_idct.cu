@@ -145,7 +145,119 @@ __global__ void __launch_bounds__(kThreads) k_dequant_idct_u8(const __grid_const
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// fp64 variant: same mapping, the butterfly in double precision.  Used for ADAPTIVE plans, whose
+// dequantised values are full-scale (q * Q * (2-nv)): there the fp32 dynamic bound flags most
+// blocks of busy content, while the fp64 band (~1e-9) flags only true near-ties.  fp64 runs at
+// half the fp32 rate on B200, so this costs ~1.5x the fp32 kernel but is content-independent.
+// ------------------------------------------------------------------------------------------
+constexpr int kThreads64 = 128;
+constexpr int kWarps64 = kThreads64 / 32;
+constexpr double kMagic52_128 = 6755399441055744.0 + 128.0;   // 1.5 * 2^52 + 128
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kThreads64) k_dequant_idct_u8_f64(const __grid_constant__ InvParams p, const ExactTables *__restrict__ tab)
+{
+    __shared__ uint4 stage[kWarps64 * kStageWordsPerWarp / 4];
+    __shared__ double s_mp[64];
+    __shared__ float s_gain[64];
+    if (threadIdx.x < 64) {
+        s_mp[threadIdx.x] = tab->mp64[threadIdx.x];
+        s_gain[threadIdx.x] = tab->gain32[threadIdx.x];
+    }
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warp_base = blockIdx.x * kThreads64 + warp * 32;
+    const uint32_t b = warp_base + lane;
+    const bool valid = b < p.nblocks;
+
+    uint32_t *wstage = reinterpret_cast<uint32_t *>(stage) + warp * kStageWordsPerWarp;
+    const uint4 *srcv = reinterpret_cast<const uint4 *>(p.coef) + (size_t)warp_base * 8;
+    const uint32_t full = warp_base < p.nblocks ? p.nblocks - warp_base : 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t c = j * 32 + lane;
+        const uint4 chunk = (j * 4 + (lane >> 3) < full) ? ldg_stream_u4(srcv + c) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(wstage + (c >> 3) * kStageWordsPerBlock + 4 * (c & 7)) = chunk;
+    }
+    __syncwarp();
+
+    // (2 - nv) in fp64 with the reference's own expression (src/quantization.c:186-190)
+    const double var = (p.var_in != nullptr && valid) ? p.var_in[b] : 0.0;
+    const double two_minus_nv = __dsub_rn(2.0, fmin(1.0, fmax(0.1, __ddiv_rn(var, 1000.0))));
+
+    double v[64];
+    double bound = 0.0;
+    static_for<0, 8>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        const uint4 t = *reinterpret_cast<const uint4 *>(wstage + lane * kStageWordsPerBlock + 4 * j);
+        const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+        static_for<0, 8>([&](auto Hh) {
+            constexpr int h = decltype(Hh)::value;
+            constexpr int k = storage_to_natural<LAYOUT>(8 * j + h);
+            const int q = (int)(int16_t)(h & 1 ? (w4[h >> 1] >> 16) : (w4[h >> 1] & 0xFFFFu));
+            // q * (1/R) * (2-nv) * prescale: a few ulps from the reference's reciprocal chain, inside the
+            // 8 * 2^-53 relative input error the bound allows for
+            double x = (double)q * s_mp[k];
+            if (k != 0) x *= two_minus_nv;
+            v[k] = x;
+            bound = fma(fabs(x), (double)s_gain[k], bound);
+        });
+    });
+#pragma unroll
+    for (int j = 0; j < 8; ++j) idct8<double, 8>(&v[j]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) idct8<double, 1>(&v[8 * i]);
+
+    const uint32_t bb = valid ? b : p.nblocks - 1;
+    const uint32_t by = bb / p.bw, bx = bb - by * p.bw;
+    uint8_t *dst = p.px + (long long)by * 8 * p.pitch + (long long)bx * 8;
+
+    // 1e-9 tie-accounting margin + 8 * 2^-53 * bound (fp64 butterfly + the reference's own rounding)
+    const double thr = 0.5 - (2e-9 + bound * 8.9e-16);
+    bool flag = !(bound < 1e12);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double x = v[8 * i + j];
+            const double t = x + kMagic52_128;            // low mantissa bits: round(x) + 128
+            const double e = x - (t - kMagic52_128);
+            flag |= fabs(e) >= thr;
+            int px = __double2loint(t);
+            px = px < 0 ? 0 : (px > 255 ? 255 : px);
+            if (j < 4) lo |= (uint32_t)px << (8 * j);
+            else hi |= (uint32_t)px << (8 * (j - 4));
+        }
+        if (valid) stg_stream_u2(dst + i * p.pitch, lo, hi);
+    }
+
+    const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
+    if (ballot != 0) {
+        const int leader = __ffs(ballot) - 1;
+        unsigned base = 0;
+        if ((int)lane == leader) base = atomicAdd(&p.ctr->wl_count, (unsigned)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (flag && valid) {
+            const unsigned pos = base + __popc(ballot & ((1u << lane) - 1u));
+            if (pos < p.wl_cap) p.worklist[pos] = b;
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_dequant_idct_u8_f64(const InvParams &p, const ExactTables *d_tab, int layout, cudaStream_t s)
+{
+    if (p.nblocks == 0) return cudaSuccess;
+    const unsigned grid = (p.nblocks + kThreads64 - 1) / kThreads64;
+    if (layout == LAYOUT_ZIGZAG) k_dequant_idct_u8_f64<LAYOUT_ZIGZAG><<<grid, kThreads64, 0, s>>>(p, d_tab);
+    else k_dequant_idct_u8_f64<LAYOUT_NATURAL><<<grid, kThreads64, 0, s>>>(p, d_tab);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s)
 {

@@ -24,6 +24,7 @@ struct ExactTables {
     double D[64];   // dct_matrix, row-major
     double Q[64];   // quant_matrix
     double R[64];   // dequant_matrix
+    double mp64[64];    // K3's fp64 pass: dequantisation multiplier (R, or 1/R when adaptive) * a_u a_v / 8
     // the fused kernels' fp32 tables, so that K3 can repeat their arithmetic bit for bit
     float r32[64];      // K1: 1 / (Q_k * 8 a_u a_v)
     float thr32[64];    // K1: 0.5 - band_k
@@ -87,6 +88,7 @@ struct ReplayParams {
 
 cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s);
 cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s);
+cudaError_t launch_dequant_idct_u8_f64(const InvParams &p, const ExactTables *d_tab, int layout, cudaStream_t s);
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s);
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s);
 

@@ -89,7 +89,7 @@ __device__ __forceinline__ double byte_centered(uint2 raw, int m)
 
 struct ReplayShared {
     ExactTables tab;
-    alignas(16) float tile[kReplayThreads / 32][4][8][9];   // [warp][block][row][col + pad]; 288 B per block
+    alignas(16) double tile[kReplayThreads / 32][4][8][9];  // [warp][block][row][col + pad]; reused as float / int16
 };
 
 template <int LAYOUT>
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
     }
     const bool replay_all = p.worklist == nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 3, r = lane & 7, gbase = lane & 24;
-    float(*T)[9] = sh.tile[warp][g];
+    float(*T)[9] = reinterpret_cast<float(*)[9]>(&sh.tile[warp][g][0][0]);
     unsigned ties = 0, sat = 0;
     const unsigned groups_per_grid = gridDim.x * (kReplayThreads / 8);
 
@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
     }
     const bool replay_all = p.worklist == nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 3, r = lane & 7, gbase = lane & 24;
-    float(*T)[9] = sh.tile[warp][g];
+    float(*T)[9] = reinterpret_cast<float(*)[9]>(&sh.tile[warp][g][0][0]);
+    double(*Td)[9] = sh.tile[warp][g];
     unsigned ties = 0;
     const unsigned groups_per_grid = gridDim.x * (kReplayThreads / 8);
 
@@ -260,11 +261,12 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
         const unsigned by = b / p.bw, bx = b - by * p.bw;
         uint8_t *dst = p.px_out + (long long)by * 8 * p.pitch + (long long)bx * 8;
 
-        double inv_two_minus_nv = 1.0;
+        double inv_two_minus_nv = 1.0, two_minus_nv = 1.0;
         float s32 = 1.0f;
         if (p.adaptive) {
             const double var = p.var_in ? p.var_in[b] : 0.0;
-            inv_two_minus_nv = __ddiv_rn(1.0, __dsub_rn(2.0, norm_variance(var)));   // src/quantization.c:193
+            two_minus_nv = __dsub_rn(2.0, norm_variance(var));
+            inv_two_minus_nv = __ddiv_rn(1.0, two_minus_nv);   // src/quantization.c:193
             s32 = adaptive_scale(var);
         }
 
@@ -323,11 +325,58 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
             need = group_or(need);
         }
 
-        // ---- phase 2: exact replay of single pixels ------------------------------------------
+        // ---- phase 2 and 3 -------------------------------------------------------------------
         if (__any_sync(0xffffffffu, need != 0)) {
-            double in[8];                                 // exact dequantised column r
+            // phase 2: the same butterfly in fp64.  Its error (~1e-13 * bound) is far below the fp32
+            // band, so it settles every flagged pixel that is not within band64 of a boundary -- with a
+            // loose dynamic fp32 bound (large coefficients, adaptive decode) that is nearly all of them.
+            // Worth its ~100 fp64 instructions only when a block has several flagged pixels.
+            if (__any_sync(0xffffffffu, __popcll(need) >= 3)) {
+                double x[8];
+                double bound64 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = 8 * i + r;
+                    // q * multiplier * (2-nv) instead of the reference's reciprocal chain: a few ulps apart,
+                    // inside the 8 * 2^-53 input error the bound allows for
+                    x[i] = (double)q[i] * tab.mp64[k];
+                    if (k != 0) x[i] *= two_minus_nv;
+                    bound64 = fma(fabs(x[i]), (double)tab.gain32[k], bound64);
+                }
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) bound64 += shfl_double(bound64, lane ^ d);
+                idct8<double, 1>(x);                      // column r
+#pragma unroll
+                for (int i = 0; i < 8; ++i) Td[i][r] = x[i];
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = Td[r][j];
+                __syncwarp();
+                idct8<double, 1>(x);                      // row r
+                // 1e-9: the tie-accounting margin; 8 * 2^-53 * bound: fp64 butterfly + the reference's own rounding
+                const double band64 = 2e-9 + bound64 * 8.9e-16;
+                unsigned long long settled = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned long long bit = 1ull << (8 * r + j);
+                    if (need & bit) {
+                        const double val = x[j] + 128.0;
+                        const double n = rint(val);
+                        if (fabs(val - n) < 0.5 - band64 && fabs(val) < 1e9) {
+                            if (active) dst[r * p.pitch + j] = (uint8_t)(int)fmin(fmax(n, 0.0), 255.0);
+                            settled |= bit;
+                        }
+                    }
+                }
+                need &= ~group_or(settled);
+            }
+        }
+        if (__any_sync(0xffffffffu, need != 0)) {
+            double in[8];                                 // the reference's dequantised column r, exactly
 #pragma unroll
             for (int m = 0; m < 8; ++m) in[m] = exact_dequant(tab, p.adaptive, inv_two_minus_nv, 8 * m + r, q[m]);
+
+            // phase 3: exact replay of what is left (values within ~1e-9 of a .5 boundary)
             while (__any_sync(0xffffffffu, need != 0)) {
                 const bool mine = need != 0;
                 const int e = mine ? __ffsll((long long)need) - 1 : 0;

@@ -99,6 +99,7 @@ struct dct_cuda_plan {
     Lane lane[kLanes];
     Counters *h_ctr = nullptr;                  // pinned, kLanes entries
     bool profile = false;
+    bool force_fp32_inverse = false;            // DCT_CUDA_INV_FP32=1: keep the fp32 inverse for adaptive plans too
     bool skip_replay = false;                   // test hook: leave K1/K2's fast-path values unpatched
 };
 
@@ -157,6 +158,7 @@ int read_tables(dct_cuda_plan *p)
         const double mult = p->adaptive ? 1.0 / R : R;
         p->rs[k] = (float)(mult * kInvPrescale[k]);
         p->gain[k] = exotic ? 1e30f : kInvGain[k] * 1.02f;
+        p->h_tab.mp64[k] = mult * kInvPrescale[k];
     }
     p->band_floor = 1.0e-6f;
     // One band for all coefficients costs half the instructions of 64 separate compares but replays
@@ -304,7 +306,9 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
             CU_TRY(cudaEventCreate(&e1));
             CU_TRY(cudaEventRecord(e0, s));
         }
-        CU_TRY(launch_dequant_idct_u8(ip, layout, p->adaptive, s));
+        // adaptive plans decode full-scale values: the fp64 butterfly keeps the replay list short
+        if (p->adaptive && !p->force_fp32_inverse) CU_TRY(launch_dequant_idct_u8_f64(ip, p->d_tab, layout, s));
+        else CU_TRY(launch_dequant_idct_u8(ip, layout, p->adaptive, s));
         if (p->profile) {
             CU_TRY(cudaEventRecord(e1, s));
             ln.ev_inv.emplace_back(e0, e1);
@@ -374,6 +378,7 @@ extern "C" dct_cuda_plan *dct_cuda_plan_create(const DCTContext *dct, const Quan
         return nullptr;
     }
     p->device = device;
+    p->force_fp32_inverse = getenv("DCT_CUDA_INV_FP32") != nullptr;
     p->dct = dct;
     p->quant = quant;
     DeviceGuard g(device);
