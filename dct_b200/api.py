@@ -113,6 +113,10 @@ _skip_replay = _sig("dct_cuda_plan_debug_skip_replay", C.c_int, C.c_void_p, C.c_
 _profile = _sig("dct_cuda_plan_profile", C.c_int, C.c_void_p, C.c_int)
 _profile_fetch = _sig("dct_cuda_profile_fetch", C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int),
                       C.POINTER(C.c_double), C.POINTER(C.c_int))
+_rle_count = _sig("dct_cuda_rle_count_dev", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                  C.POINTER(C.c_uint64), C.c_void_p)
+_rle_emit = _sig("dct_cuda_rle_emit_dev", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
+                 C.c_void_p)
 _rec_to_block = _sig("dct_cuda_record_to_block", None, C.POINTER(C.c_int16), C.c_int, _PP_I)
 _block_to_rec = _sig("dct_cuda_block_to_record", None, _PP_I, C.c_int, C.POINTER(C.c_int16))
 _host_alloc = _sig("dct_cuda_host_alloc", C.c_void_p, C.c_size_t)
@@ -392,6 +396,20 @@ class Plan:
         _check(_profile_fetch(self._h, C.byref(fm), C.byref(fn), C.byref(im), C.byref(inn)))
         return {"fwd_ms": fm.value, "fwd_launches": fn.value, "inv_ms": im.value, "inv_launches": inn.value}
 
+    def rle_dev(self, coef, layout=NATURAL, stream=None):
+        """Run-length symbols of device-resident records (torch int16 [nblocks, 64]).
+        -> (offsets uint32-as-int32 tensor [nblocks+1], symbols int32 tensor [total, 2] = (value, run_length))."""
+        import torch
+        assert coef.is_cuda and coef.dtype == torch.int16 and coef.is_contiguous()
+        nb = coef.numel() // 64
+        off = torch.empty(nb + 1, dtype=torch.int32, device=coef.device)
+        total = C.c_uint64(0)
+        _check(_rle_count(self._h, coef.data_ptr(), nb, off.data_ptr(), C.byref(total), _stream_ptr(stream)))
+        sym = torch.empty((int(total.value), 2), dtype=torch.int32, device=coef.device)
+        if total.value:
+            _check(_rle_emit(self._h, coef.data_ptr(), nb, layout, off.data_ptr(), sym.data_ptr(), _stream_ptr(stream)))
+        return off, sym
+
     def stats(self, stream=None):
         st = Stats()
         _check(_stats_fetch(self._h, C.byref(st), _stream_ptr(stream)))
@@ -431,6 +449,7 @@ def exported_symbols():
             "dct_cuda_dequant_idct_u8_dev", "dct_cuda_fwd_quant_planes_dev", "dct_cuda_dequant_idct_planes_dev",
             "dct_cuda_fwd_quant_u8", "dct_cuda_dequant_idct_u8", "dct_cuda_fwd_quant_u8_async",
             "dct_cuda_dequant_idct_u8_async", "dct_cuda_plan_wait", "dct_cuda_fwd_quant_u8_multi",
-            "dct_cuda_dequant_idct_u8_multi", "dct_cuda_stats_fetch", "dct_cuda_plan_profile", "dct_cuda_plan_debug_skip_replay",
+            "dct_cuda_dequant_idct_u8_multi", "dct_cuda_stats_fetch", "dct_cuda_plan_profile", "dct_cuda_plan_debug_skip_replay", "dct_cuda_rle_count_dev",
+            "dct_cuda_rle_emit_dev",
             "dct_cuda_profile_fetch", "dct_cuda_record_to_block",
             "dct_cuda_block_to_record", "dct_cuda_host_alloc", "dct_cuda_host_free"]

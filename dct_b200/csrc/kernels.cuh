@@ -92,6 +92,12 @@ cudaError_t launch_dequant_idct_u8_f64(const InvParams &p, const ExactTables *d_
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s);
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s);
 
+// K5: run-length symbols of the records (rle.cu)
+cudaError_t launch_rle_count(const int16_t *d_coef, uint32_t nblocks, uint32_t *d_offsets, uint32_t *d_cta_sums,
+                             unsigned long long *d_total, cudaStream_t s);
+cudaError_t launch_rle_emit(const int16_t *d_coef, uint32_t nblocks, int layout, const uint32_t *d_offsets, void *d_symbols,
+                            cudaStream_t s);
+
 // generic-N single block kernels behind the per-block drop-in API (K4/K6)
 cudaError_t launch_block_dct_f64(int n, const double *d_D, const double *d_in, double *d_out, int inverse,
                                  cudaStream_t s);

@@ -99,6 +99,9 @@ struct dct_cuda_plan {
     Lane lane[kLanes];
     Counters *h_ctr = nullptr;                  // pinned, kLanes entries
     bool profile = false;
+    uint32_t *d_rle_sums = nullptr;             // K5 workspace: per-CTA symbol totals + the grand total
+    size_t rle_sums_cap = 0;
+    unsigned long long *d_rle_total = nullptr;
     bool force_fp32_inverse = false;            // DCT_CUDA_INV_FP32=1: keep the fp32 inverse for adaptive plans too
     bool skip_replay = false;                   // test hook: leave K1/K2's fast-path values unpatched
 };
@@ -427,6 +430,8 @@ extern "C" void dct_cuda_plan_destroy(dct_cuda_plan *p)
         if (ln.d_var) cudaFree(ln.d_var);
         if (ln.stream) cudaStreamDestroy(ln.stream);
     }
+    if (p->d_rle_sums) cudaFree(p->d_rle_sums);
+    if (p->d_rle_total) cudaFree(p->d_rle_total);
     if (p->d_tab) cudaFree(p->d_tab);
     if (p->h_ctr) cudaFreeHost(p->h_ctr);
     delete p;
@@ -679,6 +684,54 @@ extern "C" int dct_cuda_dequant_idct_u8_multi(dct_cuda_plan *const *plans, int n
         return dct_cuda_dequant_idct_u8(p, coef + (size_t)r0 * bw * 64, W, (r1 - r0) * 8, layout,
                                         var ? var + (size_t)r0 * bw : nullptr, px + (size_t)r0 * 8 * pitch, pitch, st);
     });
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: run-length symbols for the host entropy coder (src/entropy.c:216-256)
+// ------------------------------------------------------------------------------------------
+extern "C" int dct_cuda_rle_count_dev(dct_cuda_plan *p, const int16_t *d_coef, size_t nblocks, uint32_t *d_offsets,
+                                      uint64_t *total_symbols, void *stream)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    if ((nblocks && !d_coef) || !d_offsets) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
+    if (nblocks > (1u << 26)) return fail(DCT_CUDA_EINVAL, "at most 2^26 records per call (32-bit symbol offsets)");
+    if ((uintptr_t)d_coef % 16) return fail(DCT_CUDA_EINVAL, "coefficients must be 16-byte aligned");
+    DeviceGuard g(p->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!p->d_rle_total) CU_TRY(cudaMalloc(&p->d_rle_total, sizeof(unsigned long long)));
+    const size_t ctas = (nblocks + 255) / 256;
+    if (p->rle_sums_cap < ctas + 1) {
+        CU_TRY(cudaStreamSynchronize(s));
+        if (p->d_rle_sums) CU_TRY(cudaFree(p->d_rle_sums));
+        p->d_rle_sums = nullptr;
+        CU_TRY(cudaMalloc(&p->d_rle_sums, (ctas + 1) * sizeof(uint32_t)));
+        p->rle_sums_cap = ctas + 1;
+    }
+    unsigned long long total = 0;
+    if (nblocks == 0) {
+        CU_TRY(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t), s));
+    } else {
+        CU_TRY(launch_rle_count(d_coef, (uint32_t)nblocks, d_offsets, p->d_rle_sums, p->d_rle_total, s));
+        CU_TRY(cudaMemcpyAsync(&total, p->d_rle_total, sizeof total, cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    if (total_symbols) *total_symbols = total;
+    return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_rle_emit_dev(dct_cuda_plan *p, const int16_t *d_coef, size_t nblocks, int layout,
+                                     const uint32_t *d_offsets, dct_cuda_rle_symbol *d_symbols, void *stream)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    if (nblocks == 0) return DCT_CUDA_OK;
+    if (!d_coef || !d_offsets || !d_symbols) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
+    if (nblocks > (1u << 26)) return fail(DCT_CUDA_EINVAL, "at most 2^26 records per call (32-bit symbol offsets)");
+    if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
+    if (((uintptr_t)d_coef % 16) || ((uintptr_t)d_symbols % 8)) return fail(DCT_CUDA_EINVAL, "misaligned buffer");
+    if (nblocks == 0) return DCT_CUDA_OK;
+    DeviceGuard g(p->device);
+    CU_TRY(launch_rle_emit(d_coef, (uint32_t)nblocks, layout, d_offsets, d_symbols, (cudaStream_t)stream));
+    return DCT_CUDA_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -135,6 +135,25 @@ int dct_cuda_plan_profile(dct_cuda_plan *plan, int enable);
 int dct_cuda_profile_fetch(dct_cuda_plan *plan, double *fwd_ms, int *fwd_launches, double *inv_ms,
                            int *inv_launches);
 
+/* ---- run-length symbols for the host entropy coder (device-resident records) ----
+ * For every record, the list of symbols the untouched run_length_encode() (src/entropy.c:216-256)
+ * would produce for that block: zigzag order, one {value, run_length} per non-zero coefficient plus
+ * the closing symbol at position 63.  dct_cuda_rle_symbol has the layout of RLESymbol
+ * (include/entropy.h:35-38), so a block's list can be memcpy'd into EntropyContext.symbols
+ * (set .count) before build_huffman_codes().
+ *   pass 1  fills d_offsets[0..nblocks] (exclusive prefix sums of the per-record symbol counts) and
+ *           returns their total (synchronises `stream`); the caller sizes d_symbols from it;
+ *   pass 2  writes the symbols of record b to d_symbols[d_offsets[b] .. d_offsets[b+1]).
+ * `layout` is how the records are stored; the symbols are in zigzag order either way. */
+typedef struct {
+    int value;
+    int run_length;
+} dct_cuda_rle_symbol;
+int dct_cuda_rle_count_dev(dct_cuda_plan *plan, const int16_t *d_coef, size_t n_blocks, uint32_t *d_offsets,
+                           uint64_t *total_symbols, void *stream);
+int dct_cuda_rle_emit_dev(dct_cuda_plan *plan, const int16_t *d_coef, size_t n_blocks, int layout,
+                          const uint32_t *d_offsets, dct_cuda_rle_symbol *d_symbols, void *stream);
+
 /* Test hook: with skip != 0 the fp64 replay (K3) is not queued, so the output holds the fused kernels'
  * own fp32-path values.  Used by the tests to prove that every value outside a replayed block is
  * already bit-exact, i.e. that the replay hides nothing.  Never set this in production. */

@@ -68,6 +68,7 @@ class CpuChecker:
           _P_D, C.c_int, _P_U64)
         f("dequant_idct_plane", C.c_int, _P_I16, C.c_int, C.c_int, _P_D, _P_D, C.c_int, C.c_int, _P_D,
           _P_U8, C.c_size_t, C.c_int, _P_U64)
+        f("rle_plane", C.c_size_t, _P_I16, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int32))
         if prefix == "orc_":
             self.lib.orc_fill_xorshift.argtypes = [_P_U8, C.c_size_t, C.c_uint64, C.c_int, C.c_int]
             self.lib.orc_fill_xorshift.restype = None
@@ -179,6 +180,17 @@ class CpuChecker:
         if rc != 0:
             raise ValueError(f"{self.prefix}dequant_idct_plane rc={rc}")
         return px, int(ties.value)
+
+    def rle_plane(self, coef, layout=NATURAL):
+        """-> (offsets uint32 [nblocks+1], symbols int32 [total, 2] = (value, run_length))."""
+        coef = np.ascontiguousarray(coef, dtype=np.int16).reshape(-1, 64)
+        nb = coef.shape[0]
+        off = np.zeros(nb + 1, dtype=np.uint32)
+        total = self._rle_plane(coef.ctypes.data_as(_P_I16), nb, int(layout), off.ctypes.data_as(C.POINTER(C.c_uint32)), None)
+        sym = np.zeros((total, 2), dtype=np.int32)
+        self._rle_plane(coef.ctypes.data_as(_P_I16), nb, int(layout), off.ctypes.data_as(C.POINTER(C.c_uint32)),
+                        sym.ctypes.data_as(C.POINTER(C.c_int32)))
+        return off, sym
 
     # ---- oracle-only helpers ----------------------------------------------------------
     def fill_xorshift(self, H, W, seed=0x9E3779B97F4A7C15, dist=0):

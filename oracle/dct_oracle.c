@@ -335,6 +335,40 @@ int orc_dequant_idct_plane(const int16_t *coef, int W, int H, const double *Q, c
 }
 
 /* ------------------------------------------------------------------------ */
+/* Run-length symbols of every record, as run_length_encode (src/entropy.c:  */
+/* 216-256) produces them: zigzag order, one (value, zero-run) symbol per     */
+/* non-zero coefficient, plus a closing symbol at position 63 whose run       */
+/* counts a zero last coefficient too.  symbols == NULL only counts.          */
+/* ------------------------------------------------------------------------ */
+size_t orc_rle_plane(const int16_t *coef, size_t nblocks, int layout, uint32_t *offsets, int32_t *symbols)
+{
+    int zz[64];
+    orc_zigzag_order(8, zz);
+    size_t total = 0;
+    for (size_t b = 0; b < nblocks; ++b) {
+        const int16_t *rec = coef + b * 64;
+        int zero_count = 0;
+        offsets[b] = (uint32_t)total;
+        for (int i = 0; i < 64; ++i) {
+            const int v = layout == ORC_LAYOUT_ZIGZAG ? rec[i] : rec[zz[i]];
+            if (v != 0 || i == 63) {
+                if (i == 63 && v == 0) zero_count++;
+                if (symbols) {
+                    symbols[2 * total] = v;
+                    symbols[2 * total + 1] = zero_count;
+                }
+                ++total;
+                zero_count = 0;
+            } else {
+                zero_count++;
+            }
+        }
+    }
+    offsets[nblocks] = (uint32_t)total;
+    return total;
+}
+
+/* ------------------------------------------------------------------------ */
 /* Synthetic inputs and hashes                  */
 /* ------------------------------------------------------------------------ */
 

@@ -48,6 +48,9 @@ int orc_dequant_idct_plane(const int16_t *coef, int W, int H, const double *Q, c
                            int adaptive, int layout, const double *var_in, uint8_t *px, size_t pitch,
                            int nthreads, uint64_t *near_ties);
 
+/* ---- run-length symbols (value, run) per record; returns the total, offsets has nblocks+1 entries ---- */
+size_t orc_rle_plane(const int16_t *coef, size_t nblocks, int layout, uint32_t *offsets, int32_t *symbols);
+
 /* ---- helpers shared by the tests --------------------------------------- */
 void     orc_fill_xorshift(uint8_t *dst, size_t n, uint64_t seed, int dist, int W);
 uint64_t orc_fnv_i16(const int16_t *v, size_t n);

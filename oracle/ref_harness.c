@@ -296,3 +296,34 @@ int ref_dequant_idct_plane(const int16_t *coef, int W, int H, const double *Q, c
     if (near_ties) *near_ties = 0;
     return ref_run(&jb, Q, nthreads);
 }
+
+/* ---- the reference's run_length_encode over every record (src/entropy.c:216-256) ---- */
+size_t ref_rle_plane(const int16_t *coef, size_t nblocks, int layout, uint32_t *offsets, int32_t *symbols)
+{
+    EntropyContext *e = entropy_init(0);
+    int **q = alloc_int_array(8, 8);
+    int zz[64];
+    size_t total = 0;
+    for (size_t b = 0; b < nblocks; ++b) {
+        const int16_t *rec = coef + b * 64;
+        if (layout == 1) {
+            for (int k = 0; k < 64; ++k) zz[k] = rec[k];
+            zigzag_to_block(zz, q, 8);
+        } else {
+            for (int k = 0; k < 64; ++k) q[k / 8][k % 8] = rec[k];
+        }
+        const int n = run_length_encode(e, q, 8);
+        offsets[b] = (uint32_t)total;
+        for (int i = 0; i < n; ++i) {
+            if (symbols) {
+                symbols[2 * (total + i)] = e->symbols[i].value;
+                symbols[2 * (total + i) + 1] = e->symbols[i].run_length;
+            }
+        }
+        total += (size_t)n;
+    }
+    offsets[nblocks] = (uint32_t)total;
+    free_int_array(q, 8);
+    entropy_free(e);
+    return total;
+}

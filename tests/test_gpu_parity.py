@@ -443,6 +443,35 @@ def test_config5_huge_plane_sampled_strips(api, oracle, torch):
     torch.cuda.empty_cache()
 
 
+def test_rle_symbols_match_run_length_encode(api, oracle, torch):
+    """the device-side symbol lists equal what the untouched run_length_encode
+    (src/entropy.c:216-256) produces for every block, for both record layouts."""
+    rng = np.random.default_rng(77)
+    c = rng.integers(-4, 5, size=(5000, 64)).astype(np.int16)
+    c[rng.random(c.shape) < 0.7] = 0
+    c[0] = 0
+    c[1] = 0
+    c[1, 63] = 7
+    c[2] = 3
+    c[3, :] = -32768
+    with Ctx(api, 50, 0) as cx:
+        for layout in (api.NATURAL, api.ZIGZAG):
+            off, sym = cx.plan.rle_dev(torch.from_numpy(c).cuda(), layout)
+            want_off, want_sym = oracle.rle_plane(c, layout)
+            assert np.array_equal(off.cpu().numpy().view(np.uint32), want_off)
+            assert np.array_equal(sym.cpu().numpy(), want_sym)
+        # through the real pipeline: a 4K frame, quantised on the device, both layouts
+        px = torch.from_numpy(rng.integers(0, 256, size=(2160, 3840), dtype=np.uint8)).cuda()
+        for layout in (api.NATURAL, api.ZIGZAG):
+            coef = cx.plan.fwd_quant_dev(px, layout)
+            off, sym = cx.plan.rle_dev(coef, layout)
+            want_off, want_sym = oracle.rle_plane(coef.cpu().numpy(), layout)
+            assert np.array_equal(off.cpu().numpy().view(np.uint32), want_off)
+            assert np.array_equal(sym.cpu().numpy(), want_sym)
+        off, sym = cx.plan.rle_dev(torch.empty((0, 64), dtype=torch.int16, device="cuda"))
+        assert off.cpu().tolist() == [0] and sym.shape[0] == 0
+
+
 def test_adaptive_round_trip_reconstructs(api, oracle):
     """Property: with adaptive=1 (the one mode whose dequantize is mathematically right, SURVEY.md
     S3) a high-quality round trip returns nearly the input; with adaptive=0 it is the reference's

@@ -145,3 +145,36 @@ def test_oracle_equals_reference_on_random_planes(oracle, quality, adaptive, lay
     po, _ = oracle.dequant_idct_plane(junk, 192, 128, Q, adaptive, layout, vo)
     pr, _ = ref.dequant_idct_plane(junk, 192, 128, Q, adaptive, layout, vr)
     assert np.array_equal(po, pr)
+
+
+def test_rle_symbols_restate_run_length_encode(oracle, golden_planes):
+    # reference: src/entropy.c:216-256 (symbols) on top of :158-178 (zigzag)
+    rng = np.random.default_rng(8)
+    c = rng.integers(-4, 5, size=(300, 64)).astype(np.int16)
+    c[rng.random(c.shape) < 0.7] = 0
+    c[0] = 0                      # all zero: one closing symbol (0, 64)
+    c[1] = 0
+    c[1, 63] = 7                  # only the last coefficient: (7, 63)
+    c[2] = 3                      # dense: 64 symbols, all runs 0
+    for layout in (0, 1):
+        off, sym = oracle.rle_plane(c, layout)
+        assert off[0] == 0 and off[-1] == len(sym)
+        assert sym[off[0]:off[1]].tolist() == [[0, 64]]
+        assert sym[off[1]:off[2]].tolist() == [[7, 63]]
+        assert sym[off[2]:off[3]].tolist() == [[3, 0]] * 64
+        # decoding the symbols gives the zigzag sequence back (run_length_decode, src/entropy.c:333-358)
+        zz = oracle.zigzag_order(8)
+        for b in (3, 17, 299):
+            seq = []
+            for v, run in sym[off[b]:off[b + 1]]:
+                seq += [0] * run + [v]
+            want = c[b] if layout == 1 else c[b][zz]
+            assert seq[:64] == list(want) and len(seq) in (64, 65)
+    if B.have_ref():
+        ref = B.load("ref")
+        for layout in (0, 1):
+            a, b_ = oracle.rle_plane(c, layout), ref.rle_plane(c, layout)
+            assert np.array_equal(a[0], b_[0]) and np.array_equal(a[1], b_[1])
+        coef = golden_planes["u64x48/q50/a0/coef"]
+        a, b_ = oracle.rle_plane(coef, 0), ref.rle_plane(coef, 0)
+        assert np.array_equal(a[0], b_[0]) and np.array_equal(a[1], b_[1])
