@@ -443,6 +443,38 @@ def test_config5_huge_plane_sampled_strips(api, oracle, torch):
     torch.cuda.empty_cache()
 
 
+def test_no_write_outside_the_output_buffers(api, oracle, torch):
+    """Guard bands around every device output (compute-sanitizer is not available on this pool):
+    partial warp tiles, a pitched destination, both directions, replay included."""
+    rng = np.random.default_rng(91)
+    for (H, W) in [(8, 8), (72, 520), (16, 2056)]:
+        nb = (H // 8) * (W // 8)
+        px = torch.from_numpy(rng.integers(0, 256, size=(H, W), dtype=np.uint8)).cuda()
+        guard = 4096
+        cbuf = torch.full((guard + nb * 64 + guard,), 0x5A5A, dtype=torch.int16, device="cuda")
+        vbuf = torch.full((64 + nb + 64,), -7.0, dtype=torch.float64, device="cuda")
+        pbuf = torch.full((H + 16, W + 64), 0xAB, dtype=torch.uint8, device="cuda")
+        coef = cbuf[guard:guard + nb * 64].view(nb, 64)
+        var = vbuf[64:64 + nb]
+        rec = pbuf[8:8 + H, 16:16 + W]
+        with Ctx(api, 90, 1) as cx:
+            cx.plan.fwd_quant_dev(px, api.ZIGZAG, coef, var)
+            cx.plan.dequant_idct_dev(coef, W, H, api.ZIGZAG, var, rec)
+            off, sym = cx.plan.rle_dev(coef.contiguous(), api.ZIGZAG)
+            torch.cuda.synchronize()
+        assert bool((cbuf[:guard] == 0x5A5A).all()) and bool((cbuf[guard + nb * 64:] == 0x5A5A).all())
+        assert bool((vbuf[:64] == -7.0).all()) and bool((vbuf[64 + nb:] == -7.0).all())
+        frame = pbuf.clone()
+        frame[8:8 + H, 16:16 + W] = 0xAB
+        assert bool((frame == 0xAB).all())
+        Q = oracle.quant_table(90)
+        want_c, want_v, _ = oracle.fwd_quant_plane(px.cpu().numpy(), Q, 1, 1)
+        assert np.array_equal(coef.cpu().numpy(), want_c)
+        want_p, _ = oracle.dequant_idct_plane(want_c, W, H, Q, 1, 1, want_v)
+        assert np.array_equal(rec.cpu().numpy(), want_p)
+        assert int(off[-1]) == sym.shape[0]
+
+
 def test_rle_symbols_match_run_length_encode(api, oracle, torch):
     """the device-side symbol lists equal what the untouched run_length_encode
     (src/entropy.c:216-256) produces for every block, for both record layouts."""
