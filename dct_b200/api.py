@@ -99,6 +99,10 @@ _fwd_host = _sig("dct_cuda_fwd_quant_u8", C.c_int, C.c_void_p, C.c_void_p, C.c_s
                  C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Stats))
 _inv_host = _sig("dct_cuda_dequant_idct_u8", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                  C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Stats))
+_fwd_f32_dev = _sig("dct_cuda_fwd_quant_f32_dev", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                    C.c_void_p, C.c_int, C.c_void_p)
+_fwd_f32_host = _sig("dct_cuda_fwd_quant_f32", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                     C.c_void_p, C.c_int, C.POINTER(Stats))
 _fwd_host_async = _sig("dct_cuda_fwd_quant_u8_async", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                        C.c_void_p, C.c_int, C.c_void_p)
 _inv_host_async = _sig("dct_cuda_dequant_idct_u8_async", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -331,6 +335,23 @@ class Plan:
         out = (coef, var) if self.adaptive else coef
         return (out, st.as_dict()) if want_stats else out
 
+    def fwd_quant_f32(self, pixels, layout=NATURAL, want_stats=False):
+        """Float pixel tiles (numpy float32 on the host, or a torch cuda float32 tensor): block = p - 128."""
+        if _is_torch(pixels):
+            import torch
+            assert pixels.is_cuda and pixels.dtype == torch.float32 and pixels.dim() == 2 and pixels.stride(1) == 1
+            H, W = pixels.shape
+            coef = torch.empty(((H // 8) * (W // 8), 64), dtype=torch.int16, device=pixels.device)
+            _check(_fwd_f32_dev(self._h, pixels.data_ptr(), pixels.stride(0) * 4, W, H, coef.data_ptr(), layout,
+                                _stream_ptr(None)))
+            return coef
+        assert pixels.dtype == np.float32 and pixels.ndim == 2 and pixels.strides[1] == 4
+        H, W = pixels.shape
+        coef = np.empty(((H // 8) * (W // 8), 64), dtype=np.int16)
+        st = Stats()
+        _check(_fwd_f32_host(self._h, pixels.ctypes.data, pixels.strides[0], W, H, coef.ctypes.data, layout, C.byref(st)))
+        return (coef, st.as_dict()) if want_stats else coef
+
     def dequant_idct(self, coef, W, H, layout=NATURAL, var=None, pixels_out=None, want_stats=False):
         if _is_torch(coef):
             return self.dequant_idct_dev(coef, W, H, layout, var, pixels_out)
@@ -447,7 +468,7 @@ def exported_symbols():
             "adjust_matrix_for_block", "dct_cuda_last_error", "dct_cuda_device_count", "dct_cuda_plan_create",
             "dct_cuda_plan_refresh", "dct_cuda_plan_destroy", "dct_cuda_plan_device", "dct_cuda_fwd_quant_u8_dev",
             "dct_cuda_dequant_idct_u8_dev", "dct_cuda_fwd_quant_planes_dev", "dct_cuda_dequant_idct_planes_dev",
-            "dct_cuda_fwd_quant_u8", "dct_cuda_dequant_idct_u8", "dct_cuda_fwd_quant_u8_async",
+            "dct_cuda_fwd_quant_u8", "dct_cuda_dequant_idct_u8", "dct_cuda_fwd_quant_u8_async", "dct_cuda_fwd_quant_f32_dev", "dct_cuda_fwd_quant_f32",
             "dct_cuda_dequant_idct_u8_async", "dct_cuda_plan_wait", "dct_cuda_fwd_quant_u8_multi",
             "dct_cuda_dequant_idct_u8_multi", "dct_cuda_stats_fetch", "dct_cuda_plan_profile", "dct_cuda_plan_debug_skip_replay", "dct_cuda_rle_count_dev",
             "dct_cuda_rle_emit_dev",

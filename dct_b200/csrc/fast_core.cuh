@@ -36,6 +36,9 @@ __device__ __forceinline__ void fdct8_row_from_bytes(float *x, uint2 raw)
     fdct8_tail<float, 1>(x, s07, s16, s25, s34, d07, d16, d25, d34);
 }
 
+// float pixel -> centred sample on the fast path (the reference's (double)p - 128.0 is exact; this rounds once)
+__device__ __forceinline__ float centre_float_pixel(float p) { return __fsub_rn(p, 128.0f); }
+
 // sum and sum of squares of the centred samples of one 8-pixel row, exact (packed byte dot products)
 __device__ __forceinline__ void row_moments(uint2 raw, int &isum, int &isq)
 {

@@ -192,6 +192,95 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
     }   // tile loop
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K1 from FLOAT pixel tiles (north_star: "8-bit or float pixel tiles"): block = (double)p - 128.0
+// for arbitrary float p, then dct_forward + quantize -- what a caller of the reference gets by
+// filling the input block by hand (tests/test_dct.c:46-50).  256 B in + 128 B out per block.
+// One-shot grid, 16 LDG.128 per lane (a warp instruction covers 1 KB contiguous); the loaded
+// registers ARE the block.  The band table assumes p in [0, 255] (|p - 128| <= 128, input rounding
+// <= 128 u); blocks with a pixel outside that range, or NaN, are replayed whole in fp64.
+// Non-adaptive plans only (the host rejects the others).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream_f4(const void *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kThreads) k_fwd_quant_f32(const __grid_constant__ FwdParams p)
+{
+    __shared__ uint4 stage[kWarps * kStageWordsPerWarp / 4];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warp_base = blockIdx.x * kThreads + warp * 32;
+    const uint32_t b = warp_base + lane;
+    const bool valid = b < p.nblocks;
+    const uint32_t bb = valid ? b : p.nblocks - 1;
+    const uint32_t by = bb / p.bw, bx = bb - by * p.bw;
+    const uint8_t *src = p.px + (long long)by * 8 * p.pitch + (long long)bx * 32;
+
+    float v[64];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 lo = ldg_stream_f4(src + i * p.pitch), hi = ldg_stream_f4(src + i * p.pitch + 16);
+        v[8 * i + 0] = lo.x, v[8 * i + 1] = lo.y, v[8 * i + 2] = lo.z, v[8 * i + 3] = lo.w;
+        v[8 * i + 4] = hi.x, v[8 * i + 5] = hi.y, v[8 * i + 6] = hi.z, v[8 * i + 7] = hi.w;
+    }
+    float amax = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 64; k += 2) {
+        v[k] = centre_float_pixel(v[k]);
+        v[k + 1] = centre_float_pixel(v[k + 1]);
+        amax = fmaxf(fmaxf(amax, fabsf(v[k])), fabsf(v[k + 1]));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fdct8<float, 1>(&v[8 * i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fdct8<float, 8>(&v[j]);
+
+    uint32_t w[32];
+    bool flag = !(amax <= 128.0f);   // outside the band table's domain (or NaN): whole block to fp64
+    static_for<0, 32>([&](auto M) {
+        constexpr int m = decltype(M)::value;
+        constexpr int k0 = storage_to_natural<LAYOUT>(2 * m), k1 = storage_to_natural<LAYOUT>(2 * m + 1);
+        float t0, t1, e0, e1;
+        quant_residual(v[k0], p.r[k0], t0, e0);
+        quant_residual(v[k1], p.r[k1], t1, e1);
+        flag |= (fabsf(e0) >= p.thr[k0]) | (fabsf(e1) >= p.thr[k1]);
+        w[m] = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x5410);
+    });
+
+    uint32_t *wstage = reinterpret_cast<uint32_t *>(stage) + warp * kStageWordsPerWarp;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4 *>(wstage + lane * kStageWordsPerBlock + 4 * j) =
+            make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    __syncwarp();
+    uint4 *dst = reinterpret_cast<uint4 *>(p.coef) + (size_t)warp_base * 8 + lane;
+    const uint32_t *rd = wstage + (lane >> 3) * kStageWordsPerBlock + 4 * (lane & 7);
+    const uint32_t full = warp_base < p.nblocks ? p.nblocks - warp_base : 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j * 4 + (lane >> 3) < full)
+            stg_stream_u4(dst + j * 32, *reinterpret_cast<const uint4 *>(rd + j * 4 * kStageWordsPerBlock));
+
+    const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
+    if (ballot != 0) {
+        const int leader = __ffs(ballot) - 1;
+        unsigned base = 0;
+        if ((int)lane == leader) base = atomicAdd(&p.ctr->wl_count, (unsigned)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (flag && valid) {
+            const unsigned pos = base + __popc(ballot & ((1u << lane) - 1u));
+            if (pos < p.wl_cap) p.worklist[pos] = b;
+        }
+    }
+}
+
 }  // namespace
 
 static int sm_count()
@@ -232,6 +321,15 @@ template <int LAYOUT, bool ADAPTIVE> static cudaError_t launch_k1(const FwdParam
 {
     return p.uniform_band ? launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, true>, p, s)
                           : launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, false>, p, s);
+}
+
+cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s)
+{
+    if (p.nblocks == 0) return cudaSuccess;
+    const unsigned grid = (p.nblocks + kThreads - 1) / kThreads;
+    if (layout == LAYOUT_ZIGZAG) k_fwd_quant_f32<LAYOUT_ZIGZAG><<<grid, kThreads, 0, s>>>(p);
+    else k_fwd_quant_f32<LAYOUT_NATURAL><<<grid, kThreads, 0, s>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s)

@@ -28,6 +28,7 @@ struct ExactTables {
     // the fused kernels' fp32 tables, so that K3 can repeat their arithmetic bit for bit
     float r32[64];      // K1: 1 / (Q_k * 8 a_u a_v)
     float thr32[64];    // K1: 0.5 - band_k
+    float thr32f[64];   // K1 from float pixel tiles: 0.5 - band_k (wider: inputs carry a rounding error)
     float rs32[64];     // K2: dequantisation multiplier * a_u a_v / 8
     float gain32[64];   // K2: error gain per unit |input|
     float band_floor;   // K2
@@ -36,7 +37,7 @@ struct ExactTables {
 
 // K1: forward DCT + quantise.  One thread per 8x8 block.
 struct FwdParams {
-    const uint8_t *px;
+    const uint8_t *px;     // uint8 pixels, or float pixels (k_fwd_quant_f32) reinterpreted
     long long pitch;       // bytes between pixel rows (multiple of 8)
     uint32_t bw;           // blocks per block-row (W/8)
     uint32_t nblocks;
@@ -78,7 +79,8 @@ struct ReplayParams {
     int adaptive;
     int layout;
     long long pitch;
-    const uint8_t *px_in;       // forward
+    const uint8_t *px_in;       // forward (uint8 pixels; float pixels when px_is_f32)
+    int px_is_f32;
     int16_t *coef_out;
     double *var_out;
     const int16_t *coef_in;     // inverse
@@ -87,6 +89,7 @@ struct ReplayParams {
 };
 
 cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s);
+cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s);
 cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s);
 cudaError_t launch_dequant_idct_u8_f64(const InvParams &p, const ExactTables *d_tab, int layout, cudaStream_t s);
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s);

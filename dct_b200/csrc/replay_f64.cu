@@ -92,7 +92,31 @@ struct ReplayShared {
     alignas(16) double tile[kReplayThreads / 32][4][8][9];  // [warp][block][row][col + pad]; reused as float / int16
 };
 
-template <int LAYOUT>
+// one 8-pixel row of a block, as the fused kernel read it: 8 bytes, or 8 floats (float pixel tiles)
+template <bool F32> struct PixelRow;
+template <> struct PixelRow<false> {
+    uint2 raw;
+    __device__ __forceinline__ void load(const uint8_t *base, long long pitch, unsigned by, unsigned bx, int r)
+    {
+        raw = *reinterpret_cast<const uint2 *>(base + ((long long)by * 8 + r) * pitch + (long long)bx * 8);
+    }
+    __device__ __forceinline__ double exact(int m) const { return byte_centered(raw, m); }
+};
+template <> struct PixelRow<true> {
+    float4 lo, hi;
+    __device__ __forceinline__ void load(const uint8_t *base, long long pitch, unsigned by, unsigned bx, int r)
+    {
+        const float4 *row = reinterpret_cast<const float4 *>(base + ((long long)by * 8 + r) * pitch + (long long)bx * 32);
+        lo = row[0], hi = row[1];
+    }
+    __device__ __forceinline__ float at(int m) const
+    {
+        return m == 0 ? lo.x : m == 1 ? lo.y : m == 2 ? lo.z : m == 3 ? lo.w : m == 4 ? hi.x : m == 5 ? hi.y : m == 6 ? hi.z : hi.w;
+    }
+    __device__ __forceinline__ double exact(int m) const { return __dsub_rn((double)at(m), 128.0); }   // src/dct.c:115 on a float
+};
+
+template <int LAYOUT, bool F32>
 __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -118,17 +142,17 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
 
     // Warp-uniform trip count so that the shuffles below always see the whole warp.  The worklist
     // entry and the pixel row of the NEXT iteration are fetched before this iteration's arithmetic.
-    auto fetch = [&](unsigned base_, bool &act_, unsigned &b_, uint2 &raw_) {
+    auto fetch = [&](unsigned base_, bool &act_, unsigned &b_, PixelRow<F32> &raw_) {
         const unsigned slot = base_ + g;
         act_ = slot < count;
         b_ = act_ ? (p.worklist ? p.worklist[slot] : slot) : 0;
         const unsigned by = b_ / p.bw, bx = b_ - by * p.bw;
-        raw_ = *reinterpret_cast<const uint2 *>(p.px_in + ((long long)by * 8 + r) * p.pitch + (long long)bx * 8);
+        raw_.load(p.px_in, p.pitch, by, bx, r);
     };
     unsigned base = (blockIdx.x * (kReplayThreads / 32) + warp) * 4;
     bool active = false, active_n = false;
     unsigned b = 0, b_n = 0;
-    uint2 raw = make_uint2(0, 0), raw_n = make_uint2(0, 0);
+    PixelRow<F32> raw{}, raw_n{};
     if (base < count) fetch(base, active, b, raw);
     for (; base < count; base += groups_per_grid, active = active_n, b = b_n, raw = raw_n) {
         if (base + groups_per_grid < count) fetch(base + groups_per_grid, active_n, b_n, raw_n);
@@ -136,9 +160,9 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
         // per-block variance (adaptive): exact integers, reduced over the 8 rows
         double scale = 1.0;
         float inv_s = 1.0f;
-        if (p.adaptive) {
+        if constexpr (!F32) if (p.adaptive) {
             int isum = 0, isq = 0;
-            row_moments(raw, isum, isq);
+            row_moments(raw.raw, isum, isq);
 #pragma unroll
             for (int d = 1; d < 8; d <<= 1) {
                 isum += __shfl_xor_sync(0xffffffffu, isum, d);
@@ -157,7 +181,19 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
         unsigned long long need = ~0ull;
         if (!replay_all) {
             float x[8];
-            fdct8_row_from_bytes(x, raw);
+            bool whole = false;
+            if constexpr (F32) {
+                float amax = 0.0f;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    x[m] = centre_float_pixel(raw.at(m));
+                    amax = fmaxf(amax, fabsf(x[m]));
+                }
+                whole = __any_sync(0xffu << gbase, !(amax <= 128.0f));   // K1 flagged the block as out of domain
+                fdct8<float, 1>(x);
+            } else {
+                fdct8_row_from_bytes(x, raw.raw);
+            }
 #pragma unroll
             for (int m = 0; m < 8; ++m) T[r][m] = x[m];
             __syncwarp();
@@ -173,9 +209,10 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
                 if (p.adaptive && k != 0) rk = __fmul_rn(rk, inv_s);
                 float t, e;
                 quant_residual(x[u], rk, t, e);
-                if (fabsf(e) >= tab.thr32[k]) need |= 1ull << k;
+                if (fabsf(e) >= (F32 ? tab.thr32f[k] : tab.thr32[k])) need |= 1ull << k;
             }
-            need = group_or(need);
+            need = group_or(need);            // full-warp shuffles: every lane must take part
+            if (whole) need = ~0ull;
         }
 
         // ---- phase 2: exact replay of single coefficients, cooperatively by the group ---------
@@ -186,7 +223,7 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
             const int i = k >> 3, j = k & 7;
             double temp = 0.0;   // temp[r][j] = sum_m X[r][m] * D[j][m]      (src/dct.c:57-64)
 #pragma unroll
-            for (int m = 0; m < 8; ++m) temp = __dadd_rn(temp, __dmul_rn(byte_centered(raw, m), tab.D[j * 8 + m]));
+            for (int m = 0; m < 8; ++m) temp = __dadd_rn(temp, __dmul_rn(raw.exact(m), tab.D[j * 8 + m]));
             const double prod = __dmul_rn(tab.D[i * 8 + r], temp);
             double out = 0.0;    // out[i][j] = sum_kk D[i][kk] * temp[kk][j]  (src/dct.c:67-74), kk ascending
 #pragma unroll
@@ -476,8 +513,11 @@ template <typename K> static cudaError_t launch_replay(K kernel, const ReplayPar
 
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s)
 {
-    return p.layout == LAYOUT_ZIGZAG ? launch_replay(k_replay_fwd<LAYOUT_ZIGZAG>, p, s)
-                                     : launch_replay(k_replay_fwd<LAYOUT_NATURAL>, p, s);
+    if (p.px_is_f32)
+        return p.layout == LAYOUT_ZIGZAG ? launch_replay(k_replay_fwd<LAYOUT_ZIGZAG, true>, p, s)
+                                         : launch_replay(k_replay_fwd<LAYOUT_NATURAL, true>, p, s);
+    return p.layout == LAYOUT_ZIGZAG ? launch_replay(k_replay_fwd<LAYOUT_ZIGZAG, false>, p, s)
+                                     : launch_replay(k_replay_fwd<LAYOUT_NATURAL, false>, p, s);
 }
 
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s)

@@ -94,6 +94,7 @@ struct dct_cuda_plan {
     ExactTables h_tab;
     ExactTables *d_tab = nullptr;
     float r[64], thr[64], thr_min;              // K1
+    float thr_f32[64];                          // K1 from float pixel tiles
     int uniform_band;
     float rs[64], gain[64], band_floor;         // K2
     Lane lane[kLanes];
@@ -156,6 +157,11 @@ int read_tables(dct_cuda_plan *p)
         if (exotic || !(thr > 0.0)) thr = -1.0;   // everything replays
         p->thr[k] = (float)thr;
         if ((double)p->thr[k] > thr) p->thr[k] = std::nextafterf(p->thr[k], -1.0f);   // round down
+        // float pixel tiles: same multiplier, wider band (the inputs fl32(p - 128) are already rounded)
+        double thr_f = 0.5 - (((double)kFwdBetaF32[k] * 1.02) / Q + std::ldexp(1.0, -22));
+        if (exotic || !(thr_f > 0.0)) thr_f = -1.0;
+        p->thr_f32[k] = (float)thr_f;
+        if ((double)p->thr_f32[k] > thr_f) p->thr_f32[k] = std::nextafterf(p->thr_f32[k], -1.0f);
         // K2: v = q * rs.  non-adaptive: rs = R * prescale (sic: the reference multiplies by 1/Q);
         //     adaptive: rs = (1/R) * prescale, times (2-nv) per block in the kernel.
         const double mult = p->adaptive ? 1.0 / R : R;
@@ -172,6 +178,7 @@ int read_tables(dct_cuda_plan *p)
     p->uniform_band = (!exotic && (0.5 - (double)p->thr_min) * 128.0 < 0.01) ? 1 : 0;
     memcpy(p->h_tab.r32, p->r, sizeof p->r);
     memcpy(p->h_tab.thr32, p->thr, sizeof p->thr);
+    memcpy(p->h_tab.thr32f, p->thr_f32, sizeof p->thr_f32);
     memcpy(p->h_tab.rs32, p->rs, sizeof p->rs);
     memcpy(p->h_tab.gain32, p->gain, sizeof p->gain);
     p->h_tab.band_floor = p->band_floor;
@@ -207,13 +214,16 @@ int check_plane(const void *a, const void *b, size_t pitch, int W, int H, bool d
 }
 
 // queue K1 (+K3) for one device-resident plane on lane `ln`, stream `s`
+// elem: bytes per pixel of the source plane -- 1 (uint8) or 4 (float tiles); pitch is in bytes
 int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int W, int H, int16_t *d_coef,
-              int layout, double *d_var, cudaStream_t s)
+              int layout, double *d_var, cudaStream_t s, int elem = 1)
 {
     const uint32_t bw = W / 8, nblocks = bw * (uint32_t)(H / 8);
     if (nblocks == 0) return DCT_CUDA_OK;
-    if (((uintptr_t)d_px % 8) || ((uintptr_t)d_coef % 16))
-        return fail(DCT_CUDA_EINVAL, "pixels must be 8-byte and coefficients 16-byte aligned");
+    if (((uintptr_t)d_px % (elem == 4 ? 16 : 8)) || ((uintptr_t)d_coef % 16))
+        return fail(DCT_CUDA_EINVAL, "pixels must be %d-byte and coefficients 16-byte aligned", elem == 4 ? 16 : 8);
+    if (elem == 4 && p->adaptive)
+        return fail(DCT_CUDA_EINVAL, "float pixel tiles are supported for non-adaptive plans only");
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     int rc = ensure_worklist(ln, nblocks);
     if (rc) return rc;
@@ -229,6 +239,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
     rp.layout = layout;
     rp.pitch = (long long)pitch;
     rp.px_in = d_px;
+    rp.px_is_f32 = elem == 4;
     rp.coef_out = d_coef;
     rp.var_out = p->adaptive ? d_var : nullptr;
     if (!p->exotic) {
@@ -243,7 +254,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
         fp.wl_cap = ln.wl_cap;
         fp.ctr = ln.d_ctr;
         memcpy(fp.r, p->r, sizeof fp.r);
-        memcpy(fp.thr, p->thr, sizeof fp.thr);
+        memcpy(fp.thr, elem == 4 ? p->thr_f32 : p->thr, sizeof fp.thr);
         fp.thr_min = p->thr_min;
         fp.uniform_band = p->uniform_band;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -252,7 +263,8 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
             CU_TRY(cudaEventCreate(&e1));
             CU_TRY(cudaEventRecord(e0, s));
         }
-        CU_TRY(launch_fwd_quant_u8(fp, layout, p->adaptive, s));
+        if (elem == 4) CU_TRY(launch_fwd_quant_f32(fp, layout, s));
+        else CU_TRY(launch_fwd_quant_u8(fp, layout, p->adaptive, s));
         if (p->profile) {
             CU_TRY(cudaEventRecord(e1, s));
             ln.ev_fwd.emplace_back(e0, e1);
@@ -323,8 +335,9 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
     return DCT_CUDA_OK;
 }
 
-int ensure_strip_buffers(dct_cuda_plan *p, Lane &ln, size_t blocks)
+int ensure_strip_buffers(dct_cuda_plan *p, Lane &ln, size_t blocks, int elem = 1)
 {
+    blocks *= (size_t)elem;   // the pixel buffer is sized in 64-byte units: float tiles need four per block
     if (ln.cap_blocks >= blocks) return DCT_CUDA_OK;
     CU_TRY(cudaStreamSynchronize(ln.stream));
     if (ln.d_px) cudaFree(ln.d_px);
@@ -452,6 +465,17 @@ extern "C" int dct_cuda_fwd_quant_u8_dev(dct_cuda_plan *p, const uint8_t *d_px, 
     return queue_fwd(p, p->lane[0], d_px, pitch, W, H, d_coef, layout, d_var, (cudaStream_t)stream);
 }
 
+extern "C" int dct_cuda_fwd_quant_f32_dev(dct_cuda_plan *p, const float *d_px, size_t pitch_bytes, int W, int H,
+                                          int16_t *d_coef, int layout, void *stream)
+{
+    if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    int rc = check_plane(d_px, d_coef, pitch_bytes / 4, W, H, false);
+    if (rc) return rc;
+    if (pitch_bytes % 16) return fail(DCT_CUDA_EINVAL, "float planes need a pitch that is a multiple of 16 bytes");
+    DeviceGuard g(p->device);
+    return queue_fwd(p, p->lane[0], (const uint8_t *)d_px, pitch_bytes, W, H, d_coef, layout, nullptr, (cudaStream_t)stream, 4);
+}
+
 extern "C" int dct_cuda_dequant_idct_u8_dev(dct_cuda_plan *p, const int16_t *d_coef, int W, int H, int layout,
                                             const double *d_var, uint8_t *d_px, size_t pitch, void *stream)
 {
@@ -549,32 +573,50 @@ static int strip_rows(int W, int H)
     return (int)std::min(rows, total);
 }
 
-extern "C" int dct_cuda_fwd_quant_u8_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H,
-                                           int16_t *coef, int layout, double *var)
+static int fwd_host_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H, int16_t *coef, int layout,
+                          double *var, int elem)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
-    int rc = check_plane(px, coef, pitch, W, H, false);
+    int rc = check_plane(px, coef, pitch / elem, W, H, false);
     if (rc) return rc;
+    if (elem == 4 && p->adaptive) return fail(DCT_CUDA_EINVAL, "float pixel tiles are supported for non-adaptive plans only");
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     DeviceGuard g(p->device);
     const int bw = W / 8, total_rows = H / 8, rows = strip_rows(W, H);
     if (rows > 0) {
         for (int l = 0; l < kLanes; ++l)
-            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw))) return rc;
+            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw, elem))) return rc;
         int idx = 0;
+        const size_t row_bytes = (size_t)W * elem;
         for (int r0 = 0; r0 < total_rows; r0 += rows, ++idx) {
             Lane &ln = p->lane[idx % kLanes];
             const int nr = std::min(rows, total_rows - r0);
             const size_t nb = (size_t)nr * bw, b0 = (size_t)r0 * bw;
-            CU_TRY(cudaMemcpy2DAsync(ln.d_px, (size_t)W, px + (size_t)r0 * 8 * pitch, pitch, (size_t)W, (size_t)nr * 8,
+            CU_TRY(cudaMemcpy2DAsync(ln.d_px, row_bytes, px + (size_t)r0 * 8 * pitch, pitch, row_bytes, (size_t)nr * 8,
                                      cudaMemcpyHostToDevice, ln.stream));
-            if ((rc = queue_fwd(p, ln, ln.d_px, (size_t)W, W, nr * 8, ln.d_coef, layout, ln.d_var, ln.stream))) return rc;
+            if ((rc = queue_fwd(p, ln, ln.d_px, row_bytes, W, nr * 8, ln.d_coef, layout, ln.d_var, ln.stream, elem))) return rc;
             CU_TRY(cudaMemcpyAsync(coef + b0 * 64, ln.d_coef, nb * 128, cudaMemcpyDeviceToHost, ln.stream));
             if (p->adaptive && var)
                 CU_TRY(cudaMemcpyAsync(var + b0, ln.d_var, nb * sizeof(double), cudaMemcpyDeviceToHost, ln.stream));
         }
     }
     return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_fwd_quant_u8_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H,
+                                           int16_t *coef, int layout, double *var)
+{
+    return fwd_host_async(p, px, pitch, W, H, coef, layout, var, 1);
+}
+
+extern "C" int dct_cuda_plan_wait(dct_cuda_plan *p, dct_cuda_stats *stats);
+
+extern "C" int dct_cuda_fwd_quant_f32(dct_cuda_plan *p, const float *px, size_t pitch_bytes, int W, int H, int16_t *coef,
+                                      int layout, dct_cuda_stats *stats)
+{
+    int rc = fwd_host_async(p, (const uint8_t *)px, pitch_bytes, W, H, coef, layout, nullptr, 4);
+    if (rc) return rc;
+    return dct_cuda_plan_wait(p, stats);
 }
 
 extern "C" int dct_cuda_plan_wait(dct_cuda_plan *p, dct_cuda_stats *stats)

@@ -105,6 +105,15 @@ int dct_cuda_fwd_quant_u8(dct_cuda_plan *plan, const uint8_t *pixels, size_t pit
 int dct_cuda_dequant_idct_u8(dct_cuda_plan *plan, const int16_t *coef, int width, int height, int layout,
                              const double *variance, uint8_t *pixels, size_t pitch, dct_cuda_stats *stats);
 
+/* ---- float pixel tiles (forward only, non-adaptive plans): the block is (double)p - 128.0 for any
+ * float p, i.e. what a caller of the reference gets by filling dct_forward's input block by hand
+ * (tests/test_dct.c:46-50).  Bit-exact like the uint8 path; pixels outside [0, 255] are legal (their
+ * blocks are computed in fp64).  `pitch_bytes` must be a multiple of 16 for the device call. ---- */
+int dct_cuda_fwd_quant_f32_dev(dct_cuda_plan *plan, const float *d_pixels, size_t pitch_bytes, int width, int height,
+                               int16_t *d_coef, int layout, void *stream);
+int dct_cuda_fwd_quant_f32(dct_cuda_plan *plan, const float *pixels, size_t pitch_bytes, int width, int height,
+                           int16_t *coef, int layout, dct_cuda_stats *stats);
+
 /* Asynchronous forms: queue the whole strip pipeline on the plan's own streams and return at once.
  * The host buffers must be PINNED and stay untouched until dct_cuda_plan_wait(plan, stats) returns.
  * Two plans (e.g. an encoder and a decoder) driven this way overlap each other's H2D and D2H

@@ -68,6 +68,8 @@ class CpuChecker:
           _P_D, C.c_int, _P_U64)
         f("dequant_idct_plane", C.c_int, _P_I16, C.c_int, C.c_int, _P_D, _P_D, C.c_int, C.c_int, _P_D,
           _P_U8, C.c_size_t, C.c_int, _P_U64)
+        f("fwd_quant_plane_f32", C.c_int, C.POINTER(C.c_float), C.c_size_t, C.c_int, C.c_int, _P_D, C.c_int, C.c_int, _P_I16,
+          _P_D, C.c_int, _P_U64)
         f("rle_plane", C.c_size_t, _P_I16, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int32))
         if prefix == "orc_":
             self.lib.orc_fill_xorshift.argtypes = [_P_U8, C.c_size_t, C.c_uint64, C.c_int, C.c_int]
@@ -165,6 +167,21 @@ class CpuChecker:
                                    C.byref(ties))
         if rc != 0:
             raise ValueError(f"{self.prefix}fwd_quant_plane rc={rc}")
+        return coef, var, int(ties.value)
+
+    def fwd_quant_plane_f32(self, px, Q, adaptive=0, layout=NATURAL, nthreads=1):
+        """px: (H, W) float32 -> like fwd_quant_plane, the block being (double)px - 128.0."""
+        px = np.ascontiguousarray(px, dtype=np.float32)
+        H, W = px.shape
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        nb = (H // 8) * (W // 8)
+        coef = np.zeros((nb, 64), dtype=np.int16)
+        var = np.zeros(nb, dtype=np.float64)
+        ties = C.c_uint64(0)
+        rc = self._fwd_quant_plane_f32(px.ctypes.data_as(C.POINTER(C.c_float)), W, W, H, _dp(Q), int(adaptive), int(layout),
+                                       coef.ctypes.data_as(_P_I16), _dp(var), int(nthreads), C.byref(ties))
+        if rc != 0:
+            raise ValueError(f"{self.prefix}fwd_quant_plane_f32 rc={rc}")
         return coef, var, int(ties.value)
 
     def dequant_idct_plane(self, coef, W, H, Q, adaptive=0, layout=NATURAL, var=None, nthreads=1):

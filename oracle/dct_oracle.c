@@ -190,6 +190,7 @@ static int near_half(double a)
 
 typedef struct {
     int dir; /* 0 fwd, 1 inv */
+    const float *pxf_in; /* forward from float pixels when non-NULL (pitch in floats) */
     const uint8_t *px_in;
     uint8_t *px_out;
     size_t pitch;
@@ -219,9 +220,11 @@ static void *plane_worker(void *arg)
             if (jb->dir == 0) {
                 /* src/dct.c:109-120 */
                 for (int i = 0; i < 8; ++i)
-                    for (int j = 0; j < 8; ++j)
-                        blk[i * 8 + j] =
-                            (double)jb->px_in[((size_t)by * 8 + i) * jb->pitch + (size_t)bx * 8 + j] - 128.0;
+                    for (int j = 0; j < 8; ++j) {
+                        const size_t at = ((size_t)by * 8 + i) * jb->pitch + (size_t)bx * 8 + j;
+                        /* float tiles: the block a caller fills by hand, tests/test_dct.c:46-50 */
+                        blk[i * 8 + j] = (jb->pxf_in ? (double)jb->pxf_in[at] : (double)jb->px_in[at]) - 128.0;
+                    }
                 orc_dct_forward(8, jb->D, blk, c);
                 double var = 0.0;
                 const double *m = jb->Q;
@@ -304,6 +307,24 @@ int orc_fwd_quant_plane(const uint8_t *px, size_t pitch, int W, int H, const dou
     jb.dir = 0;
     jb.px_in = px;
     jb.pitch = pitch;
+    jb.W = W;
+    jb.H = H;
+    jb.Q = Q;
+    jb.adaptive = adaptive;
+    jb.layout = layout;
+    jb.coef_out = coef;
+    jb.var_out = var_out;
+    return run_plane(&jb, nthreads, near_ties);
+}
+
+int orc_fwd_quant_plane_f32(const float *px, size_t pitch_floats, int W, int H, const double *Q, int adaptive,
+                            int layout, int16_t *coef, double *var_out, int nthreads, uint64_t *near_ties)
+{
+    job_t jb;
+    memset(&jb, 0, sizeof jb);
+    jb.dir = 0;
+    jb.pxf_in = px;
+    jb.pitch = pitch_floats;
     jb.W = W;
     jb.H = H;
     jb.Q = Q;

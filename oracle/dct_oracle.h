@@ -44,6 +44,8 @@ void   orc_round_to_int(int n, const double *blk, int *out);
 /* coefficient record: block-major, coef[(by*(W/8)+bx)*64 + k], int16.       */
 int orc_fwd_quant_plane(const uint8_t *px, size_t pitch, int W, int H, const double *Q, int adaptive,
                         int layout, int16_t *coef, double *var_out, int nthreads, uint64_t *near_ties);
+int orc_fwd_quant_plane_f32(const float *px, size_t pitch_floats, int W, int H, const double *Q, int adaptive,
+                            int layout, int16_t *coef, double *var_out, int nthreads, uint64_t *near_ties);
 int orc_dequant_idct_plane(const int16_t *coef, int W, int H, const double *Q, const double *R,
                            int adaptive, int layout, const double *var_in, uint8_t *px, size_t pitch,
                            int nthreads, uint64_t *near_ties);

@@ -327,3 +327,46 @@ size_t ref_rle_plane(const int16_t *coef, size_t nblocks, int layout, uint32_t *
     entropy_free(e);
     return total;
 }
+
+/* ---- float pixel tiles: the block is filled by hand as tests/test_dct.c:46-50 does, then the
+ * reference's dct_forward / quantize ---- */
+int ref_fwd_quant_plane_f32(const float *px, size_t pitch_floats, int W, int H, const double *Q, int adaptive,
+                            int layout, int16_t *coef, double *var_out, int nthreads, uint64_t *near_ties)
+{
+    (void)nthreads;
+    if (W <= 0 || H <= 0 || W % 8 || H % 8) return -1;
+    DCTContext *d = dct_init(8);
+    QuantContext *qc = ctx_with_table(8, Q, adaptive);
+    double **blk = alloc_array(8, 8), **c = alloc_array(8, 8);
+    int **q = alloc_int_array(8, 8);
+    int zz[64];
+    const int bw = W / 8;
+    for (int by = 0; by < H / 8; ++by)
+        for (int bx = 0; bx < bw; ++bx) {
+            const size_t b = (size_t)by * bw + bx;
+            for (int i = 0; i < 8; ++i)
+                for (int j = 0; j < 8; ++j)
+                    blk[i][j] = (double)px[((size_t)by * 8 + i) * pitch_floats + (size_t)bx * 8 + j] - 128.0;
+            dct_forward(d, blk, c);
+            double var = 0.0;
+            if (adaptive) {
+                var = calculate_block_variance(blk, 8);
+                if (var_out) var_out[b] = var;
+            }
+            quantize(qc, c, q, var);
+            int16_t *dst = coef + b * 64;
+            if (layout == 1) {
+                block_to_zigzag(q, zz, 8);
+                for (int k = 0; k < 64; ++k) dst[k] = (int16_t)zz[k];
+            } else {
+                for (int k = 0; k < 64; ++k) dst[k] = (int16_t)q[k / 8][k % 8];
+            }
+        }
+    if (near_ties) *near_ties = 0;
+    free_array(blk, 8);
+    free_array(c, 8);
+    free_int_array(q, 8);
+    dct_free(d);
+    quant_free(qc);
+    return 0;
+}

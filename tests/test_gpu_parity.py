@@ -443,6 +443,34 @@ def test_config5_huge_plane_sampled_strips(api, oracle, torch):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("quality,layout", [(50, 0), (90, 1), (100, 0)])
+def test_float_pixel_tiles(api, oracle, torch, quality, layout):
+    """north_star: "8-bit or float pixel tiles".  Arbitrary float pixels, block = (double)p - 128.0
+    (tests/test_dct.c:46-50 fills dct_forward's input that way); bit-exact quantised output, including
+    pixels outside [0, 255], exact-tie blocks and integer-valued floats (== the uint8 path)."""
+    rng = np.random.default_rng(300 + quality)
+    H, W = 200, 1000
+    px = (rng.random((H, W)) * 255.0).astype(np.float32)
+    px[8:16, 8:16] = rng.integers(0, 256, (8, 8))            # an integer-valued block
+    px[16:24, :64] = 128.0
+    px[16, 0:64:8] = 192.0                                    # exact DC ties at q50
+    px[40:48, 40:48] = rng.normal(128, 900, (8, 8))          # far outside the band table's domain
+    px[56, 57] = -3.5
+    Q = oracle.quant_table(quality)
+    want, _, ties = oracle.fwd_quant_plane_f32(px, Q, 0, layout, nthreads=8)
+    with Ctx(api, quality, 0) as cx:
+        got, st = cx.plan.fwd_quant_f32(px, layout, want_stats=True)
+        assert np.array_equal(got, want), np.count_nonzero(got != want)
+        assert st["near_ties"] == ties and st["replayed_blocks"] >= 2
+        dev = cx.plan.fwd_quant_f32(torch.from_numpy(px).cuda(), layout)
+        assert np.array_equal(dev.cpu().numpy(), want)
+        ipx = rng.integers(0, 256, size=(64, 256), dtype=np.uint8)
+        assert np.array_equal(cx.plan.fwd_quant_f32(ipx.astype(np.float32), layout), cx.plan.fwd_quant(ipx, layout))
+    with Ctx(api, quality, 1) as cx:
+        with pytest.raises(api.DctCudaError, match="non-adaptive"):
+            cx.plan.fwd_quant_f32(px, layout)
+
+
 def test_no_write_outside_the_output_buffers(api, oracle, torch):
     """Guard bands around every device output (compute-sanitizer is not available on this pool):
     partial warp tiles, a pitched destination, both directions, replay included."""

@@ -150,11 +150,16 @@ def two_d(o, f, X, rows_first):
     return [f(o, T[i]) for i in range(8)]
 
 
-def fwd_tables():
+def fwd_tables(float_pixels=False):
     """beta[k]: bound on |fp32 coefficient - exact coefficient| + |exact coefficient| * u,
-    in orthonormal-coefficient units (the K1 band is beta[k] / Q[k], see band_tables.h)."""
+    in orthonormal-coefficient units (the K1 band is beta[k] / Q[k], see band_tables.h).
+    float_pixels: the inputs are fl32(p - 128) of arbitrary floats p in [0, 255] -- not integers,
+    each already carrying a rounding error <= 128 u -- instead of exact integers."""
     o = BoundOps(np.full(64, 128.0))
-    X = [[Bound(np.eye(64)[8 * i + j], 0.0, True) for j in range(8)] for i in range(8)]
+    if float_pixels:
+        X = [[Bound(np.eye(64)[8 * i + j], 128.0 * U, False) for j in range(8)] for i in range(8)]
+    else:
+        X = [[Bound(np.eye(64)[8 * i + j], 0.0, True) for j in range(8)] for i in range(8)]
     Y = two_d(o, fdct8, X, rows_first=True)
     S = 8.0 * np.outer(AAN, AAN)
     beta, cmax = np.zeros(64), np.zeros(64)
@@ -184,6 +189,7 @@ def inv_tables():
 
 def emit(path):
     beta, cmax, S = fwd_tables()
+    beta_f, _, _ = fwd_tables(float_pixels=True)
     G, P = inv_tables()
 
     def arr(name, a, fmt="%.9ef"):
@@ -194,12 +200,14 @@ def emit(path):
         f.write("// GENERATED by tools/derive_bands.py -- do not edit.\n"
                 "// Worst-case fp32 error tables of the scaled butterflies in butterfly.cuh.\n"
                 "//   kFwdBeta[k] : |fp32 coef - exact coef| + |coef|max * 2^-24, orthonormal units\n"
+                "//   kFwdBetaF32[k]: the same for float pixel tiles (inputs fl32(p - 128), p in [0, 255])\n"
                 "//   kFwdCmax[k] : max |orthonormal coefficient k| over u8 blocks\n"
                 "//   kFwdScale[k]: 8*a_u*a_v, the butterfly's output scale (double precision below)\n"
                 "//   kInvGain[k] : |fp32 pixel - exact pixel| <= 2^-24 * sum_k kInvGain[k]*|v_k|\n"
                 "//   kInvPrescale[k]: a_u*a_v/8, folded into the dequantisation multiplier\n"
                 "#pragma once\n")
         f.write(arr("kFwdBeta", beta))
+        f.write(arr("kFwdBetaF32", beta_f))
         f.write(arr("kFwdCmax", cmax))
         f.write(arr("kInvGain", G))
         d = lambda name, a: (f"static const double {name}[64] = {{\n    " + ",\n    ".join(
