@@ -201,6 +201,8 @@ def main():
     assert torch.cuda.is_available() and api.device_count() > 0, "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from dct_b200 import numa
+    numa_info = numa.bind_to_gpu_node(local_rank) if world > 1 else {}   # pinned buffers on the GPU's socket
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -321,6 +323,7 @@ def main():
                "mode": "pipelined" if t_pipe <= t_sync else "sync",
                "sync_value": 2.0 * e_px * world / t_sync / 1e9, "pipelined_value": 2.0 * e_px * world / t_pipe / 1e9,
                "timer": "host wall clock, barrier + synchronize on both sides, max over ranks",
+               "numa_binding_rank0": numa_info,
                "result_matches_device_path": result_ok}
         plan_inv.close()
 

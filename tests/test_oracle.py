@@ -178,3 +178,19 @@ def test_rle_symbols_restate_run_length_encode(oracle, golden_planes):
         coef = golden_planes["u64x48/q50/a0/coef"]
         a, b_ = oracle.rle_plane(coef, 0), ref.rle_plane(coef, 0)
         assert np.array_equal(a[0], b_[0]) and np.array_equal(a[1], b_[1])
+
+
+@pytest.mark.skipif(not B.have_ref(), reason="oracle/_ref not built (no /root/reference on this box)")
+def test_float_pixel_forward_equals_reference(oracle):
+    # block filled by hand as tests/test_dct.c:46-50 does, from float pixels (incl. outside [0, 255])
+    ref = B.load("ref")
+    rng = np.random.default_rng(12)
+    px = (rng.random((64, 96)) * 300.0 - 20.0).astype(np.float32)
+    for q, adaptive, layout in [(50, 0, 0), (90, 1, 1)]:
+        Q = oracle.quant_table(q)
+        a = oracle.fwd_quant_plane_f32(px, Q, adaptive, layout, nthreads=2)
+        b_ = ref.fwd_quant_plane_f32(px, Q, adaptive, layout)
+        assert np.array_equal(a[0], b_[0]) and np.array_equal(bits(a[1]), bits(b_[1]))
+    ipx = rng.integers(0, 256, size=(32, 64), dtype=np.uint8)
+    Q = oracle.quant_table(50)
+    assert np.array_equal(oracle.fwd_quant_plane_f32(ipx.astype(np.float32), Q)[0], oracle.fwd_quant_plane(ipx, Q)[0])
