@@ -12,8 +12,8 @@ enum { LAYOUT_NATURAL = 0, LAYOUT_ZIGZAG = 1 };
 
 // Device-side counters of one plan (zeroed by the host before each plane call).
 struct Counters {
-    unsigned int wl_count;         // blocks appended to the replay worklist by K1/K2
-    unsigned int pad;
+    unsigned int wl_count;         // blocks appended to the replay worklist by K1/K2; zeroed again by K3's last CTA
+    unsigned int done_ctas;        // K3 CTAs that have finished (for that reset)
     unsigned long long replayed;   // blocks re-done in fp64 by K3 (== min(wl_count, capacity))
     unsigned long long near_ties;  // fp64 values within 1e-9 of a .5 boundary seen by K3
     unsigned long long saturated;  // fp64 quantised values outside int16 (exotic tables only)

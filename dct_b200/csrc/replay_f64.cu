@@ -140,22 +140,31 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
     unsigned ties = 0, sat = 0;
     const unsigned groups_per_grid = gridDim.x * (kReplayThreads / 8);
 
-    // Warp-uniform trip count so that the shuffles below always see the whole warp.  The worklist
-    // entry and the pixel row of the NEXT iteration are fetched before this iteration's arithmetic.
-    auto fetch = [&](unsigned base_, bool &act_, unsigned &b_, PixelRow<F32> &raw_) {
+    // Warp-uniform trip count so that the shuffles below always see the whole warp.  Two dependent
+    // global loads feed an iteration (worklist entry -> pixel row), so the pipeline is two deep: the
+    // entry of iteration i+2 and the pixel row of iteration i+1 are requested before the arithmetic
+    // of iteration i, and each has a whole iteration to arrive.
+    auto fetch_entry = [&](unsigned base_, bool &act_, unsigned &b_) {
         const unsigned slot = base_ + g;
         act_ = slot < count;
         b_ = act_ ? (p.worklist ? p.worklist[slot] : slot) : 0;
+    };
+    auto fetch_row = [&](unsigned b_, PixelRow<F32> &raw_) {
         const unsigned by = b_ / p.bw, bx = b_ - by * p.bw;
         raw_.load(p.px_in, p.pitch, by, bx, r);
     };
     unsigned base = (blockIdx.x * (kReplayThreads / 32) + warp) * 4;
-    bool active = false, active_n = false;
-    unsigned b = 0, b_n = 0;
+    bool active = false, active_n = false, active_nn = false;
+    unsigned b = 0, b_n = 0, b_nn = 0;
     PixelRow<F32> raw{}, raw_n{};
-    if (base < count) fetch(base, active, b, raw);
-    for (; base < count; base += groups_per_grid, active = active_n, b = b_n, raw = raw_n) {
-        if (base + groups_per_grid < count) fetch(base + groups_per_grid, active_n, b_n, raw_n);
+    if (base < count) {
+        fetch_entry(base, active, b);
+        fetch_row(b, raw);
+    }
+    if (base + groups_per_grid < count) fetch_entry(base + groups_per_grid, active_n, b_n);
+    for (; base < count; base += groups_per_grid, active = active_n, b = b_n, raw = raw_n, active_n = active_nn, b_n = b_nn) {
+        if (base + groups_per_grid < count) fetch_row(b_n, raw_n);
+        if (base + 2 * groups_per_grid < count && base + 2 * groups_per_grid > base) fetch_entry(base + 2 * groups_per_grid, active_nn, b_nn);
 
         // per-block variance (adaptive): exact integers, reduced over the 8 rows
         double scale = 1.0;
@@ -253,6 +262,16 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
         if (sat) atomicAdd(&p.ctr->saturated, (unsigned long long)sat);
     }
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
+    // the last CTA to finish empties the worklist for the next K1/K2 on this lane (saves a memset launch);
+    // every CTA has read wl_count long before it gets here
+    __syncthreads();
+    if (threadIdx.x == 0 && p.worklist != nullptr) {
+        __threadfence();
+        if (atomicAdd(&p.ctr->done_ctas, 1u) == gridDim.x - 1) {
+            p.ctr->wl_count = 0;
+            p.ctr->done_ctas = 0;
+        }
+    }
 }
 
 // the reference's dequantised value of natural index k (src/quantization.c:133-151)
@@ -441,6 +460,16 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
     ties = __reduce_add_sync(0xffffffffu, ties);
     if (lane == 0 && ties) atomicAdd(&p.ctr->near_ties, (unsigned long long)ties);
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
+    // the last CTA to finish empties the worklist for the next K1/K2 on this lane (saves a memset launch);
+    // every CTA has read wl_count long before it gets here
+    __syncthreads();
+    if (threadIdx.x == 0 && p.worklist != nullptr) {
+        __threadfence();
+        if (atomicAdd(&p.ctr->done_ctas, 1u) == gridDim.x - 1) {
+            p.ctr->wl_count = 0;
+            p.ctr->done_ctas = 0;
+        }
+    }
 }
 
 // ---- generic n x n single-block kernels (n <= 32): the per-block drop-in API -------------

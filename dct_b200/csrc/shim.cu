@@ -227,7 +227,8 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     int rc = ensure_worklist(ln, nblocks);
     if (rc) return rc;
-    CU_TRY(cudaMemsetAsync(&ln.d_ctr->wl_count, 0, sizeof(unsigned), s));
+    // wl_count is zero here: plan creation zeroes it and K3's last CTA re-zeroes it after every replay
+    if (p->skip_replay) CU_TRY(cudaMemsetAsync(&ln.d_ctr->wl_count, 0, sizeof(unsigned), s));
 
     ReplayParams rp{};
     rp.tab = p->d_tab;
@@ -287,7 +288,8 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
     if (p->adaptive && !d_var) return fail(DCT_CUDA_EINVAL, "adaptive plan needs the per-block variance array");
     int rc = ensure_worklist(ln, nblocks);
     if (rc) return rc;
-    CU_TRY(cudaMemsetAsync(&ln.d_ctr->wl_count, 0, sizeof(unsigned), s));
+    // wl_count is zero here: plan creation zeroes it and K3's last CTA re-zeroes it after every replay
+    if (p->skip_replay) CU_TRY(cudaMemsetAsync(&ln.d_ctr->wl_count, 0, sizeof(unsigned), s));
 
     ReplayParams rp{};
     rp.tab = p->d_tab;
@@ -519,6 +521,10 @@ extern "C" int dct_cuda_stats_fetch(dct_cuda_plan *p, dct_cuda_stats *stats, voi
 extern "C" int dct_cuda_plan_debug_skip_replay(dct_cuda_plan *p, int skip)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    DeviceGuard g(p->device);
+    CU_TRY(cudaDeviceSynchronize());
+    for (int l = 0; l < kLanes; ++l)   // skipped replays leave their worklist count behind
+        CU_TRY(cudaMemset(&p->lane[l].d_ctr->wl_count, 0, 2 * sizeof(unsigned)));
     p->skip_replay = skip != 0;
     return DCT_CUDA_OK;
 }

@@ -119,6 +119,15 @@ def test_reference_test_programs_link_against_libdct_cuda(name):
     assert out == open(os.path.join(GOLDEN, f"ref_{name}.stdout"), "rb").read()
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "c_roundtrip")),
+                    reason="examples/c_roundtrip.c not built (make -C oracle dropin, needs /root/reference)")
+def test_c_host_program_roundtrip():
+    """examples/c_roundtrip.c: a C99 program on the reference's headers + dct_cuda.h + the untouched
+    entropy.c; plane calls == per-block drop-in calls for every block, records feed run_length_encode."""
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "c_roundtrip")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "C ROUNDTRIP PASSED" in r.stdout, r.stdout + r.stderr
+
+
 # ---------------------------------------------------------------------------------------------
 # planes: golden fixtures and oracle comparisons
 # ---------------------------------------------------------------------------------------------
