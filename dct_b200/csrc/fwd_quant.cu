@@ -156,6 +156,12 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
 
     if constexpr (UNIFORM) flag = emax >= p.thr_min;
 
+    // Warp-aggregated reservation of worklist slots.  The atomicAdd is issued here and its result (an
+    // L2 round trip) is consumed after the record stores below, so most of its latency is covered.
+    const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
+    unsigned wl_base = 0;
+    if (ballot != 0 && (int)lane == __ffs(ballot) - 1) wl_base = atomicAdd(&p.ctr->wl_count, (unsigned)__popc(ballot));
+
     // stage: lane-major padded records in shared memory, then 512-byte contiguous warp stores
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -176,14 +182,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
                 stg_stream_u4(dst + j * 32, *reinterpret_cast<const uint4 *>(rd + j * 4 * kStageWordsPerBlock));
     }
 
-    // warp-aggregated append to the replay worklist
-    const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
     if (ballot != 0) {
-        const int leader = __ffs(ballot) - 1;
-        unsigned base = 0;
-        if ((int)lane == leader) base = atomicAdd(&p.ctr->wl_count, (unsigned)__popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (flag && valid) {
+        const unsigned base = __shfl_sync(0xffffffffu, wl_base, __ffs(ballot) - 1);
+        if (ballot & (1u << lane)) {
             const unsigned pos = base + __popc(ballot & ((1u << lane) - 1u));
             if (pos < p.wl_cap) p.worklist[pos] = b;
         }
