@@ -359,7 +359,7 @@ def main():
         "fwd_gpixel_per_s_per_gpu": npx / (fwd_ms / args.steps * 1e-3) / 1e9,
         "inv_gpixel_per_s_per_gpu": npx / (inv_ms / args.steps * 1e-3) / 1e9,
         "e2e": e2e, "gpu_launches": 4 * args.steps,
-        "launches_per_step": "K1 fwd_quant, K3 replay_fwd, K2 dequant_idct, K3 replay_inv (+2 four-byte memsets)",
+        "launches_per_step": "K1 k_fwd_quant_u8, K3 k_replay_fwd, K2 k_dequant_idct_u8, K3 k_replay_inv",
         "roofline": roofline, "clocks": clocks,
         "replay": {"blocks": stats["blocks"], "replayed_blocks": stats["replayed_blocks"],
                    "exact_ties": stats["near_ties"]},

@@ -297,6 +297,7 @@ class Plan:
     def __init__(self, dct_ctx, quant_ctx, device: int = 0):
         self.dct_ctx, self.quant_ctx, self.device = dct_ctx, quant_ctx, device
         self.adaptive = int(quant_ctx.contents.adaptive)
+        self.n = int(dct_ctx.contents.block_size)      # records hold n*n coefficients
         self._h = _plan_create(dct_ctx, quant_ctx, device)
         if not self._h:
             raise DctCudaError(_last_error().decode(errors="replace"))
@@ -322,12 +323,13 @@ class Plan:
             return self.fwd_quant_dev(pixels, layout, coef_out, var_out)
         assert pixels.dtype == np.uint8 and pixels.ndim == 2
         H, W = pixels.shape
-        nb = (H // 8) * (W // 8)
-        if pixels.size == 0 and H % 8 == 0 and W % 8 == 0:   # empty plane: nothing to queue
-            out = (np.empty((0, 64), np.int16), np.empty(0)) if self.adaptive else np.empty((0, 64), np.int16)
+        n = self.n
+        nb = (H // n) * (W // n)
+        if pixels.size == 0 and H % n == 0 and W % n == 0:   # empty plane: nothing to queue
+            out = (np.empty((0, n * n), np.int16), np.empty(0)) if self.adaptive else np.empty((0, n * n), np.int16)
             return (out, Stats().as_dict()) if want_stats else out
         assert pixels.strides[1] == 1
-        coef = coef_out if coef_out is not None else np.empty((nb, 64), dtype=np.int16)
+        coef = coef_out if coef_out is not None else np.empty((nb, n * n), dtype=np.int16)
         var = var_out if var_out is not None else (np.empty(nb, dtype=np.float64) if self.adaptive else None)
         st = Stats()
         _check(_fwd_host(self._h, pixels.ctypes.data, pixels.strides[0], W, H, coef.ctypes.data, layout,
@@ -388,8 +390,8 @@ class Plan:
         import torch
         assert pixels.is_cuda and pixels.dtype == torch.uint8 and pixels.dim() == 2 and pixels.stride(1) == 1
         H, W = pixels.shape
-        nb = (H // 8) * (W // 8)
-        coef = coef_out if coef_out is not None else torch.empty((nb, 64), dtype=torch.int16, device=pixels.device)
+        nb = (H // self.n) * (W // self.n)
+        coef = coef_out if coef_out is not None else torch.empty((nb, self.n * self.n), dtype=torch.int16, device=pixels.device)
         var = var_out
         if self.adaptive and var is None:
             var = torch.empty(nb, dtype=torch.float64, device=pixels.device)

@@ -95,6 +95,25 @@ cudaError_t launch_dequant_idct_u8_f64(const InvParams &p, const ExactTables *d_
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s);
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s);
 
+// K6: plane calls for block sizes other than 8 (generic_n.cu): the reference's arithmetic in fp64
+struct GenericParams {
+    int n;                  // block size, 1..32
+    int blocks_per_cta;     // max(1, 256 / (n*n))
+    int adaptive, layout;
+    uint32_t bw, nblocks;
+    long long pitch;
+    const double *D, *Q, *R;         // n*n each, as the host contexts hold them
+    const int *pos_of_natural;       // n*n: zigzag position of natural index (src/entropy.c:158-178)
+    Counters *ctr;
+    const uint8_t *px_in;
+    int16_t *coef_out;
+    double *var_out;
+    const int16_t *coef_in;
+    const double *var_in;
+    uint8_t *px_out;
+};
+cudaError_t launch_generic_plane(const GenericParams &p, int forward, cudaStream_t s);
+
 // K5: run-length symbols of the records (rle.cu)
 cudaError_t launch_rle_count(const int16_t *d_coef, uint32_t nblocks, uint32_t *d_offsets, uint32_t *d_cta_sums,
                              unsigned long long *d_total, cudaStream_t s);

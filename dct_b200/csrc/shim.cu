@@ -90,6 +90,9 @@ struct dct_cuda_plan {
     const DCTContext *dct = nullptr;
     const QuantContext *quant = nullptr;
     int adaptive = 0;
+    int n = 8;                                  // block size; != 8 routes every plane call to K6 (generic_n.cu)
+    double *d_gen = nullptr;                    // K6 tables: D, Q, R (n*n doubles each)
+    int *d_gen_pos = nullptr;                   // K6: zigzag position of each natural index
     bool exotic = false;                        // tables outside the fast path's proven domain
     ExactTables h_tab;
     ExactTables *d_tab = nullptr;
@@ -127,10 +130,12 @@ int read_tables(dct_cuda_plan *p)
 {
     const DCTContext *d = p->dct;
     const QuantContext *q = p->quant;
-    if (d->block_size != 8 || q->block_size != 8)
-        return fail(DCT_CUDA_EINVAL, "plane kernels are 8x8 only (block_size %d / %d); use the per-block calls",
+    if (d->block_size != q->block_size || d->block_size < 1 || d->block_size > 32)
+        return fail(DCT_CUDA_EINVAL, "block sizes %d / %d: both contexts must use the same size in 1..32",
                     d->block_size, q->block_size);
+    p->n = d->block_size;
     p->adaptive = q->adaptive ? 1 : 0;
+    if (p->n != 8) return DCT_CUDA_OK;   // K6 reads the contexts' tables as they are (upload_generic_tables)
     bool exotic = false;
     for (int i = 0; i < 8; ++i)
         for (int j = 0; j < 8; ++j) {
@@ -186,6 +191,64 @@ int read_tables(dct_cuda_plan *p)
     return DCT_CUDA_OK;
 }
 
+// K6: n*n tables exactly as the host contexts hold them + the zigzag position of every natural index
+// (the scan of src/entropy.c:158-178 for block size n)
+int upload_generic_tables(dct_cuda_plan *p)
+{
+    const int n = p->n, nn = n * n;
+    std::vector<double> tab(3 * (size_t)nn);
+    std::vector<int> pos(nn);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            tab[i * n + j] = p->dct->dct_matrix[i][j];
+            tab[nn + i * n + j] = p->quant->quant_matrix[i][j];
+            tab[2 * nn + i * n + j] = p->quant->dequant_matrix[i][j];
+        }
+    int idx = 0;
+    for (int sum = 0; sum <= 2 * (n - 1); ++sum) {
+        if (sum % 2 == 0) {
+            for (int i = (sum < n) ? sum : n - 1; i >= 0 && (sum - i) < n; --i) pos[i * n + (sum - i)] = idx++;
+        } else {
+            for (int i = (sum < n) ? 0 : sum - n + 1; i < n && (sum - i) >= 0; ++i) pos[i * n + (sum - i)] = idx++;
+        }
+    }
+    if (!p->d_gen) CU_TRY(cudaMalloc(&p->d_gen, 3 * (size_t)nn * sizeof(double)));
+    if (!p->d_gen_pos) CU_TRY(cudaMalloc(&p->d_gen_pos, (size_t)nn * sizeof(int)));
+    CU_TRY(cudaMemcpy(p->d_gen, tab.data(), 3 * (size_t)nn * sizeof(double), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(p->d_gen_pos, pos.data(), (size_t)nn * sizeof(int), cudaMemcpyHostToDevice));
+    return DCT_CUDA_OK;
+}
+
+int queue_generic(dct_cuda_plan *p, Lane &ln, int forward, const uint8_t *px_in, uint8_t *px_out, size_t pitch, int W, int H,
+                  const int16_t *coef_in, int16_t *coef_out, int layout, const double *var_in, double *var_out, cudaStream_t s)
+{
+    const int n = p->n;
+    GenericParams gp{};
+    gp.n = n;
+    gp.blocks_per_cta = std::max(1, 256 / (n * n));
+    gp.adaptive = p->adaptive;
+    gp.layout = layout;
+    gp.bw = (uint32_t)(W / n);
+    gp.nblocks = gp.bw * (uint32_t)(H / n);
+    gp.pitch = (long long)pitch;
+    gp.D = p->d_gen;
+    gp.Q = p->d_gen + n * n;
+    gp.R = p->d_gen + 2 * n * n;
+    gp.pos_of_natural = p->d_gen_pos;
+    gp.ctr = ln.d_ctr;
+    gp.px_in = px_in;
+    gp.px_out = px_out;
+    gp.coef_in = coef_in;
+    gp.coef_out = coef_out;
+    gp.var_in = var_in;
+    gp.var_out = var_out;
+    if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
+    if (!forward && p->adaptive && !var_in) return fail(DCT_CUDA_EINVAL, "adaptive plan needs the per-block variance array");
+    CU_TRY(launch_generic_plane(gp, forward, s));
+    ln.blocks += gp.nblocks;
+    return DCT_CUDA_OK;
+}
+
 int ensure_worklist(Lane &ln, size_t nblocks)
 {
     if (ln.wl_cap >= nblocks) return DCT_CUDA_OK;
@@ -202,14 +265,14 @@ int ensure_worklist(Lane &ln, size_t nblocks)
 }
 
 // `dev`: the pitch is used by the kernels directly (8-byte rows); host planes are re-packed by the copy
-int check_plane(const void *a, const void *b, size_t pitch, int W, int H, bool dev)
+int check_plane(const void *a, const void *b, size_t pitch, int W, int H, bool dev, int n = 8)
 {
     if (!a || !b) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
-    if (W < 0 || H < 0 || (W % 8) || (H % 8))
-        return fail(DCT_CUDA_EINVAL, "width and height must be non-negative multiples of 8 (got %dx%d)", W, H);
-    if (pitch < (size_t)W || (dev && (pitch % 8)))
+    if (W < 0 || H < 0 || (W % n) || (H % n))
+        return fail(DCT_CUDA_EINVAL, "width and height must be non-negative multiples of %d (got %dx%d)", n, W, H);
+    if (pitch < (size_t)W || (dev && n == 8 && (pitch % 8)))
         return fail(DCT_CUDA_EINVAL, "pitch %zu must be >= width%s", pitch, dev ? " and a multiple of 8" : "");
-    if ((uint64_t)(W / 8) * (uint64_t)(H / 8) > 0xFFFFFFF0ull) return fail(DCT_CUDA_EINVAL, "too many blocks");
+    if ((uint64_t)(W / n) * (uint64_t)(H / n) > 0xFFFFFFF0ull) return fail(DCT_CUDA_EINVAL, "too many blocks");
     return DCT_CUDA_OK;
 }
 
@@ -218,6 +281,10 @@ int check_plane(const void *a, const void *b, size_t pitch, int W, int H, bool d
 int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int W, int H, int16_t *d_coef,
               int layout, double *d_var, cudaStream_t s, int elem = 1)
 {
+    if (p->n != 8) {
+        if (elem != 1) return fail(DCT_CUDA_EINVAL, "float pixel tiles are 8x8 only");
+        return queue_generic(p, ln, 1, d_px, nullptr, pitch, W, H, nullptr, d_coef, layout, nullptr, p->adaptive ? d_var : nullptr, s);
+    }
     const uint32_t bw = W / 8, nblocks = bw * (uint32_t)(H / 8);
     if (nblocks == 0) return DCT_CUDA_OK;
     if (((uintptr_t)d_px % (elem == 4 ? 16 : 8)) || ((uintptr_t)d_coef % 16))
@@ -280,6 +347,8 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
 int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, int layout, const double *d_var,
               uint8_t *d_px, size_t pitch, cudaStream_t s)
 {
+    if (p->n != 8)
+        return queue_generic(p, ln, 0, nullptr, d_px, pitch, W, H, d_coef, nullptr, layout, p->adaptive ? d_var : nullptr, nullptr, s);
     const uint32_t bw = W / 8, nblocks = bw * (uint32_t)(H / 8);
     if (nblocks == 0) return DCT_CUDA_OK;
     if (((uintptr_t)d_px % 8) || ((uintptr_t)d_coef % 16))
@@ -337,19 +406,21 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
     return DCT_CUDA_OK;
 }
 
-int ensure_strip_buffers(dct_cuda_plan *p, Lane &ln, size_t blocks, int elem = 1)
+// device strip buffers of one lane, sized in pixels: `pixels * elem` bytes of pixels, 2 bytes of record per
+// pixel, one variance per block
+int ensure_strip_buffers(dct_cuda_plan *p, Lane &ln, size_t pixels, int elem = 1)
 {
-    blocks *= (size_t)elem;   // the pixel buffer is sized in 64-byte units: float tiles need four per block
-    if (ln.cap_blocks >= blocks) return DCT_CUDA_OK;
+    const size_t need = pixels * (size_t)elem;
+    if (ln.cap_blocks >= need) return DCT_CUDA_OK;
     CU_TRY(cudaStreamSynchronize(ln.stream));
     if (ln.d_px) cudaFree(ln.d_px);
     if (ln.d_coef) cudaFree(ln.d_coef);
     if (ln.d_var) cudaFree(ln.d_var);
     ln.d_px = nullptr, ln.d_coef = nullptr, ln.d_var = nullptr, ln.cap_blocks = 0;
-    CU_TRY(cudaMalloc(&ln.d_px, blocks * 64));
-    CU_TRY(cudaMalloc(&ln.d_coef, blocks * 128));
-    if (p->adaptive) CU_TRY(cudaMalloc(&ln.d_var, blocks * sizeof(double)));
-    ln.cap_blocks = blocks;
+    CU_TRY(cudaMalloc(&ln.d_px, need));
+    CU_TRY(cudaMalloc(&ln.d_coef, need * 2));
+    if (p->adaptive) CU_TRY(cudaMalloc(&ln.d_var, (need / ((size_t)p->n * p->n) + 1) * sizeof(double)));
+    ln.cap_blocks = need;
     return DCT_CUDA_OK;
 }
 
@@ -403,6 +474,7 @@ extern "C" dct_cuda_plan *dct_cuda_plan_create(const DCTContext *dct, const Quan
     auto init = [&]() -> int {
         int rc = read_tables(p);
         if (rc) return rc;
+        if (p->n != 8 && (rc = upload_generic_tables(p))) return rc;
         CU_TRY(cudaMalloc(&p->d_tab, sizeof(ExactTables)));
         CU_TRY(cudaMemcpy(p->d_tab, &p->h_tab, sizeof(ExactTables), cudaMemcpyHostToDevice));
         CU_TRY(cudaMallocHost(&p->h_ctr, kLanes * sizeof(Counters)));
@@ -427,6 +499,7 @@ extern "C" int dct_cuda_plan_refresh(dct_cuda_plan *p)
     CU_TRY(cudaDeviceSynchronize());
     int rc = read_tables(p);
     if (rc) return rc;
+    if (p->n != 8) return upload_generic_tables(p);
     CU_TRY(cudaMemcpy(p->d_tab, &p->h_tab, sizeof(ExactTables), cudaMemcpyHostToDevice));
     return DCT_CUDA_OK;
 }
@@ -445,6 +518,8 @@ extern "C" void dct_cuda_plan_destroy(dct_cuda_plan *p)
         if (ln.d_var) cudaFree(ln.d_var);
         if (ln.stream) cudaStreamDestroy(ln.stream);
     }
+    if (p->d_gen) cudaFree(p->d_gen);
+    if (p->d_gen_pos) cudaFree(p->d_gen_pos);
     if (p->d_rle_sums) cudaFree(p->d_rle_sums);
     if (p->d_rle_total) cudaFree(p->d_rle_total);
     if (p->d_tab) cudaFree(p->d_tab);
@@ -461,7 +536,7 @@ extern "C" int dct_cuda_fwd_quant_u8_dev(dct_cuda_plan *p, const uint8_t *d_px, 
                                          int16_t *d_coef, int layout, double *d_var, void *stream)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
-    int rc = check_plane(d_px, d_coef, pitch, W, H, true);
+    int rc = check_plane(d_px, d_coef, pitch, W, H, true, p->n);
     if (rc) return rc;
     DeviceGuard g(p->device);
     return queue_fwd(p, p->lane[0], d_px, pitch, W, H, d_coef, layout, d_var, (cudaStream_t)stream);
@@ -471,6 +546,7 @@ extern "C" int dct_cuda_fwd_quant_f32_dev(dct_cuda_plan *p, const float *d_px, s
                                           int16_t *d_coef, int layout, void *stream)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    if (p->n != 8) return fail(DCT_CUDA_EINVAL, "float pixel tiles are 8x8 only");
     int rc = check_plane(d_px, d_coef, pitch_bytes / 4, W, H, false);
     if (rc) return rc;
     if (pitch_bytes % 16) return fail(DCT_CUDA_EINVAL, "float planes need a pitch that is a multiple of 16 bytes");
@@ -482,7 +558,7 @@ extern "C" int dct_cuda_dequant_idct_u8_dev(dct_cuda_plan *p, const int16_t *d_c
                                             const double *d_var, uint8_t *d_px, size_t pitch, void *stream)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
-    int rc = check_plane(d_px, d_coef, pitch, W, H, true);
+    int rc = check_plane(d_px, d_coef, pitch, W, H, true, p->n);
     if (rc) return rc;
     DeviceGuard g(p->device);
     return queue_inv(p, p->lane[0], d_coef, W, H, layout, d_var, d_px, pitch, (cudaStream_t)stream);
@@ -568,12 +644,12 @@ extern "C" int dct_cuda_profile_fetch(dct_cuda_plan *p, double *fwd_ms, int *fwd
 // ------------------------------------------------------------------------------------------
 // host planes: strips of block rows through a kLanes-deep H2D / kernel / D2H pipeline
 // ------------------------------------------------------------------------------------------
-static int strip_rows(int W, int H)
+static int strip_rows(int W, int H, int n = 8)
 {
-    const size_t bw = (size_t)W / 8;
+    const size_t bw = (size_t)W / n;
     if (bw == 0 || H == 0) return 0;
-    size_t rows = std::max<size_t>(1, kStripPixels / (bw * 64));            // block rows per strip
-    const size_t total = (size_t)H / 8;
+    size_t rows = std::max<size_t>(1, kStripPixels / (bw * n * n));         // block rows per strip
+    const size_t total = (size_t)H / n;
     // at least kLanes strips when the plane is big enough to be worth overlapping
     if (total >= (size_t)kLanes * 4) rows = std::min(rows, (total + kLanes - 1) / kLanes);
     return (int)std::min(rows, total);
@@ -583,25 +659,26 @@ static int fwd_host_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int
                           double *var, int elem)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
-    int rc = check_plane(px, coef, pitch / elem, W, H, false);
+    const int n = p->n, nn = n * n;
+    int rc = check_plane(px, coef, pitch / elem, W, H, false, n);
     if (rc) return rc;
     if (elem == 4 && p->adaptive) return fail(DCT_CUDA_EINVAL, "float pixel tiles are supported for non-adaptive plans only");
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     DeviceGuard g(p->device);
-    const int bw = W / 8, total_rows = H / 8, rows = strip_rows(W, H);
+    const int bw = W / n, total_rows = H / n, rows = strip_rows(W, H, n);
     if (rows > 0) {
         for (int l = 0; l < kLanes; ++l)
-            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw, elem))) return rc;
+            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw * nn, elem))) return rc;
         int idx = 0;
         const size_t row_bytes = (size_t)W * elem;
         for (int r0 = 0; r0 < total_rows; r0 += rows, ++idx) {
             Lane &ln = p->lane[idx % kLanes];
             const int nr = std::min(rows, total_rows - r0);
             const size_t nb = (size_t)nr * bw, b0 = (size_t)r0 * bw;
-            CU_TRY(cudaMemcpy2DAsync(ln.d_px, row_bytes, px + (size_t)r0 * 8 * pitch, pitch, row_bytes, (size_t)nr * 8,
+            CU_TRY(cudaMemcpy2DAsync(ln.d_px, row_bytes, px + (size_t)r0 * n * pitch, pitch, row_bytes, (size_t)nr * n,
                                      cudaMemcpyHostToDevice, ln.stream));
-            if ((rc = queue_fwd(p, ln, ln.d_px, row_bytes, W, nr * 8, ln.d_coef, layout, ln.d_var, ln.stream, elem))) return rc;
-            CU_TRY(cudaMemcpyAsync(coef + b0 * 64, ln.d_coef, nb * 128, cudaMemcpyDeviceToHost, ln.stream));
+            if ((rc = queue_fwd(p, ln, ln.d_px, row_bytes, W, nr * n, ln.d_coef, layout, ln.d_var, ln.stream, elem))) return rc;
+            CU_TRY(cudaMemcpyAsync(coef + b0 * nn, ln.d_coef, nb * nn * 2, cudaMemcpyDeviceToHost, ln.stream));
             if (p->adaptive && var)
                 CU_TRY(cudaMemcpyAsync(var + b0, ln.d_var, nb * sizeof(double), cudaMemcpyDeviceToHost, ln.stream));
         }
@@ -646,25 +723,26 @@ extern "C" int dct_cuda_dequant_idct_u8_async(dct_cuda_plan *p, const int16_t *c
                                               const double *var, uint8_t *px, size_t pitch)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
-    int rc = check_plane(px, coef, pitch, W, H, false);
+    const int n = p->n, nn = n * n;
+    int rc = check_plane(px, coef, pitch, W, H, false, n);
     if (rc) return rc;
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     if (p->adaptive && !var) return fail(DCT_CUDA_EINVAL, "adaptive plan needs the per-block variance array");
     DeviceGuard g(p->device);
-    const int bw = W / 8, total_rows = H / 8, rows = strip_rows(W, H);
+    const int bw = W / n, total_rows = H / n, rows = strip_rows(W, H, n);
     if (rows > 0) {
         for (int l = 0; l < kLanes; ++l)
-            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw))) return rc;
+            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw * nn))) return rc;
         int idx = 0;
         for (int r0 = 0; r0 < total_rows; r0 += rows, ++idx) {
             Lane &ln = p->lane[idx % kLanes];
             const int nr = std::min(rows, total_rows - r0);
             const size_t nb = (size_t)nr * bw, b0 = (size_t)r0 * bw;
-            CU_TRY(cudaMemcpyAsync(ln.d_coef, coef + b0 * 64, nb * 128, cudaMemcpyHostToDevice, ln.stream));
+            CU_TRY(cudaMemcpyAsync(ln.d_coef, coef + b0 * nn, nb * nn * 2, cudaMemcpyHostToDevice, ln.stream));
             if (p->adaptive)
                 CU_TRY(cudaMemcpyAsync(ln.d_var, var + b0, nb * sizeof(double), cudaMemcpyHostToDevice, ln.stream));
-            if ((rc = queue_inv(p, ln, ln.d_coef, W, nr * 8, layout, ln.d_var, ln.d_px, (size_t)W, ln.stream))) return rc;
-            CU_TRY(cudaMemcpy2DAsync(px + (size_t)r0 * 8 * pitch, pitch, ln.d_px, (size_t)W, (size_t)W, (size_t)nr * 8,
+            if ((rc = queue_inv(p, ln, ln.d_coef, W, nr * n, layout, ln.d_var, ln.d_px, (size_t)W, ln.stream))) return rc;
+            CU_TRY(cudaMemcpy2DAsync(px + (size_t)r0 * n * pitch, pitch, ln.d_px, (size_t)W, (size_t)W, (size_t)nr * n,
                                      cudaMemcpyDeviceToHost, ln.stream));
         }
     }
@@ -714,6 +792,8 @@ extern "C" int dct_cuda_fwd_quant_u8_multi(dct_cuda_plan *const *plans, int n, c
 {
     int rc = check_plane(px, coef, pitch, W, H, false);
     if (rc) return rc;
+    for (int g = 0; plans && g < n; ++g)
+        if (plans[g] && plans[g]->n != 8) return fail(DCT_CUDA_EINVAL, "the multi-GPU helpers are 8x8 only");
     const size_t bw = (size_t)W / 8;
     return run_sharded(plans, n, H, stats, [&](dct_cuda_plan *p, int r0, int r1, dct_cuda_stats *st) {
         return dct_cuda_fwd_quant_u8(p, px + (size_t)r0 * 8 * pitch, pitch, W, (r1 - r0) * 8, coef + (size_t)r0 * bw * 64,
@@ -727,6 +807,8 @@ extern "C" int dct_cuda_dequant_idct_u8_multi(dct_cuda_plan *const *plans, int n
 {
     int rc = check_plane(px, coef, pitch, W, H, false);
     if (rc) return rc;
+    for (int g = 0; plans && g < n; ++g)
+        if (plans[g] && plans[g]->n != 8) return fail(DCT_CUDA_EINVAL, "the multi-GPU helpers are 8x8 only");
     const size_t bw = (size_t)W / 8;
     return run_sharded(plans, n, H, stats, [&](dct_cuda_plan *p, int r0, int r1, dct_cuda_stats *st) {
         return dct_cuda_dequant_idct_u8(p, coef + (size_t)r0 * bw * 64, W, (r1 - r0) * 8, layout,
@@ -741,6 +823,7 @@ extern "C" int dct_cuda_rle_count_dev(dct_cuda_plan *p, const int16_t *d_coef, s
                                       uint64_t *total_symbols, void *stream)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    if (p->n != 8) return fail(DCT_CUDA_EINVAL, "run-length symbols are implemented for 8x8 records only");
     if ((nblocks && !d_coef) || !d_offsets) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
     if (nblocks > (1u << 26)) return fail(DCT_CUDA_EINVAL, "at most 2^26 records per call (32-bit symbol offsets)");
     if ((uintptr_t)d_coef % 16) return fail(DCT_CUDA_EINVAL, "coefficients must be 16-byte aligned");

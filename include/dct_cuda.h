@@ -29,6 +29,11 @@
  *                 reference passes as `block_variance`), written by the forward call and read
  *                 by the inverse call.
  *
+ * Block sizes other than 8 (any block_size <= 32, both contexts alike) are accepted by the same calls:
+ * records then hold n*n coefficients, W and H must be multiples of n, and the arithmetic is the
+ * reference's fp64 loops (bit-identical, not a throughput path).  Float tiles, run-length symbols and
+ * the multi-GPU helpers are 8x8 only.
+ *
  * A dct_cuda_plan binds a (DCTContext, QuantContext) pair to one GPU: it uploads the host-made
  * fp64 tables, derives the fp32 multipliers and error bands, and owns the replay worklist.
  * Plans are cheap; use one per host thread / stream.  All functions return 0 or a negative

@@ -70,6 +70,10 @@ class CpuChecker:
           _P_U8, C.c_size_t, C.c_int, _P_U64)
         f("fwd_quant_plane_f32", C.c_int, C.POINTER(C.c_float), C.c_size_t, C.c_int, C.c_int, _P_D, C.c_int, C.c_int, _P_I16,
           _P_D, C.c_int, _P_U64)
+        f("fwd_quant_plane_n", C.c_int, C.c_int, _P_U8, C.c_size_t, C.c_int, C.c_int, _P_D, C.c_int, C.c_int, _P_I16,
+          _P_D, C.c_int, _P_U64)
+        f("dequant_idct_plane_n", C.c_int, C.c_int, _P_I16, C.c_int, C.c_int, _P_D, _P_D, C.c_int, C.c_int, _P_D,
+          _P_U8, C.c_size_t, C.c_int, _P_U64)
         f("rle_plane", C.c_size_t, _P_I16, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int32))
         if prefix == "orc_":
             self.lib.orc_fill_xorshift.argtypes = [_P_U8, C.c_size_t, C.c_uint64, C.c_int, C.c_int]
@@ -197,6 +201,32 @@ class CpuChecker:
         if rc != 0:
             raise ValueError(f"{self.prefix}dequant_idct_plane rc={rc}")
         return px, int(ties.value)
+
+    def fwd_quant_plane_n(self, n, px, Q, adaptive=0, layout=NATURAL, nthreads=1):
+        """Any block size n: px (H, W) uint8 -> (coef int16 [nblocks, n*n], var [nblocks])."""
+        px = np.ascontiguousarray(px, dtype=np.uint8)
+        H, W = px.shape
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        nb = (H // n) * (W // n)
+        coef = np.zeros((nb, n * n), dtype=np.int16)
+        var = np.zeros(nb, dtype=np.float64)
+        rc = self._fwd_quant_plane_n(n, px.ctypes.data_as(_P_U8), W, W, H, _dp(Q), int(adaptive), int(layout),
+                                     coef.ctypes.data_as(_P_I16), _dp(var), int(nthreads), None)
+        if rc != 0:
+            raise ValueError(f"{self.prefix}fwd_quant_plane_n rc={rc}")
+        return coef, var
+
+    def dequant_idct_plane_n(self, n, coef, W, H, Q, adaptive=0, layout=NATURAL, var=None, nthreads=1):
+        coef = np.ascontiguousarray(coef, dtype=np.int16)
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        R = self.dequant_table(Q)
+        px = np.zeros((H, W), dtype=np.uint8)
+        vptr = _dp(np.ascontiguousarray(var, dtype=np.float64)) if var is not None else None
+        rc = self._dequant_idct_plane_n(n, coef.ctypes.data_as(_P_I16), W, H, _dp(Q), _dp(R), int(adaptive), int(layout),
+                                        vptr, px.ctypes.data_as(_P_U8), W, int(nthreads), None)
+        if rc != 0:
+            raise ValueError(f"{self.prefix}dequant_idct_plane_n rc={rc}")
+        return px
 
     def rle_plane(self, coef, layout=NATURAL):
         """-> (offsets uint32 [nblocks+1], symbols int32 [total, 2] = (value, run_length))."""

@@ -189,6 +189,7 @@ static int near_half(double a)
 }
 
 typedef struct {
+    int n;   /* block size, 0 = 8 */
     int dir; /* 0 fwd, 1 inv */
     const float *pxf_in; /* forward from float pixels when non-NULL (pitch in floats) */
     const uint8_t *px_in;
@@ -210,71 +211,74 @@ typedef struct {
 static void *plane_worker(void *arg)
 {
     job_t *jb = (job_t *)arg;
-    const int bw = jb->W / 8;
-    double blk[64], c[64], adj[64];
-    int q[64];
+    const int n = jb->n, nn = n * n;
+    const int bw = jb->W / n;
+    double *blk = malloc(sizeof(double) * nn), *c = malloc(sizeof(double) * nn), *adj = malloc(sizeof(double) * nn);
+    int *q = malloc(sizeof(int) * nn);
     uint64_t ties = 0;
     for (int by = jb->row0; by < jb->row1; ++by) {
         for (int bx = 0; bx < bw; ++bx) {
             size_t b = (size_t)by * bw + bx;
             if (jb->dir == 0) {
                 /* src/dct.c:109-120 */
-                for (int i = 0; i < 8; ++i)
-                    for (int j = 0; j < 8; ++j) {
-                        const size_t at = ((size_t)by * 8 + i) * jb->pitch + (size_t)bx * 8 + j;
+                for (int i = 0; i < n; ++i)
+                    for (int j = 0; j < n; ++j) {
+                        const size_t at = ((size_t)by * n + i) * jb->pitch + (size_t)bx * n + j;
                         /* float tiles: the block a caller fills by hand, tests/test_dct.c:46-50 */
-                        blk[i * 8 + j] = (jb->pxf_in ? (double)jb->pxf_in[at] : (double)jb->px_in[at]) - 128.0;
+                        blk[i * n + j] = (jb->pxf_in ? (double)jb->pxf_in[at] : (double)jb->px_in[at]) - 128.0;
                     }
-                orc_dct_forward(8, jb->D, blk, c);
+                orc_dct_forward(n, jb->D, blk, c);
                 double var = 0.0;
                 const double *m = jb->Q;
                 if (jb->adaptive) {
-                    var = orc_block_variance(8, blk); /* tests/test_entropy.c:315 */
+                    var = orc_block_variance(n, blk); /* tests/test_entropy.c:315 */
                     if (jb->var_out) jb->var_out[b] = var;
-                    orc_adjust_table(8, jb->Q, var, 1, adj);
+                    orc_adjust_table(n, jb->Q, var, 1, adj);
                     m = adj;
                 }
-                orc_quantize(8, jb->Q, jb->adaptive, c, q, var);
-                for (int k = 0; k < 64; ++k) ties += near_half(c[k] / m[k]);
-                int16_t *dst = jb->coef_out + b * 64;
+                orc_quantize(n, jb->Q, jb->adaptive, c, q, var);
+                for (int k = 0; k < nn; ++k) ties += near_half(c[k] / m[k]);
+                int16_t *dst = jb->coef_out + b * nn;
                 if (jb->layout == ORC_LAYOUT_ZIGZAG)
-                    for (int k = 0; k < 64; ++k) dst[k] = (int16_t)q[jb->zz[k]];
+                    for (int k = 0; k < nn; ++k) dst[k] = (int16_t)q[jb->zz[k]];
                 else
-                    for (int k = 0; k < 64; ++k) dst[k] = (int16_t)q[k];
+                    for (int k = 0; k < nn; ++k) dst[k] = (int16_t)q[k];
             } else {
-                const int16_t *src = jb->coef_in + b * 64;
+                const int16_t *src = jb->coef_in + b * nn;
                 if (jb->layout == ORC_LAYOUT_ZIGZAG) {
-                    for (int k = 0; k < 64; ++k) q[jb->zz[k]] = src[k]; /* src/entropy.c:183-210 */
+                    for (int k = 0; k < nn; ++k) q[jb->zz[k]] = src[k]; /* src/entropy.c:183-210 */
                 } else {
-                    for (int k = 0; k < 64; ++k) q[k] = src[k];
+                    for (int k = 0; k < nn; ++k) q[k] = src[k];
                 }
                 double var = (jb->adaptive && jb->var_in) ? jb->var_in[b] : 0.0;
-                orc_dequantize(8, jb->Q, jb->R, jb->adaptive, q, c, var);
-                orc_dct_inverse(8, jb->D, c, blk);
-                for (int i = 0; i < 8; ++i)
-                    for (int j = 0; j < 8; ++j) {
-                        double v = blk[i * 8 + j] + 128.0;
+                orc_dequantize(n, jb->Q, jb->R, jb->adaptive, q, c, var);
+                orc_dct_inverse(n, jb->D, c, blk);
+                for (int i = 0; i < n; ++i)
+                    for (int j = 0; j < n; ++j) {
+                        double v = blk[i * n + j] + 128.0;
                         ties += near_half(v);
                         double r = round(v);
                         if (r < 0.0) r = 0.0;
                         if (r > 255.0) r = 255.0;
-                        jb->px_out[((size_t)by * 8 + i) * jb->pitch + (size_t)bx * 8 + j] = (uint8_t)r;
+                        jb->px_out[((size_t)by * n + i) * jb->pitch + (size_t)bx * n + j] = (uint8_t)r;
                     }
             }
         }
     }
+    free(blk), free(c), free(adj), free(q);
     jb->ties = ties;
     return NULL;
 }
 
 static int run_plane(job_t *proto, int nthreads, uint64_t *near_ties)
 {
-    if (proto->W <= 0 || proto->H <= 0 || proto->W % 8 || proto->H % 8) return -1;
-    double D[64];
-    int zz[64];
-    orc_dct_matrix(8, D);
-    orc_zigzag_order(8, zz);
-    const int bh = proto->H / 8;
+    const int n = proto->n ? proto->n : 8;
+    if (n < 1 || n > 32 || proto->W <= 0 || proto->H <= 0 || proto->W % n || proto->H % n) return -1;
+    double D[32 * 32];
+    int zz[32 * 32];
+    orc_dct_matrix(n, D);
+    orc_zigzag_order(n, zz);
+    const int bh = proto->H / n;
     if (nthreads < 1) nthreads = 1;
     if (nthreads > bh) nthreads = bh;
     if (nthreads > 256) nthreads = 256;
@@ -282,6 +286,7 @@ static int run_plane(job_t *proto, int nthreads, uint64_t *near_ties)
     pthread_t th[256];
     for (int t = 0; t < nthreads; ++t) {
         jobs[t] = *proto;
+        jobs[t].n = n;
         jobs[t].D = D;
         jobs[t].zz = zz;
         jobs[t].row0 = (int)((long long)bh * t / nthreads);
@@ -297,6 +302,47 @@ static int run_plane(job_t *proto, int nthreads, uint64_t *near_ties)
     for (int t = 0; t < nthreads; ++t) ties += jobs[t].ties;
     if (near_ties) *near_ties = ties;
     return 0;
+}
+
+/* generic block size n (the reference's block_size argument, include/dct.h:34): tables are n*n */
+int orc_fwd_quant_plane_n(int n, const uint8_t *px, size_t pitch, int W, int H, const double *Q, int adaptive,
+                          int layout, int16_t *coef, double *var_out, int nthreads, uint64_t *near_ties)
+{
+    job_t jb;
+    memset(&jb, 0, sizeof jb);
+    jb.n = n;
+    jb.dir = 0;
+    jb.px_in = px;
+    jb.pitch = pitch;
+    jb.W = W;
+    jb.H = H;
+    jb.Q = Q;
+    jb.adaptive = adaptive;
+    jb.layout = layout;
+    jb.coef_out = coef;
+    jb.var_out = var_out;
+    return run_plane(&jb, nthreads, near_ties);
+}
+
+int orc_dequant_idct_plane_n(int n, const int16_t *coef, int W, int H, const double *Q, const double *R,
+                             int adaptive, int layout, const double *var_in, uint8_t *px, size_t pitch,
+                             int nthreads, uint64_t *near_ties)
+{
+    job_t jb;
+    memset(&jb, 0, sizeof jb);
+    jb.n = n;
+    jb.dir = 1;
+    jb.coef_in = coef;
+    jb.px_out = px;
+    jb.pitch = pitch;
+    jb.W = W;
+    jb.H = H;
+    jb.Q = Q;
+    jb.R = R;
+    jb.adaptive = adaptive;
+    jb.layout = layout;
+    jb.var_in = var_in;
+    return run_plane(&jb, nthreads, near_ties);
 }
 
 int orc_fwd_quant_plane(const uint8_t *px, size_t pitch, int W, int H, const double *Q, int adaptive,

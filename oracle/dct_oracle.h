@@ -50,6 +50,13 @@ int orc_dequant_idct_plane(const int16_t *coef, int W, int H, const double *Q, c
                            int adaptive, int layout, const double *var_in, uint8_t *px, size_t pitch,
                            int nthreads, uint64_t *near_ties);
 
+/* ---- the same for any block size n <= 32 (tables n*n, records n*n int16, W and H multiples of n) ---- */
+int orc_fwd_quant_plane_n(int n, const uint8_t *px, size_t pitch, int W, int H, const double *Q, int adaptive,
+                          int layout, int16_t *coef, double *var_out, int nthreads, uint64_t *near_ties);
+int orc_dequant_idct_plane_n(int n, const int16_t *coef, int W, int H, const double *Q, const double *R,
+                             int adaptive, int layout, const double *var_in, uint8_t *px, size_t pitch,
+                             int nthreads, uint64_t *near_ties);
+
 /* ---- run-length symbols (value, run) per record; returns the total, offsets has nblocks+1 entries ---- */
 size_t orc_rle_plane(const int16_t *coef, size_t nblocks, int layout, uint32_t *offsets, int32_t *symbols);
 

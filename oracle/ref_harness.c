@@ -370,3 +370,87 @@ int ref_fwd_quant_plane_f32(const float *px, size_t pitch_floats, int W, int H, 
     quant_free(qc);
     return 0;
 }
+
+/* ---- any block size n: the reference's block functions with block_size = n ---- */
+int ref_fwd_quant_plane_n(int n, const uint8_t *px, size_t pitch, int W, int H, const double *Q, int adaptive,
+                          int layout, int16_t *coef, double *var_out, int nthreads, uint64_t *near_ties)
+{
+    (void)nthreads;
+    if (n < 1 || W <= 0 || H <= 0 || W % n || H % n) return -1;
+    DCTContext *d = dct_init(n);
+    QuantContext *qc = ctx_with_table(n, Q, adaptive);
+    double **c = alloc_array(n, n);
+    int **q = alloc_int_array(n, n);
+    int *zz = (int *)malloc(sizeof(int) * n * n);
+    const int bw = W / n;
+    for (int by = 0; by < H / n; ++by)
+        for (int bx = 0; bx < bw; ++bx) {
+            const size_t b = (size_t)by * bw + bx;
+            unsigned char *strip = (unsigned char *)px + (size_t)by * n * pitch;
+            double **blk = create_block_from_pixels(strip, (int)pitch, 0, bx * n, n);
+            dct_forward(d, blk, c);
+            double var = 0.0;
+            if (adaptive) {
+                var = calculate_block_variance(blk, n);
+                if (var_out) var_out[b] = var;
+            }
+            quantize(qc, c, q, var);
+            int16_t *dst = coef + b * n * n;
+            if (layout == 1) {
+                block_to_zigzag(q, zz, n);
+                for (int k = 0; k < n * n; ++k) dst[k] = (int16_t)zz[k];
+            } else {
+                for (int k = 0; k < n * n; ++k) dst[k] = (int16_t)q[k / n][k % n];
+            }
+            free_array(blk, n);
+        }
+    if (near_ties) *near_ties = 0;
+    free(zz);
+    free_array(c, n);
+    free_int_array(q, n);
+    dct_free(d);
+    quant_free(qc);
+    return 0;
+}
+
+int ref_dequant_idct_plane_n(int n, const int16_t *coef, int W, int H, const double *Q, const double *R,
+                             int adaptive, int layout, const double *var_in, uint8_t *px, size_t pitch,
+                             int nthreads, uint64_t *near_ties)
+{
+    (void)R;
+    (void)nthreads;
+    if (n < 1 || W <= 0 || H <= 0 || W % n || H % n) return -1;
+    DCTContext *d = dct_init(n);
+    QuantContext *qc = ctx_with_table(n, Q, adaptive);
+    double **c = alloc_array(n, n), **o = alloc_array(n, n);
+    int **q = alloc_int_array(n, n);
+    int *zz = (int *)malloc(sizeof(int) * n * n);
+    const int bw = W / n;
+    for (int by = 0; by < H / n; ++by)
+        for (int bx = 0; bx < bw; ++bx) {
+            const size_t b = (size_t)by * bw + bx;
+            const int16_t *src = coef + b * n * n;
+            if (layout == 1) {
+                for (int k = 0; k < n * n; ++k) zz[k] = src[k];
+                zigzag_to_block(zz, q, n);
+            } else {
+                for (int k = 0; k < n * n; ++k) q[k / n][k % n] = src[k];
+            }
+            dequantize(qc, q, c, (adaptive && var_in) ? var_in[b] : 0.0);
+            dct_inverse(d, c, o);
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) {
+                    double v = round(o[i][j] + 128.0);
+                    v = v < 0.0 ? 0.0 : (v > 255.0 ? 255.0 : v);
+                    px[((size_t)by * n + i) * pitch + (size_t)bx * n + j] = (uint8_t)v;
+                }
+        }
+    if (near_ties) *near_ties = 0;
+    free(zz);
+    free_array(c, n);
+    free_array(o, n);
+    free_int_array(q, n);
+    dct_free(d);
+    quant_free(qc);
+    return 0;
+}

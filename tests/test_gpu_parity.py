@@ -336,7 +336,7 @@ def test_bad_arguments_are_rejected(api, oracle, torch):
         assert np.array_equal(cx.plan.fwd_quant(odd), want)
     d4 = api.dct_init(4)
     q8 = api.quant_init(8, 50, 0)
-    with pytest.raises(api.DctCudaError, match="8x8 only"):
+    with pytest.raises(api.DctCudaError, match="same size"):
         api.Plan(d4, q8)
     api.dct_free(d4), api.quant_free(q8)
 
@@ -494,6 +494,38 @@ def test_config5_full_image_block_row_shards_and_quality_sweep(api, oracle, torc
     del big
     torch.cuda.empty_cache()
 
+
+
+@pytest.mark.parametrize("n", [4, 16, 32])
+@pytest.mark.parametrize("adaptive,layout", [(0, 0), (1, 1)])
+def test_generic_block_sizes_on_the_plane_calls(api, oracle, torch, n, adaptive, layout):
+    """block_size != 8 (custom distance-based table, src/quantization.c:78-96) through the
+    plane calls.  fp64 in the reference's operation order, so bit-exact by construction."""
+    rng = np.random.default_rng(n * 10 + adaptive)
+    H, W = 6 * n, 10 * n + 0
+    px = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
+    Q = oracle.quant_table(60, n)
+    want_c, want_v = oracle.fwd_quant_plane_n(n, px, Q, adaptive, layout, nthreads=2)
+    want_p = oracle.dequant_idct_plane_n(n, want_c, W, H, Q, adaptive, layout, want_v)
+    d, q = api.dct_init(n), api.quant_init(n, 60, adaptive)
+    plan = api.Plan(d, q)
+    try:
+        out, st = plan.fwd_quant(px, layout, want_stats=True)
+        coef, var = out if adaptive else (out, None)
+        assert coef.shape == (60, n * n) and np.array_equal(coef, want_c)
+        if adaptive:
+            assert np.array_equal(bits(var), bits(want_v))
+        rec = plan.dequant_idct(coef, W, H, layout, var)
+        assert np.array_equal(rec, want_p)
+        dev = plan.fwd_quant_dev(torch.from_numpy(px).cuda(), layout)
+        dev = dev[0] if adaptive else dev
+        assert np.array_equal(dev.cpu().numpy(), want_c)
+        assert st["blocks"] == 60 and st["saturated"] == 0
+        with pytest.raises(api.DctCudaError, match="multiples of"):
+            plan.fwd_quant(np.zeros((n + 1, n), np.uint8))
+    finally:
+        plan.close()
+        api.dct_free(d), api.quant_free(q)
 
 
 @pytest.mark.parametrize("quality,layout", [(50, 0), (90, 1), (100, 0)])
