@@ -194,3 +194,23 @@ def test_float_pixel_forward_equals_reference(oracle):
     ipx = rng.integers(0, 256, size=(32, 64), dtype=np.uint8)
     Q = oracle.quant_table(50)
     assert np.array_equal(oracle.fwd_quant_plane_f32(ipx.astype(np.float32), Q)[0], oracle.fwd_quant_plane(ipx, Q)[0])
+
+
+@pytest.mark.skipif(not B.have_ref(), reason="oracle/_ref not built (no /root/reference on this box)")
+@pytest.mark.parametrize("n", [4, 8, 16, 32])
+def test_generic_block_size_planes_equal_reference(oracle, n):
+    # the reference's block functions with block_size = n, custom table src/quantization.c:78-96
+    ref = B.load("ref")
+    rng = np.random.default_rng(n)
+    px = rng.integers(0, 256, size=(2 * n, 3 * n), dtype=np.uint8)
+    Q = oracle.quant_table(60, n)
+    for adaptive, layout in ((0, 0), (1, 1)):
+        c1, v1 = oracle.fwd_quant_plane_n(n, px, Q, adaptive, layout, nthreads=2)
+        c2, v2 = ref.fwd_quant_plane_n(n, px, Q, adaptive, layout)
+        assert np.array_equal(c1, c2) and np.array_equal(bits(v1), bits(v2))
+        p1 = oracle.dequant_idct_plane_n(n, c1, 3 * n, 2 * n, Q, adaptive, layout, v1)
+        p2 = ref.dequant_idct_plane_n(n, c2, 3 * n, 2 * n, Q, adaptive, layout, v2)
+        assert np.array_equal(p1, p2)
+    if n == 8:
+        c8, _, _ = oracle.fwd_quant_plane(px, Q)
+        assert np.array_equal(c8, oracle.fwd_quant_plane_n(8, px, Q)[0])
