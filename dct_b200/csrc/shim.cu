@@ -180,7 +180,7 @@ int read_tables(dct_cuda_plan *p)
     // 2 * 64 * max_band of all blocks.  Worth it while that stays below ~1 %.
     p->thr_min = p->thr[0];
     for (int k = 1; k < 64; ++k) p->thr_min = std::min(p->thr_min, p->thr[k]);
-    p->uniform_band = (!exotic && (0.5 - (double)p->thr_min) * 128.0 < 0.01) ? 1 : 0;
+    p->uniform_band = (!exotic && (0.5 - (double)p->thr_min) * 128.0 < 0.02) ? 1 : 0;
     memcpy(p->h_tab.r32, p->r, sizeof p->r);
     memcpy(p->h_tab.thr32, p->thr, sizeof p->thr);
     memcpy(p->h_tab.thr32f, p->thr_f32, sizeof p->thr_f32);
