@@ -23,7 +23,6 @@ template <> struct Ops<float> {
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float mul(float a, float c) { return __fmul_rn(a, c); }
     static __device__ __forceinline__ float fma(float a, float c, float b) { return __fmaf_rn(a, c, b); }
-    static __device__ __forceinline__ float fms(float a, float c, float b) { return __fmaf_rn(a, c, -b); }
 };
 
 template <> struct Ops<double> {
@@ -31,10 +30,46 @@ template <> struct Ops<double> {
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     static __device__ __forceinline__ double mul(double a, double c) { return __dmul_rn(a, c); }
     static __device__ __forceinline__ double fma(double a, double c, double b) { return __fma_rn(a, c, b); }
-    static __device__ __forceinline__ double fms(double a, double c, double b) { return __fma_rn(a, c, -b); }
 };
 
-// exact reals; T(...) rounds them once, exactly as numpy.float32(c) does in the model
+// Two independent fp32 lanes per instruction (sm_100 FADD2 / FMUL2 / FFMA2): each lane is an ordinary
+// IEEE round-to-nearest operation, so a packed butterfly is bit-identical, lane by lane, to the scalar
+// one -- it just needs half the issue slots.  Constants are broadcast immediates.
+template <> struct Ops<float2> {
+    static __device__ __forceinline__ float2 add(float2 a, float2 b)
+    {
+        float2 r;
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(b)));
+        return r;
+    }
+    static __device__ __forceinline__ float2 sub(float2 a, float2 b)
+    {
+        float2 r;
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(b)));
+        return r;
+    }
+    static __device__ __forceinline__ float2 mul(float2 a, float2 c)
+    {
+        float2 r;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(c)));
+        return r;
+    }
+    static __device__ __forceinline__ float2 fma(float2 a, float2 c, float2 b)
+    {
+        float2 r;
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long &>(r)) : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(c)), "l"(reinterpret_cast<unsigned long long &>(b)));
+        return r;
+    }
+};
+
+// a butterfly constant in the arithmetic type: rounded once to fp32 (as numpy.float32(c) in the model),
+// broadcast to both lanes of a packed pair
+template <typename T> __device__ __forceinline__ T cst(double c);
+template <> __device__ __forceinline__ float cst<float>(double c) { return (float)c; }
+template <> __device__ __forceinline__ double cst<double>(double c) { return c; }
+template <> __device__ __forceinline__ float2 cst<float2>(double c) { return make_float2((float)c, (float)c); }
+
+// exact reals; cst<T>(...) rounds them once, exactly as numpy.float32(c) does in the model
 #define DCTB_C4    0.70710678118654752440
 #define DCTB_C382  0.38268343236508977173
 #define DCTB_C541  0.54119610014619698440
@@ -55,12 +90,12 @@ __device__ __forceinline__ void fdct8_tail(T *x, T s07, T s16, T s25, T s34, T d
     x[0 * S] = O::add(e0, e1);
     x[4 * S] = O::sub(e0, e1);
     const T t = O::add(e2, e3);
-    x[2 * S] = O::fma(t, T(DCTB_C4), e3);
-    x[6 * S] = O::fma(t, T(-DCTB_C4), e3);
+    x[2 * S] = O::fma(t, cst<T>(DCTB_C4), e3);
+    x[6 * S] = O::fma(t, cst<T>(-DCTB_C4), e3);
     const T a = O::add(d34, d25), b = O::add(d25, d16), c = O::add(d16, d07);
-    const T z5 = O::mul(O::sub(a, c), T(DCTB_C382));
-    const T z2 = O::fma(a, T(DCTB_C541), z5), z4 = O::fma(c, T(DCTB_C1306), z5);
-    const T z11 = O::fma(b, T(DCTB_C4), d07), z13 = O::fma(b, T(-DCTB_C4), d07);
+    const T z5 = O::mul(O::sub(a, c), cst<T>(DCTB_C382));
+    const T z2 = O::fma(a, cst<T>(DCTB_C541), z5), z4 = O::fma(c, cst<T>(DCTB_C1306), z5);
+    const T z11 = O::fma(b, cst<T>(DCTB_C4), d07), z13 = O::fma(b, cst<T>(-DCTB_C4), d07);
     x[5 * S] = O::add(z13, z2);
     x[3 * S] = O::sub(z13, z2);
     x[1 * S] = O::add(z11, z4);
@@ -86,25 +121,27 @@ __device__ __forceinline__ void idct8(T *v)
     using O = Ops<T>;
     const T t10 = O::add(v[0 * S], v[4 * S]), t11 = O::sub(v[0 * S], v[4 * S]);
     const T t13 = O::add(v[2 * S], v[6 * S]);
-    const T t12 = O::fms(O::sub(v[2 * S], v[6 * S]), T(DCTB_SQRT2), t13);
+    // t12n = -(d*sqrt2 - t13): the negated form needs no operand negation; round-to-nearest is symmetric,
+    // so t11 - t12n == t11 + t12 bit for bit (the model's fms(d, sqrt2, t13))
+    const T t12n = O::fma(O::sub(v[2 * S], v[6 * S]), cst<T>(-DCTB_SQRT2), t13);
     const T e0 = O::add(t10, t13), e3 = O::sub(t10, t13);
-    const T e1 = O::add(t11, t12), e2 = O::sub(t11, t12);
+    const T e1 = O::sub(t11, t12n), e2 = O::add(t11, t12n);
     const T z13 = O::add(v[5 * S], v[3 * S]), z10 = O::sub(v[5 * S], v[3 * S]);
     const T z11 = O::add(v[1 * S], v[7 * S]), z12 = O::sub(v[1 * S], v[7 * S]);
     const T t7 = O::add(z11, z13);
     const T zd = O::sub(z11, z13);
-    const T z5 = O::mul(O::add(z10, z12), T(DCTB_C1847));
-    const T t10o = O::fma(z12, T(-DCTB_C1082), z5);
-    const T t12o = O::fma(z10, T(-DCTB_C2613), z5);
+    const T z5 = O::mul(O::add(z10, z12), cst<T>(DCTB_C1847));
+    const T t10o = O::fma(z12, cst<T>(-DCTB_C1082), z5);
+    const T t12o = O::fma(z10, cst<T>(-DCTB_C2613), z5);
     const T t6 = O::sub(t12o, t7);
-    const T t5 = O::fms(zd, T(DCTB_SQRT2), t6);
-    const T t4 = O::sub(t10o, t5);
+    const T t5n = O::fma(zd, cst<T>(-DCTB_SQRT2), t6);   // -(zd*sqrt2 - t6), same remark
+    const T t4 = O::add(t10o, t5n);
     v[0 * S] = O::add(e0, t7);
     v[1 * S] = O::add(e1, t6);
-    v[2 * S] = O::add(e2, t5);
+    v[2 * S] = O::sub(e2, t5n);
     v[3 * S] = O::add(e3, t4);
     v[4 * S] = O::sub(e3, t4);
-    v[5 * S] = O::sub(e2, t5);
+    v[5 * S] = O::add(e2, t5n);
     v[6 * S] = O::sub(e1, t6);
     v[7 * S] = O::sub(e0, t7);
 }

@@ -39,6 +39,31 @@ __device__ __forceinline__ void fdct8_row_from_bytes(float *x, uint2 raw)
 // float pixel -> centred sample on the fast path (the reference's (double)p - 128.0 is exact; this rounds once)
 __device__ __forceinline__ float centre_float_pixel(float p) { return __fsub_rn(p, 128.0f); }
 
+// The same row transform for TWO rows at once, one per lane of the packed operations: x[k] = (row A, row B).
+__device__ __forceinline__ void fdct8_rowpair_from_bytes(float2 *x, uint2 a, uint2 b)
+{
+    using O = Ops<float2>;
+    const float2 kBias2 = make_float2(-16777472.0f, -16777472.0f);   // -2 * (2^23 + 128)
+    const float2 m0 = make_float2(byte_to_magic<0>(a.x), byte_to_magic<0>(b.x)), m1 = make_float2(byte_to_magic<1>(a.x), byte_to_magic<1>(b.x)),
+                 m2 = make_float2(byte_to_magic<2>(a.x), byte_to_magic<2>(b.x)), m3 = make_float2(byte_to_magic<3>(a.x), byte_to_magic<3>(b.x)),
+                 m4 = make_float2(byte_to_magic<0>(a.y), byte_to_magic<0>(b.y)), m5 = make_float2(byte_to_magic<1>(a.y), byte_to_magic<1>(b.y)),
+                 m6 = make_float2(byte_to_magic<2>(a.y), byte_to_magic<2>(b.y)), m7 = make_float2(byte_to_magic<3>(a.y), byte_to_magic<3>(b.y));
+    const float2 s07 = O::add(O::add(m0, kBias2), m7), d07 = O::sub(m0, m7);
+    const float2 s16 = O::add(O::add(m1, kBias2), m6), d16 = O::sub(m1, m6);
+    const float2 s25 = O::add(O::add(m2, kBias2), m5), d25 = O::sub(m2, m5);
+    const float2 s34 = O::add(O::add(m3, kBias2), m4), d34 = O::sub(m3, m4);
+    fdct8_tail<float2, 1>(x, s07, s16, s25, s34, d07, d16, d25, d34);
+}
+
+// packed quantise-and-residual of two coefficients: bit-identical per lane to quant_residual
+__device__ __forceinline__ void quant_residual2(float2 c, float2 r, float2 &t, float2 &e)
+{
+    using O = Ops<float2>;
+    const float2 magic = make_float2(kMagic, kMagic);
+    t = O::fma(c, r, magic);
+    e = O::fma(c, r, O::sub(magic, t));     // magic - t == -(t - magic) exactly
+}
+
 // sum and sum of squares of the centred samples of one 8-pixel row, exact (packed byte dot products)
 __device__ __forceinline__ void row_moments(uint2 raw, int &isum, int &isq)
 {
@@ -88,6 +113,15 @@ __device__ __forceinline__ void pixel_residual(float x, float &t, float &e)
 {
     t = __fadd_rn(x, kMagic128);
     e = __fsub_rn(x, __fsub_rn(t, kMagic128));
+}
+
+// packed pixel-and-residual of two samples: bit-identical per lane to pixel_residual
+__device__ __forceinline__ void pixel_residual2(float2 x, float2 &t, float2 &e)
+{
+    using O = Ops<float2>;
+    const float2 magic = make_float2(kMagic128, kMagic128);
+    t = O::add(x, magic);
+    e = O::add(x, O::sub(magic, t));        // x - (t - magic)
 }
 
 // K2's threshold from the accumulated bound: |fp32 pixel - exact pixel| <= 2^-24 * bound (derive_bands.py);

@@ -70,28 +70,23 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
     // Each lane copies the 8 rows of its own block (lane-private data: no cross-lane hazard on the
     // input).  The lane's block coordinates advance by a fixed step from tile to tile, so the only
     // integer divisions of the kernel are the two below.
-    const uint32_t step = tile_stride * 32;                     // blocks between consecutive tiles of a warp
-    const uint32_t step_q = step / p.bw, step_r = step - step_q * p.bw;
-    const long long step_bytes = ((long long)step_q * p.pitch + step_r) * 8;
-    const long long wrap_bytes = (p.pitch - (long long)p.bw) * 8;   // bx -= bw, by += 1
-    uint32_t nb = tile * 32 + lane;                             // block the next issue() fetches
-    uint32_t nbx;
-    const uint8_t *nsrc;
+    // (step_q, step_r) = divmod(32 * tiles per grid sweep, blocks per row) comes from the host with the launch.
+    uint32_t nby, nbx;                                          // block row / column the next issue() fetches
     {
-        const uint32_t by = nb / p.bw;
-        nbx = nb - by * p.bw;
-        nsrc = p.px + ((long long)by * p.pitch + nbx) * 8;
+        const uint32_t nb = tile * 32 + lane;
+        nby = nb / p.bw;
+        nbx = nb - nby * p.bw;
     }
     auto issue = [&](int stage) {
-        if (nb < p.nblocks) {   // lanes past the end keep stale (but valid u8) data and store nothing
+        if (nby * p.bw + nbx < p.nblocks) {   // lanes past the end keep stale (but valid u8) data and store nothing
+            const uint8_t *src = p.px + ((long long)nby * p.pitch + nbx) * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cp_async_8(in_addr + stage * (kInWordsPerStage * 4) + i * 256, nsrc + i * p.pitch);
+            for (int i = 0; i < 8; ++i) cp_async_8(in_addr + stage * (kInWordsPerStage * 4) + i * 256, src + i * p.pitch);
         }
         cp_async_commit();
-        nb += step;
-        nbx += step_r;
-        nsrc += step_bytes;
-        if (nbx >= p.bw) nbx -= p.bw, nsrc += wrap_bytes;
+        nbx += p.step_r;
+        nby += p.step_q;
+        if (nbx >= p.bw) nbx -= p.bw, ++nby;
     };
 
     int stage = 0;
@@ -112,7 +107,6 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
     for (int i = 0; i < 8; ++i)
         raw[i] = *reinterpret_cast<const uint2 *>(wsm + stage * kInWordsPerStage + i * 64 + lane * 2);
 
-    float v[64];
     float inv_s = 1.0f;
     if constexpr (ADAPTIVE) {
         // Sum and sum of squares of the centred samples, as exact integers: packed byte dot products.
@@ -127,31 +121,51 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
         inv_s = adaptive_inv_scale(num);
     }
 
-    // rows (X * D^T), then columns (D * temp): same order as src/dct.c:57-74
+    // Rows (X * D^T), then columns (D * temp): same order as src/dct.c:57-74.  Both passes run on packed
+    // pairs (FADD2 / FFMA2: two fp32 lanes per instruction, half the issue slots).  The row pass takes rows
+    // a and 7-a in its two lanes -- exactly the pairs the first butterfly stage of the column pass adds and
+    // subtracts, so that stage is 64 scalar FADDs on the two halves of a register pair, whose results are
+    // written straight into (column 2b, column 2b+1) pairs: the 2x2 re-pairing costs no instruction.
+    float2 rp[4][8];                         // rp[a][k] = (T[a][k], T[7-a][k])
 #pragma unroll
-    for (int i = 0; i < 8; ++i) fdct8_row_from_bytes(&v[8 * i], raw[i]);
+    for (int a = 0; a < 4; ++a) fdct8_rowpair_from_bytes(rp[a], raw[a], raw[7 - a]);
+    float2 cp[4][8];                         // cp[b][u] = scaled coefficients (u, 2b) and (u, 2b+1)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) fdct8<float, 8>(&v[j]);
+    for (int b = 0; b < 4; ++b) {
+        float2 s[4], d[4];                   // s[a] = T[a] + T[7-a], d[a] = T[a] - T[7-a] for columns 2b, 2b+1
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            s[a] = make_float2(__fadd_rn(rp[a][2 * b].x, rp[a][2 * b].y), __fadd_rn(rp[a][2 * b + 1].x, rp[a][2 * b + 1].y));
+            d[a] = make_float2(__fsub_rn(rp[a][2 * b].x, rp[a][2 * b].y), __fsub_rn(rp[a][2 * b + 1].x, rp[a][2 * b + 1].y));
+        }
+        fdct8_tail<float2, 1>(cp[b], s[0], s[1], s[2], s[3], d[0], d[1], d[2], d[3]);
+    }
 
-    // quantise: t = c*r + 1.5*2^23 holds round(c*r) in its low mantissa bits;
-    // residual e = c*r - round(c*r) (one rounding); |e| >= 0.5 - band  => replay
-    uint32_t w[32];
+    // Quantise in natural pairs (k, k+1) = cp[(k%8)/2][k/8]: t = c*r + 1.5*2^23 holds round(c*r) in its low
+    // mantissa bits; residual e = c*r - round(c*r) (one rounding); |e| >= 0.5 - band  => replay.
+    // t overwrites cp; the layout (natural / zigzag) is applied when the int16 halves are packed.
     bool flag = false;
     float emax = 0.0f;
     static_for<0, 32>([&](auto M) {
-        constexpr int m = decltype(M)::value;
-        constexpr int k0 = storage_to_natural<LAYOUT>(2 * m), k1 = storage_to_natural<LAYOUT>(2 * m + 1);
-        float r0 = p.r[k0], r1 = p.r[k1];
+        constexpr int m = decltype(M)::value;      // natural pair: coefficients 2m, 2m+1
+        constexpr int u = m >> 2, b = m & 3;
+        float2 r2 = reinterpret_cast<const float2 *>(p.r)[m];
         if constexpr (ADAPTIVE) {
-            if (k0 != 0) r0 = __fmul_rn(r0, inv_s);   // DC keeps the unscaled table entry
-            r1 = __fmul_rn(r1, inv_s);
+            if (m == 0) r2.y = __fmul_rn(r2.y, inv_s);       // DC keeps the unscaled table entry
+            else r2 = Ops<float2>::mul(r2, make_float2(inv_s, inv_s));
         }
-        float t0, t1, e0, e1;
-        quant_residual(v[k0], r0, t0, e0);
-        quant_residual(v[k1], r1, t1, e1);
-        if constexpr (UNIFORM) emax = fmaxf(fmaxf(emax, fabsf(e0)), fabsf(e1));   // FMNMX3
-        else flag |= (fabsf(e0) >= p.thr[k0]) | (fabsf(e1) >= p.thr[k1]);
-        w[m] = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x5410);   // lo16(t0) | lo16(t1) << 16
+        float2 t2, e2;
+        quant_residual2(cp[b][u], r2, t2, e2);
+        if constexpr (UNIFORM) emax = fmaxf(fmaxf(emax, fabsf(e2.x)), fabsf(e2.y));   // FMNMX3
+        else flag |= (fabsf(e2.x) >= p.thr[2 * m]) | (fabsf(e2.y) >= p.thr[2 * m + 1]);
+        cp[b][u] = t2;
+    });
+    uint32_t w[32];
+    static_for<0, 32>([&](auto M) {
+        constexpr int m = decltype(M)::value;      // storage pair
+        constexpr int k0 = storage_to_natural<LAYOUT>(2 * m), k1 = storage_to_natural<LAYOUT>(2 * m + 1);
+        const float2 a2 = cp[(k0 & 7) >> 1][k0 >> 3], b2 = cp[(k1 & 7) >> 1][k1 >> 3];
+        w[m] = __byte_perm(__float_as_uint((k0 & 1) ? a2.y : a2.x), __float_as_uint((k1 & 1) ? b2.y : b2.x), 0x5410);
     });
 
     if constexpr (UNIFORM) flag = emax >= p.thr_min;
@@ -314,7 +328,12 @@ template <typename K> static cudaError_t launch_persistent(K kernel, const FwdPa
         if (getenv("DCT_CUDA_DEBUG")) fprintf(stderr, "libdct_cuda: %s: %d CTAs/SM, %d B smem\n", __FILE__, n, kSmemBytes);
     }
     const unsigned resident = (unsigned)sm_count() * (unsigned)per_sm;
-    kernel<<<want < resident ? want : resident, kThreads, kSmemBytes, s>>>(p);
+    const unsigned grid = want < resident ? want : resident;
+    FwdParams q = p;
+    const unsigned step = grid * kWarps * 32;                  // blocks between consecutive tiles of a warp
+    q.step_q = step / p.bw;
+    q.step_r = step - q.step_q * p.bw;
+    kernel<<<grid, kThreads, kSmemBytes, s>>>(q);
     return cudaGetLastError();
 }
 

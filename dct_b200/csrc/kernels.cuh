@@ -48,6 +48,7 @@ struct FwdParams {
     Counters *ctr;
     float r[64];           // natural index: 1 / (Q_k * 8 a_u a_v)
     float thr[64];         // natural index: 0.5 - band_k ; |residual| >= thr  => replay in fp64
+    uint32_t step_q, step_r;   // divmod(blocks between a warp's consecutive tiles, bw): set by the launcher
     float thr_min;         // min_k thr[k]: the single threshold of the uniform-band variant
     int uniform_band;      // 1: test max_k |residual| >= thr_min (cheaper, slightly more replays)
 };

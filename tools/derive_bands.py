@@ -60,9 +60,9 @@ def idct8(o, v):
     """Scaled inverse 8-point DCT, 30 operations; inputs pre-multiplied by AAN[k]/sqrt(8)."""
     t10, t11 = o.add(v[0], v[4]), o.sub(v[0], v[4])
     t13 = o.add(v[2], v[6])
-    t12 = o.fms(o.sub(v[2], v[6]), SQRT2, t13)          # d*sqrt2 - t13
+    t12n = o.fma(o.sub(v[2], v[6]), -SQRT2, t13)        # t13 - d*sqrt2  (= -t12; no operand negation needed)
     e0, e3 = o.add(t10, t13), o.sub(t10, t13)
-    e1, e2 = o.add(t11, t12), o.sub(t11, t12)
+    e1, e2 = o.sub(t11, t12n), o.add(t11, t12n)
     z13, z10 = o.add(v[5], v[3]), o.sub(v[5], v[3])
     z11, z12 = o.add(v[1], v[7]), o.sub(v[1], v[7])
     t7 = o.add(z11, z13)
@@ -71,10 +71,10 @@ def idct8(o, v):
     t10o = o.fma(z12, -C1082, z5)
     t12o = o.fma(z10, -C2613, z5)
     t6 = o.sub(t12o, t7)
-    t5 = o.fms(zd, SQRT2, t6)                            # zd*sqrt2 - t6
-    t4 = o.sub(t10o, t5)
-    return [o.add(e0, t7), o.add(e1, t6), o.add(e2, t5), o.add(e3, t4),
-            o.sub(e3, t4), o.sub(e2, t5), o.sub(e1, t6), o.sub(e0, t7)]
+    t5n = o.fma(zd, -SQRT2, t6)                          # t6 - zd*sqrt2  (= -t5)
+    t4 = o.add(t10o, t5n)
+    return [o.add(e0, t7), o.add(e1, t6), o.sub(e2, t5n), o.add(e3, t4),
+            o.sub(e3, t4), o.add(e2, t5n), o.sub(e1, t6), o.sub(e0, t7)]
 
 
 # ---------------------------------------------------------------- numeric back-ends

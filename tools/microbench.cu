@@ -55,6 +55,23 @@ template <typename Op> __global__ void __launch_bounds__(256) kd(double *out, do
     for (int i = 0; i < 8; ++i) acc += r[i];
     if (acc == 0.12345) out[threadIdx.x] = acc;
 }
+template <typename Op> __global__ void __launch_bounds__(256) kl(unsigned long long *out, unsigned long long seed)
+{
+    unsigned long long r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = seed + threadIdx.x * 8 + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Op::run(r[i]);
+    }
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc ^= r[i];
+    if (acc == 0x12345678ull) out[threadIdx.x] = acc;
+}
+struct OpFFMA2 { static __device__ __forceinline__ void run(unsigned long long &r) { asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(r)); } };
+struct OpFADD2 { static __device__ __forceinline__ void run(unsigned long long &r) { asm volatile("add.rn.f32x2 %0, %0, %0;" : "+l"(r)); } };
+struct OpFMUL2 { static __device__ __forceinline__ void run(unsigned long long &r) { asm volatile("mul.rn.f32x2 %0, %0, %0;" : "+l"(r)); } };
 struct OpDFMA { static __device__ __forceinline__ void run(double &r) { asm volatile("fma.rn.f64 %0, %0, %0, %0;" : "+d"(r)); } };
 struct OpDADD { static __device__ __forceinline__ void run(double &r) { asm volatile("add.rn.f64 %0, %0, %0;" : "+d"(r)); } };
 struct OpDMUL { static __device__ __forceinline__ void run(double &r) { asm volatile("mul.rn.f64 %0, %0, %0;" : "+d"(r)); } };
@@ -95,5 +112,8 @@ int main()
     T(OpFMNMX3); T(OpFMNMX); T(OpVIMN); T(OpH2F); T(OpHADD2); T(OpFSETP); T(OpSHFL);
 #define TD(OP) timeit(#OP, [&] { kd<OP><<<grid, block>>>(outd, 1.0); }, 8.0 * ITERS / 4, sms, mhz)
     TD(OpDFMA); TD(OpDADD); TD(OpDMUL);
+    printf("-- packed fp32x2 (each instruction = 2 fp32 operations per lane; rate below counts instructions)\n");
+#define TL(OP) timeit(#OP, [&] { kl<OP><<<grid, block>>>((unsigned long long *)outd, 1ull); }, 8.0 * ITERS, sms, mhz)
+    TL(OpFFMA2); TL(OpFADD2); TL(OpFMUL2);
     return 0;
 }
