@@ -114,20 +114,18 @@ __device__ __forceinline__ void fdct8(T *x)
     fdct8_tail<T, S>(x, s07, s16, s25, s34, d07, d16, d25, d34);
 }
 
-// v[k*S] pre-multiplied by a_k / sqrt(8); transformed in place to the 8 spatial samples.
+// Everything after the first stage of the inverse flowgraph.  Inputs (from v[k], pre-multiplied by
+// a_k / sqrt(8)):  t10 = v0+v4, t11 = v0-v4, t13 = v2+v6, d26 = v2-v6, z13 = v5+v3, z10 = v5-v3,
+// z11 = v1+v7, z12 = v1-v7.  Writes the 8 spatial samples to out[k*S].
 template <typename T, int S>
-__device__ __forceinline__ void idct8(T *v)
+__device__ __forceinline__ void idct8_tail(T *out, T t10, T t11, T t13, T d26, T z13, T z10, T z11, T z12)
 {
     using O = Ops<T>;
-    const T t10 = O::add(v[0 * S], v[4 * S]), t11 = O::sub(v[0 * S], v[4 * S]);
-    const T t13 = O::add(v[2 * S], v[6 * S]);
-    // t12n = -(d*sqrt2 - t13): the negated form needs no operand negation; round-to-nearest is symmetric,
+    // t12n = -(d26*sqrt2 - t13): the negated form needs no operand negation; round-to-nearest is symmetric,
     // so t11 - t12n == t11 + t12 bit for bit (the model's fms(d, sqrt2, t13))
-    const T t12n = O::fma(O::sub(v[2 * S], v[6 * S]), cst<T>(-DCTB_SQRT2), t13);
+    const T t12n = O::fma(d26, cst<T>(-DCTB_SQRT2), t13);
     const T e0 = O::add(t10, t13), e3 = O::sub(t10, t13);
     const T e1 = O::sub(t11, t12n), e2 = O::add(t11, t12n);
-    const T z13 = O::add(v[5 * S], v[3 * S]), z10 = O::sub(v[5 * S], v[3 * S]);
-    const T z11 = O::add(v[1 * S], v[7 * S]), z12 = O::sub(v[1 * S], v[7 * S]);
     const T t7 = O::add(z11, z13);
     const T zd = O::sub(z11, z13);
     const T z5 = O::mul(O::add(z10, z12), cst<T>(DCTB_C1847));
@@ -136,14 +134,26 @@ __device__ __forceinline__ void idct8(T *v)
     const T t6 = O::sub(t12o, t7);
     const T t5n = O::fma(zd, cst<T>(-DCTB_SQRT2), t6);   // -(zd*sqrt2 - t6), same remark
     const T t4 = O::add(t10o, t5n);
-    v[0 * S] = O::add(e0, t7);
-    v[1 * S] = O::add(e1, t6);
-    v[2 * S] = O::sub(e2, t5n);
-    v[3 * S] = O::add(e3, t4);
-    v[4 * S] = O::sub(e3, t4);
-    v[5 * S] = O::add(e2, t5n);
-    v[6 * S] = O::sub(e1, t6);
-    v[7 * S] = O::sub(e0, t7);
+    out[0 * S] = O::add(e0, t7);
+    out[1 * S] = O::add(e1, t6);
+    out[2 * S] = O::sub(e2, t5n);
+    out[3 * S] = O::add(e3, t4);
+    out[4 * S] = O::sub(e3, t4);
+    out[5 * S] = O::add(e2, t5n);
+    out[6 * S] = O::sub(e1, t6);
+    out[7 * S] = O::sub(e0, t7);
+}
+
+// v[k*S] pre-multiplied by a_k / sqrt(8); transformed in place to the 8 spatial samples (30 operations).
+template <typename T, int S>
+__device__ __forceinline__ void idct8(T *v)
+{
+    using O = Ops<T>;
+    const T t10 = O::add(v[0 * S], v[4 * S]), t11 = O::sub(v[0 * S], v[4 * S]);
+    const T t13 = O::add(v[2 * S], v[6 * S]), d26 = O::sub(v[2 * S], v[6 * S]);
+    const T z13 = O::add(v[5 * S], v[3 * S]), z10 = O::sub(v[5 * S], v[3 * S]);
+    const T z11 = O::add(v[1 * S], v[7 * S]), z12 = O::sub(v[1 * S], v[7 * S]);
+    idct8_tail<T, S>(v, t10, t11, t13, d26, z13, z10, z11, z12);
 }
 
 // zigzag position -> natural index (8i+j); the scan of src/entropy.c:158-178 for N = 8
