@@ -9,6 +9,7 @@
 // Mapping mirrors K1: one thread per block, a warp owns 32 consecutive records (4 KB, read
 // with 512-byte contiguous LDG.128 through a padded shared-memory stage) and writes a
 // 256-pixel x 8-row tile with 8 STG.64 per lane (256 contiguous bytes per warp instruction).
+// Both butterfly passes and the pixel residuals run on packed fp32 instructions (FADD2 / FFMA2).
 // The fp32 error bound is dynamic here (inputs are arbitrary int16): 2^-24 * sum gain_k |v_k|.
 #include "fast_core.cuh"
 #include "kernels.cuh"

@@ -12,9 +12,11 @@
 // tiles) and every warp runs its own two-stage cp.async pipeline, with no CTA-wide barrier:
 // while a warp transforms tile t, the 2 KB of tile t+1 are already in flight into its second
 // shared-memory stage (a warp LDGSTS instruction covers 256 contiguous bytes).  A lane keeps its
-// block in 64 registers through both butterfly passes (no transpose, no shuffles), quantises with
-// one FFMA per coefficient (round-to-nearest via the 1.5*2^23 trick), checks the fp32 residual
-// against the band, and stores through a padded per-warp stage so that every STG.128 of the warp
+// block in 64 registers through both butterfly passes (no transpose, no shuffles), both passes and
+// the quantisation on sm_100's packed fp32 instructions (FADD2 / FFMA2: two IEEE lanes per
+// instruction, half the issue slots of scalar code, bit-identical results): one FFMA2 quantises two
+// coefficients (round-to-nearest via the 1.5*2^23 trick), the fp32 residual is checked against the
+// band, and the records leave through a padded per-warp stage so that every STG.128 of the warp
 // covers 512 contiguous bytes of the record array.
 // Blocks with a coefficient inside the band go to the worklist and are replayed in fp64 (K3).
 #include <cstdio>
