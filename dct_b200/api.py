@@ -123,6 +123,28 @@ _rle_emit = _sig("dct_cuda_rle_emit_dev", C.c_int, C.c_void_p, C.c_void_p, C.c_s
                  C.c_void_p)
 _rec_to_block = _sig("dct_cuda_record_to_block", None, C.POINTER(C.c_int16), C.c_int, _PP_I)
 _block_to_rec = _sig("dct_cuda_block_to_record", None, _PP_I, C.c_int, C.POINTER(C.c_int16))
+_fwd_edge = _sig("dct_cuda_fwd_quant_u8_edge", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                 C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Stats))
+_inv_edge = _sig("dct_cuda_dequant_idct_u8_edge", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                 C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Stats))
+_pad_edges = _sig("dct_cuda_pad_edges_dev", C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int,
+                  C.c_void_p)
+
+
+class Frame420(C.Structure):  # dct_cuda_frame420
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("y_width", C.c_int), ("y_height", C.c_int),
+                ("c_width", C.c_int), ("c_height", C.c_int)]
+
+
+_frame_geometry = _sig("dct_cuda_frame420_geometry", None, C.c_int, C.c_int, C.POINTER(Frame420))
+_rgb_to_ycc = _sig("dct_cuda_rgb_to_ycbcr420_dev", C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(Frame420),
+                   C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+_ycc_to_rgb = _sig("dct_cuda_ycbcr420_to_rgb_dev", C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                   C.c_size_t, C.POINTER(Frame420), C.c_void_p, C.c_size_t, C.c_void_p)
+_encode_rgb = _sig("dct_cuda_encode_rgb420", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Stats))
+_decode_rgb = _sig("dct_cuda_decode_rgb420", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(Stats))
 _host_alloc = _sig("dct_cuda_host_alloc", C.c_void_p, C.c_size_t)
 _host_free = _sig("dct_cuda_host_free", None, C.c_void_p)
 
@@ -439,6 +461,104 @@ class Plan:
         return st.as_dict()
 
 
+# ---- planar front / back end (not in the reference; conventions in csrc/planar.cu) -------------------
+def frame420_geometry(width: int, height: int) -> Frame420:
+    g = Frame420()
+    _frame_geometry(int(width), int(height), C.byref(g))
+    return g
+
+
+def rgb_to_ycbcr420_dev(rgb, stream=None):
+    """torch cuda uint8 [H, W, 3] -> (y [y_h, y_w], cb, cr [c_h, c_w]) with the edges replicated."""
+    import torch
+    assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.dim() == 3 and rgb.shape[2] == 3 and rgb.stride(2) == 1 \
+        and rgb.stride(1) == 3
+    H, W = rgb.shape[:2]
+    g = frame420_geometry(W, H)
+    y = torch.empty((g.y_height, (g.y_width + 15) // 16 * 16), dtype=torch.uint8, device=rgb.device)[:, :g.y_width]
+    cb = torch.empty((g.c_height, g.c_width), dtype=torch.uint8, device=rgb.device)
+    cr = torch.empty_like(cb)
+    _check(_rgb_to_ycc(rgb.device.index or 0, rgb.data_ptr(), rgb.stride(0), C.byref(g), y.data_ptr(), y.stride(0),
+                       cb.data_ptr(), cr.data_ptr(), cb.stride(0), _stream_ptr(stream)))
+    return y, cb, cr
+
+
+def ycbcr420_to_rgb_dev(y, cb, cr, width, height, rgb_out=None, stream=None):
+    import torch
+    g = frame420_geometry(width, height)
+    assert tuple(y.shape) == (g.y_height, g.y_width) and tuple(cb.shape) == (g.c_height, g.c_width) == tuple(cr.shape)
+    assert cb.stride(0) == cr.stride(0)
+    rgb = rgb_out if rgb_out is not None else _alloc_rgb(height, width, y.device)
+    _check(_ycc_to_rgb(y.device.index or 0, y.data_ptr(), y.stride(0), cb.data_ptr(), cr.data_ptr(), cb.stride(0),
+                       C.byref(g), rgb.data_ptr(), rgb.stride(0), _stream_ptr(stream)))
+    return rgb
+
+
+def _alloc_rgb(height, width, device):
+    """[H, W, 3] uint8 view whose rows start 16-byte aligned (the vector path of the conversion kernels)."""
+    import torch
+    pitch = (width * 3 + 15) // 16 * 16
+    buf = torch.empty((height, pitch), dtype=torch.uint8, device=device)
+    return buf.as_strided((height, width, 3), (pitch, 3, 1))
+
+
+def pad_edges_dev(plane, width, height, stream=None):
+    """Fill plane[:, width:] and plane[height:, :] (torch cuda uint8 [H_pad, W_pad]) by edge replication, in place."""
+    _check(_pad_edges(plane.device.index or 0, plane.data_ptr(), plane.stride(0), int(width), int(height),
+                      plane.shape[1], plane.shape[0], _stream_ptr(stream)))
+    return plane
+
+
+def fwd_quant_edge(plan, pixels, layout=NATURAL, want_stats=False):
+    """Host plane of any size: records for ceil(W/n) x ceil(H/n) blocks, edge blocks completed by replication."""
+    assert pixels.dtype == np.uint8 and pixels.ndim == 2 and (pixels.size == 0 or pixels.strides[1] == 1)
+    H, W = pixels.shape
+    n = plan.n
+    nb = ((H + n - 1) // n) * ((W + n - 1) // n)
+    coef = np.empty((nb, n * n), dtype=np.int16)
+    var = np.empty(nb, dtype=np.float64) if plan.adaptive else None
+    st = Stats()
+    _check(_fwd_edge(plan._h, pixels.ctypes.data, pixels.strides[0], W, H, coef.ctypes.data, layout,
+                     var.ctypes.data if var is not None else None, C.byref(st)))
+    out = (coef, var) if plan.adaptive else coef
+    return (out, st.as_dict()) if want_stats else out
+
+
+def dequant_idct_edge(plan, coef, W, H, layout=NATURAL, var=None, want_stats=False):
+    coef = np.ascontiguousarray(coef, dtype=np.int16)
+    px = np.empty((H, W), dtype=np.uint8)
+    if var is not None:
+        var = np.ascontiguousarray(var, dtype=np.float64)
+    st = Stats()
+    _check(_inv_edge(plan._h, coef.ctypes.data, W, H, layout, var.ctypes.data if var is not None else None,
+                     px.ctypes.data, px.strides[0], C.byref(st)))
+    return (px, st.as_dict()) if want_stats else px
+
+
+def encode_rgb420(luma, chroma, rgb, layout=NATURAL):
+    """Host RGB frame [H, W, 3] uint8 -> (coef_y, coef_cb, coef_cr, stats)."""
+    assert rgb.dtype == np.uint8 and rgb.ndim == 3 and rgb.shape[2] == 3
+    assert rgb.size == 0 or (rgb.strides[2] == 1 and rgb.strides[1] == 3)
+    H, W = rgb.shape[:2]
+    g = frame420_geometry(W, H)
+    ky = np.empty((g.y_width * g.y_height // 64, 64), dtype=np.int16)
+    kcb = np.empty((g.c_width * g.c_height // 64, 64), dtype=np.int16)
+    kcr = np.empty_like(kcb)
+    st = Stats()
+    _check(_encode_rgb(luma._h, chroma._h, rgb.ctypes.data, rgb.strides[0], W, H, ky.ctypes.data, kcb.ctypes.data,
+                       kcr.ctypes.data, layout, C.byref(st)))
+    return ky, kcb, kcr, st.as_dict()
+
+
+def decode_rgb420(luma, chroma, ky, kcb, kcr, W, H, layout=NATURAL):
+    ky, kcb, kcr = (np.ascontiguousarray(k, dtype=np.int16) for k in (ky, kcb, kcr))
+    rgb = np.empty((H, W, 3), dtype=np.uint8)
+    st = Stats()
+    _check(_decode_rgb(luma._h, chroma._h, ky.ctypes.data, kcb.ctypes.data, kcr.ctypes.data, W, H, layout,
+                       rgb.ctypes.data, rgb.strides[0], C.byref(st)))
+    return rgb, st.as_dict()
+
+
 def fwd_quant_multi(plans, pixels, layout=NATURAL):
     """One host plane over several GPUs (block-row ranges, no inter-GPU traffic)."""
     H, W = pixels.shape
@@ -475,4 +595,7 @@ def exported_symbols():
             "dct_cuda_dequant_idct_u8_multi", "dct_cuda_stats_fetch", "dct_cuda_plan_profile", "dct_cuda_plan_debug_skip_replay", "dct_cuda_rle_count_dev",
             "dct_cuda_rle_emit_dev",
             "dct_cuda_profile_fetch", "dct_cuda_record_to_block",
-            "dct_cuda_block_to_record", "dct_cuda_host_alloc", "dct_cuda_host_free"]
+            "dct_cuda_block_to_record", "dct_cuda_host_alloc", "dct_cuda_host_free",
+            "dct_cuda_fwd_quant_u8_edge", "dct_cuda_dequant_idct_u8_edge", "dct_cuda_pad_edges_dev",
+            "dct_cuda_frame420_geometry", "dct_cuda_rgb_to_ycbcr420_dev", "dct_cuda_ycbcr420_to_rgb_dev",
+            "dct_cuda_encode_rgb420", "dct_cuda_decode_rgb420"]

@@ -121,6 +121,21 @@ cudaError_t launch_rle_count(const int16_t *d_coef, uint32_t nblocks, uint32_t *
 cudaError_t launch_rle_emit(const int16_t *d_coef, uint32_t nblocks, int layout, const uint32_t *d_offsets, void *d_symbols,
                             cudaStream_t s);
 
+// planar front / back end (planar.cu): colour conversion with 4:2:0 subsampling, edge completion
+struct PlanarParams {
+    const uint8_t *rgb;        // forward: interleaved R,G,B source
+    uint8_t *rgb_out;          // inverse: destination
+    long long rgb_pitch;
+    int W, H;                  // the image
+    uint8_t *y, *cb, *cr;      // planes (written by the forward kernel, read by the inverse one)
+    long long y_pitch, c_pitch;
+    int y_w, y_h, c_w, c_h;    // padded plane sizes (multiples of the block size)
+    int vec_ok;                // every base pointer / pitch allows the 16-byte path
+};
+cudaError_t launch_rgb_to_ycbcr420(const PlanarParams &p, cudaStream_t s);
+cudaError_t launch_ycbcr420_to_rgb(const PlanarParams &p, cudaStream_t s);
+cudaError_t launch_pad_edges(uint8_t *px, long long pitch, int W, int H, int Wp, int Hp, int elem, cudaStream_t s);
+
 // generic-N single block kernels behind the per-block drop-in API (K4/K6)
 cudaError_t launch_block_dct_f64(int n, const double *d_D, const double *d_in, double *d_out, int inverse,
                                  cudaStream_t s);

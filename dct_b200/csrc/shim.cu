@@ -108,6 +108,9 @@ struct dct_cuda_plan {
     unsigned long long *d_rle_total = nullptr;
     bool force_fp32_inverse = false;            // DCT_CUDA_INV_FP32=1: keep the fp32 inverse for adaptive plans too
     bool skip_replay = false;                   // test hook: leave K1/K2's fast-path values unpatched
+    // whole-frame RGB 4:2:0 calls (luma plan only): device copy of the frame, its planes and records
+    uint8_t *d_frame = nullptr;
+    size_t frame_cap = 0;
 };
 
 namespace {
@@ -273,6 +276,16 @@ int check_plane(const void *a, const void *b, size_t pitch, int W, int H, bool d
     if (pitch < (size_t)W || (dev && n == 8 && (pitch % 8)))
         return fail(DCT_CUDA_EINVAL, "pitch %zu must be >= width%s", pitch, dev ? " and a multiple of 8" : "");
     if ((uint64_t)(W / n) * (uint64_t)(H / n) > 0xFFFFFFF0ull) return fail(DCT_CUDA_EINVAL, "too many blocks");
+    return DCT_CUDA_OK;
+}
+
+// host planes whose sides are not multiples of the block size (the *_edge calls)
+int check_ragged(const void *a, const void *b, size_t pitch, int W, int H, int n)
+{
+    if (W <= 0 || H <= 0) return fail(DCT_CUDA_EINVAL, "width and height must be positive (got %dx%d)", W, H);
+    if (!a || !b) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
+    if (pitch < (size_t)W) return fail(DCT_CUDA_EINVAL, "pitch %zu must be >= width", pitch);
+    if ((uint64_t)((W + n - 1) / n) * (uint64_t)((H + n - 1) / n) > 0xFFFFFFF0ull) return fail(DCT_CUDA_EINVAL, "too many blocks");
     return DCT_CUDA_OK;
 }
 
@@ -523,6 +536,7 @@ extern "C" void dct_cuda_plan_destroy(dct_cuda_plan *p)
     if (p->d_rle_sums) cudaFree(p->d_rle_sums);
     if (p->d_rle_total) cudaFree(p->d_rle_total);
     if (p->d_tab) cudaFree(p->d_tab);
+    if (p->d_frame) cudaFree(p->d_frame);
     if (p->h_ctr) cudaFreeHost(p->h_ctr);
     delete p;
 }
@@ -655,29 +669,35 @@ static int strip_rows(int W, int H, int n = 8)
     return (int)std::min(rows, total);
 }
 
+// `ragged`: W and H are any positive sizes; the strips are completed to whole blocks on the device by
+// replicating the last column / row (planar.cu), so the records cover ceil(W/n) x ceil(H/n) blocks
 static int fwd_host_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H, int16_t *coef, int layout,
-                          double *var, int elem)
+                          double *var, int elem, bool ragged = false)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     const int n = p->n, nn = n * n;
-    int rc = check_plane(px, coef, pitch / elem, W, H, false, n);
+    int rc = ragged ? check_ragged(px, coef, pitch / elem, W, H, n) : check_plane(px, coef, pitch / elem, W, H, false, n);
     if (rc) return rc;
     if (elem == 4 && p->adaptive) return fail(DCT_CUDA_EINVAL, "float pixel tiles are supported for non-adaptive plans only");
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     DeviceGuard g(p->device);
-    const int bw = W / n, total_rows = H / n, rows = strip_rows(W, H, n);
+    const int Wp = (W + n - 1) / n * n, Hp = (H + n - 1) / n * n;   // == W, H unless ragged
+    const int bw = Wp / n, total_rows = Hp / n, rows = strip_rows(Wp, Hp, n);
     if (rows > 0) {
         for (int l = 0; l < kLanes; ++l)
             if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw * nn, elem))) return rc;
         int idx = 0;
-        const size_t row_bytes = (size_t)W * elem;
+        const size_t dev_pitch = (size_t)Wp * elem;
         for (int r0 = 0; r0 < total_rows; r0 += rows, ++idx) {
             Lane &ln = p->lane[idx % kLanes];
             const int nr = std::min(rows, total_rows - r0);
+            const int have = std::min(nr * n, H - r0 * n);               // image rows in this strip
             const size_t nb = (size_t)nr * bw, b0 = (size_t)r0 * bw;
-            CU_TRY(cudaMemcpy2DAsync(ln.d_px, row_bytes, px + (size_t)r0 * n * pitch, pitch, row_bytes, (size_t)nr * n,
+            CU_TRY(cudaMemcpy2DAsync(ln.d_px, dev_pitch, px + (size_t)r0 * n * pitch, pitch, (size_t)W * elem, (size_t)have,
                                      cudaMemcpyHostToDevice, ln.stream));
-            if ((rc = queue_fwd(p, ln, ln.d_px, row_bytes, W, nr * n, ln.d_coef, layout, ln.d_var, ln.stream, elem))) return rc;
+            if (Wp != W || have != nr * n)
+                CU_TRY(launch_pad_edges(ln.d_px, (long long)dev_pitch, W, have, Wp, nr * n, elem, ln.stream));
+            if ((rc = queue_fwd(p, ln, ln.d_px, dev_pitch, Wp, nr * n, ln.d_coef, layout, ln.d_var, ln.stream, elem))) return rc;
             CU_TRY(cudaMemcpyAsync(coef + b0 * nn, ln.d_coef, nb * nn * 2, cudaMemcpyDeviceToHost, ln.stream));
             if (p->adaptive && var)
                 CU_TRY(cudaMemcpyAsync(var + b0, ln.d_var, nb * sizeof(double), cudaMemcpyDeviceToHost, ln.stream));
@@ -719,17 +739,18 @@ extern "C" int dct_cuda_fwd_quant_u8(dct_cuda_plan *p, const uint8_t *px, size_t
     return dct_cuda_plan_wait(p, stats);
 }
 
-extern "C" int dct_cuda_dequant_idct_u8_async(dct_cuda_plan *p, const int16_t *coef, int W, int H, int layout,
-                                              const double *var, uint8_t *px, size_t pitch)
+static int inv_host_async(dct_cuda_plan *p, const int16_t *coef, int W, int H, int layout, const double *var, uint8_t *px,
+                          size_t pitch, bool ragged = false)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     const int n = p->n, nn = n * n;
-    int rc = check_plane(px, coef, pitch, W, H, false, n);
+    int rc = ragged ? check_ragged(px, coef, pitch, W, H, n) : check_plane(px, coef, pitch, W, H, false, n);
     if (rc) return rc;
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     if (p->adaptive && !var) return fail(DCT_CUDA_EINVAL, "adaptive plan needs the per-block variance array");
     DeviceGuard g(p->device);
-    const int bw = W / n, total_rows = H / n, rows = strip_rows(W, H, n);
+    const int Wp = (W + n - 1) / n * n, Hp = (H + n - 1) / n * n;   // == W, H unless ragged
+    const int bw = Wp / n, total_rows = Hp / n, rows = strip_rows(Wp, Hp, n);
     if (rows > 0) {
         for (int l = 0; l < kLanes; ++l)
             if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw * nn))) return rc;
@@ -737,16 +758,41 @@ extern "C" int dct_cuda_dequant_idct_u8_async(dct_cuda_plan *p, const int16_t *c
         for (int r0 = 0; r0 < total_rows; r0 += rows, ++idx) {
             Lane &ln = p->lane[idx % kLanes];
             const int nr = std::min(rows, total_rows - r0);
+            const int have = std::min(nr * n, H - r0 * n);               // image rows in this strip
             const size_t nb = (size_t)nr * bw, b0 = (size_t)r0 * bw;
             CU_TRY(cudaMemcpyAsync(ln.d_coef, coef + b0 * nn, nb * nn * 2, cudaMemcpyHostToDevice, ln.stream));
             if (p->adaptive)
                 CU_TRY(cudaMemcpyAsync(ln.d_var, var + b0, nb * sizeof(double), cudaMemcpyHostToDevice, ln.stream));
-            if ((rc = queue_inv(p, ln, ln.d_coef, W, nr * n, layout, ln.d_var, ln.d_px, (size_t)W, ln.stream))) return rc;
-            CU_TRY(cudaMemcpy2DAsync(px + (size_t)r0 * n * pitch, pitch, ln.d_px, (size_t)W, (size_t)W, (size_t)nr * n,
+            if ((rc = queue_inv(p, ln, ln.d_coef, Wp, nr * n, layout, ln.d_var, ln.d_px, (size_t)Wp, ln.stream))) return rc;
+            CU_TRY(cudaMemcpy2DAsync(px + (size_t)r0 * n * pitch, pitch, ln.d_px, (size_t)Wp, (size_t)W, (size_t)have,
                                      cudaMemcpyDeviceToHost, ln.stream));
         }
     }
     return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_dequant_idct_u8_async(dct_cuda_plan *p, const int16_t *coef, int W, int H, int layout,
+                                              const double *var, uint8_t *px, size_t pitch)
+{
+    return inv_host_async(p, coef, W, H, layout, var, px, pitch);
+}
+
+// ---- planes of any size: edge blocks completed by replication (not in the reference: src/dct.c:109-120
+// reads out of bounds there) ----
+extern "C" int dct_cuda_fwd_quant_u8_edge(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H, int16_t *coef,
+                                          int layout, double *var, dct_cuda_stats *stats)
+{
+    int rc = fwd_host_async(p, px, pitch, W, H, coef, layout, var, 1, true);
+    if (rc) return rc;
+    return dct_cuda_plan_wait(p, stats);
+}
+
+extern "C" int dct_cuda_dequant_idct_u8_edge(dct_cuda_plan *p, const int16_t *coef, int W, int H, int layout,
+                                             const double *var, uint8_t *px, size_t pitch, dct_cuda_stats *stats)
+{
+    int rc = inv_host_async(p, coef, W, H, layout, var, px, pitch, true);
+    if (rc) return rc;
+    return dct_cuda_plan_wait(p, stats);
 }
 
 extern "C" int dct_cuda_dequant_idct_u8(dct_cuda_plan *p, const int16_t *coef, int W, int H, int layout,
@@ -755,6 +801,203 @@ extern "C" int dct_cuda_dequant_idct_u8(dct_cuda_plan *p, const int16_t *coef, i
     int rc = dct_cuda_dequant_idct_u8_async(p, coef, W, H, layout, var, px, pitch);
     if (rc) return rc;
     return dct_cuda_plan_wait(p, stats);
+}
+
+// ------------------------------------------------------------------------------------------
+// planar front / back end (planar.cu): colour conversion + 4:2:0, edge completion.  Not in the reference.
+// ------------------------------------------------------------------------------------------
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+extern "C" void dct_cuda_frame420_geometry(int width, int height, dct_cuda_frame420 *g)
+{
+    if (!g) return;
+    g->width = width, g->height = height;
+    g->y_width = round_up(width, 8), g->y_height = round_up(height, 8);
+    g->c_width = round_up((width + 1) / 2, 8), g->c_height = round_up((height + 1) / 2, 8);
+}
+
+static int check_frame(const dct_cuda_frame420 *g, int device)
+{
+    if (!g) return fail(DCT_CUDA_EINVAL, "NULL geometry");
+    dct_cuda_frame420 want;
+    dct_cuda_frame420_geometry(g->width, g->height, &want);
+    if (g->width <= 0 || g->height <= 0 || memcmp(&want, g, sizeof want))
+        return fail(DCT_CUDA_EINVAL, "geometry does not come from dct_cuda_frame420_geometry (%dx%d)", g->width, g->height);
+    const int ndev = dct_cuda_device_count();
+    if (ndev <= 0) return fail(DCT_CUDA_ENODEV, "no CUDA device available (libdct_cuda has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(DCT_CUDA_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+    return DCT_CUDA_OK;
+}
+
+static PlanarParams planar_params(const dct_cuda_frame420 *g, const uint8_t *rgb_in, uint8_t *rgb_out, size_t rgb_pitch,
+                                  const uint8_t *y, size_t y_pitch, const uint8_t *cb, const uint8_t *cr, size_t c_pitch)
+{
+    PlanarParams pp{};
+    pp.rgb = rgb_in, pp.rgb_out = rgb_out, pp.rgb_pitch = (long long)rgb_pitch;
+    pp.W = g->width, pp.H = g->height;
+    pp.y = const_cast<uint8_t *>(y), pp.cb = const_cast<uint8_t *>(cb), pp.cr = const_cast<uint8_t *>(cr);
+    pp.y_pitch = (long long)y_pitch, pp.c_pitch = (long long)c_pitch;
+    pp.y_w = g->y_width, pp.y_h = g->y_height, pp.c_w = g->c_width, pp.c_h = g->c_height;
+    const uintptr_t rgbp = (uintptr_t)(rgb_in ? rgb_in : rgb_out);
+    pp.vec_ok = !(rgbp % 16) && !(rgb_pitch % 16) && !((uintptr_t)y % 16) && !(y_pitch % 16) && !((uintptr_t)cb % 8) &&
+                !((uintptr_t)cr % 8) && !(c_pitch % 8);
+    return pp;
+}
+
+extern "C" int dct_cuda_rgb_to_ycbcr420_dev(int device, const uint8_t *d_rgb, size_t rgb_pitch, const dct_cuda_frame420 *g,
+                                            uint8_t *d_y, size_t y_pitch, uint8_t *d_cb, uint8_t *d_cr, size_t c_pitch,
+                                            void *stream)
+{
+    int rc = check_frame(g, device);
+    if (rc) return rc;
+    if (!d_rgb || !d_y || !d_cb || !d_cr) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
+    if (rgb_pitch < (size_t)g->width * 3 || y_pitch < (size_t)g->y_width || c_pitch < (size_t)g->c_width)
+        return fail(DCT_CUDA_EINVAL, "pitch smaller than a row");
+    DeviceGuard dg(device);
+    CU_TRY(launch_rgb_to_ycbcr420(planar_params(g, d_rgb, nullptr, rgb_pitch, d_y, y_pitch, d_cb, d_cr, c_pitch),
+                                  (cudaStream_t)stream));
+    return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_ycbcr420_to_rgb_dev(int device, const uint8_t *d_y, size_t y_pitch, const uint8_t *d_cb,
+                                            const uint8_t *d_cr, size_t c_pitch, const dct_cuda_frame420 *g, uint8_t *d_rgb,
+                                            size_t rgb_pitch, void *stream)
+{
+    int rc = check_frame(g, device);
+    if (rc) return rc;
+    if (!d_rgb || !d_y || !d_cb || !d_cr) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
+    if (rgb_pitch < (size_t)g->width * 3 || y_pitch < (size_t)g->y_width || c_pitch < (size_t)g->c_width)
+        return fail(DCT_CUDA_EINVAL, "pitch smaller than a row");
+    DeviceGuard dg(device);
+    CU_TRY(launch_ycbcr420_to_rgb(planar_params(g, nullptr, d_rgb, rgb_pitch, d_y, y_pitch, d_cb, d_cr, c_pitch),
+                                  (cudaStream_t)stream));
+    return DCT_CUDA_OK;
+}
+
+extern "C" int dct_cuda_pad_edges_dev(int device, uint8_t *d_px, size_t pitch, int W, int H, int W_pad, int H_pad,
+                                      void *stream)
+{
+    if (!d_px) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
+    if (W <= 0 || H <= 0 || W_pad < W || H_pad < H || pitch < (size_t)W_pad)
+        return fail(DCT_CUDA_EINVAL, "bad sizes %dx%d -> %dx%d, pitch %zu", W, H, W_pad, H_pad, pitch);
+    const int ndev = dct_cuda_device_count();
+    if (ndev <= 0) return fail(DCT_CUDA_ENODEV, "no CUDA device available (libdct_cuda has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(DCT_CUDA_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+    DeviceGuard dg(device);
+    CU_TRY(launch_pad_edges(d_px, (long long)pitch, W, H, W_pad, H_pad, 1, (cudaStream_t)stream));
+    return DCT_CUDA_OK;
+}
+
+// whole RGB frames from / to host memory: H2D, colour conversion, K1 on the three planes, D2H (and back)
+namespace {
+struct FrameLayout {
+    dct_cuda_frame420 g;
+    size_t rgb_pitch, y_pitch, c_pitch;
+    size_t off_y, off_cb, off_cr, off_ky, off_kcb, off_kcr, bytes;   // offsets into plan->d_frame
+    size_t ny, nc;                                                    // samples per luma / chroma plane
+};
+
+FrameLayout frame_layout(int W, int H)
+{
+    FrameLayout f{};
+    dct_cuda_frame420_geometry(W, H, &f.g);
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    f.rgb_pitch = ((size_t)W * 3 + 15) / 16 * 16;
+    f.y_pitch = ((size_t)f.g.y_width + 15) / 16 * 16;
+    f.c_pitch = (size_t)f.g.c_width;
+    f.ny = (size_t)f.g.y_width * f.g.y_height, f.nc = (size_t)f.g.c_width * f.g.c_height;
+    size_t o = up(f.rgb_pitch * H);
+    f.off_y = o, o += up(f.y_pitch * f.g.y_height);
+    f.off_cb = o, o += up(f.c_pitch * f.g.c_height);
+    f.off_cr = o, o += up(f.c_pitch * f.g.c_height);
+    f.off_ky = o, o += up(f.ny * 2);
+    f.off_kcb = o, o += up(f.nc * 2);
+    f.off_kcr = o, o += up(f.nc * 2);
+    f.bytes = o;
+    return f;
+}
+
+int frame_prepare(dct_cuda_plan *luma, dct_cuda_plan *chroma, int W, int H, int layout, FrameLayout *f)
+{
+    if (!luma || !chroma) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    if (luma->n != 8 || chroma->n != 8 || luma->adaptive || chroma->adaptive)
+        return fail(DCT_CUDA_EINVAL, "the RGB 4:2:0 frame calls need two non-adaptive 8x8 plans");
+    if (luma->device != chroma->device) return fail(DCT_CUDA_EINVAL, "both plans must live on the same GPU");
+    if (W <= 0 || H <= 0) return fail(DCT_CUDA_EINVAL, "width and height must be positive (got %dx%d)", W, H);
+    if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
+    *f = frame_layout(W, H);
+    if (luma->frame_cap < f->bytes) {
+        CU_TRY(cudaDeviceSynchronize());
+        if (luma->d_frame) cudaFree(luma->d_frame);
+        luma->d_frame = nullptr, luma->frame_cap = 0;
+        CU_TRY(cudaMalloc(&luma->d_frame, f->bytes));
+        luma->frame_cap = f->bytes;
+    }
+    return DCT_CUDA_OK;
+}
+
+int frame_stats(dct_cuda_plan *luma, dct_cuda_plan *chroma, cudaStream_t s, dct_cuda_stats *stats)
+{
+    dct_cuda_stats a{}, b{};
+    int rc = collect_stats(luma, &a, s);
+    if (rc) return rc;
+    if (chroma != luma && (rc = collect_stats(chroma, &b, s))) return rc;
+    if (stats) {
+        stats->blocks = a.blocks + b.blocks, stats->replayed_blocks = a.replayed_blocks + b.replayed_blocks;
+        stats->near_ties = a.near_ties + b.near_ties, stats->saturated = a.saturated + b.saturated;
+    }
+    return DCT_CUDA_OK;
+}
+}  // namespace
+
+extern "C" int dct_cuda_encode_rgb420(dct_cuda_plan *luma, dct_cuda_plan *chroma, const uint8_t *rgb, size_t rgb_pitch,
+                                      int W, int H, int16_t *coef_y, int16_t *coef_cb, int16_t *coef_cr, int layout,
+                                      dct_cuda_stats *stats)
+{
+    FrameLayout f;
+    int rc = frame_prepare(luma, chroma, W, H, layout, &f);
+    if (rc) return rc;
+    if (!rgb || !coef_y || !coef_cb || !coef_cr) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
+    if (rgb_pitch < (size_t)W * 3) return fail(DCT_CUDA_EINVAL, "pitch %zu must be >= 3 * width", rgb_pitch);
+    DeviceGuard dg(luma->device);
+    uint8_t *base = luma->d_frame;
+    cudaStream_t s = luma->lane[0].stream;
+    CU_TRY(cudaMemcpy2DAsync(base, f.rgb_pitch, rgb, rgb_pitch, (size_t)W * 3, (size_t)H, cudaMemcpyHostToDevice, s));
+    CU_TRY(launch_rgb_to_ycbcr420(planar_params(&f.g, base, nullptr, f.rgb_pitch, base + f.off_y, f.y_pitch, base + f.off_cb,
+                                                base + f.off_cr, f.c_pitch), s));
+    int16_t *ky = (int16_t *)(base + f.off_ky), *kcb = (int16_t *)(base + f.off_kcb), *kcr = (int16_t *)(base + f.off_kcr);
+    if ((rc = queue_fwd(luma, luma->lane[0], base + f.off_y, f.y_pitch, f.g.y_width, f.g.y_height, ky, layout, nullptr, s))) return rc;
+    if ((rc = queue_fwd(chroma, chroma->lane[0], base + f.off_cb, f.c_pitch, f.g.c_width, f.g.c_height, kcb, layout, nullptr, s))) return rc;
+    if ((rc = queue_fwd(chroma, chroma->lane[0], base + f.off_cr, f.c_pitch, f.g.c_width, f.g.c_height, kcr, layout, nullptr, s))) return rc;
+    CU_TRY(cudaMemcpyAsync(coef_y, ky, f.ny * 2, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(coef_cb, kcb, f.nc * 2, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(coef_cr, kcr, f.nc * 2, cudaMemcpyDeviceToHost, s));
+    return frame_stats(luma, chroma, s, stats);
+}
+
+extern "C" int dct_cuda_decode_rgb420(dct_cuda_plan *luma, dct_cuda_plan *chroma, const int16_t *coef_y,
+                                      const int16_t *coef_cb, const int16_t *coef_cr, int W, int H, int layout,
+                                      uint8_t *rgb, size_t rgb_pitch, dct_cuda_stats *stats)
+{
+    FrameLayout f;
+    int rc = frame_prepare(luma, chroma, W, H, layout, &f);
+    if (rc) return rc;
+    if (!rgb || !coef_y || !coef_cb || !coef_cr) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
+    if (rgb_pitch < (size_t)W * 3) return fail(DCT_CUDA_EINVAL, "pitch %zu must be >= 3 * width", rgb_pitch);
+    DeviceGuard dg(luma->device);
+    uint8_t *base = luma->d_frame;
+    cudaStream_t s = luma->lane[0].stream;
+    int16_t *ky = (int16_t *)(base + f.off_ky), *kcb = (int16_t *)(base + f.off_kcb), *kcr = (int16_t *)(base + f.off_kcr);
+    CU_TRY(cudaMemcpyAsync(ky, coef_y, f.ny * 2, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(kcb, coef_cb, f.nc * 2, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(kcr, coef_cr, f.nc * 2, cudaMemcpyHostToDevice, s));
+    if ((rc = queue_inv(luma, luma->lane[0], ky, f.g.y_width, f.g.y_height, layout, nullptr, base + f.off_y, f.y_pitch, s))) return rc;
+    if ((rc = queue_inv(chroma, chroma->lane[0], kcb, f.g.c_width, f.g.c_height, layout, nullptr, base + f.off_cb, f.c_pitch, s))) return rc;
+    if ((rc = queue_inv(chroma, chroma->lane[0], kcr, f.g.c_width, f.g.c_height, layout, nullptr, base + f.off_cr, f.c_pitch, s))) return rc;
+    CU_TRY(launch_ycbcr420_to_rgb(planar_params(&f.g, nullptr, base, f.rgb_pitch, base + f.off_y, f.y_pitch, base + f.off_cb,
+                                                base + f.off_cr, f.c_pitch), s));
+    CU_TRY(cudaMemcpy2DAsync(rgb, rgb_pitch, base, f.rgb_pitch, (size_t)W * 3, (size_t)H, cudaMemcpyDeviceToHost, s));
+    return frame_stats(luma, chroma, s, stats);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -138,6 +138,50 @@ int dct_cuda_dequant_idct_u8_multi(dct_cuda_plan *const *plans, int n_plans, con
                                    int height, int layout, const double *variance, uint8_t *pixels,
                                    size_t pitch, dct_cuda_stats *stats);
 
+/* ---- planar front / back end (NOT in the reference, which starts from whole-block grayscale planes;
+ * the conventions are ours and are stated in dct_b200/csrc/planar.cu and DESIGN.md) ----
+ *   edges    a plane is completed to whole blocks by replicating its last column / row;
+ *   colour   JFIF full-range BT.601 in 16-bit fixed point, interleaved R,G,B bytes <-> Y, Cb, Cr planes;
+ *   4:2:0    one chroma sample per 2x2 pixels (from the sum of the four pixels), replicated on decode. */
+
+/* Host planes of ANY positive size: like dct_cuda_fwd_quant_u8 / dct_cuda_dequant_idct_u8, but the
+ * records cover ceil(width/n) x ceil(height/n) blocks; the inverse writes width x height pixels. */
+int dct_cuda_fwd_quant_u8_edge(dct_cuda_plan *plan, const uint8_t *pixels, size_t pitch, int width, int height,
+                               int16_t *coef, int layout, double *variance, dct_cuda_stats *stats);
+int dct_cuda_dequant_idct_u8_edge(dct_cuda_plan *plan, const int16_t *coef, int width, int height, int layout,
+                                  const double *variance, uint8_t *pixels, size_t pitch, dct_cuda_stats *stats);
+/* Device plane: fill columns [width, width_padded) and rows [height, height_padded) in place. */
+int dct_cuda_pad_edges_dev(int device, uint8_t *d_pixels, size_t pitch, int width, int height, int width_padded,
+                           int height_padded, void *stream);
+
+/* Plane sizes of a 4:2:0 frame whose planes are completed to whole 8x8 blocks. */
+typedef struct {
+    int width, height;       /* the RGB image                                              */
+    int y_width, y_height;   /* luma plane: width, height rounded up to 8                   */
+    int c_width, c_height;   /* each chroma plane: ceil(width/2), ceil(height/2) rounded up to 8 */
+} dct_cuda_frame420;
+void dct_cuda_frame420_geometry(int width, int height, dct_cuda_frame420 *geometry);
+
+/* Device frames.  The planes are written at their padded sizes (edges replicated), ready for
+ * dct_cuda_fwd_quant_planes_dev; the way back writes the width x height image only.  16-byte aligned
+ * pointers and pitches take the vector path (rgb, y: 16; cb, cr: 8), anything else a slow scalar one. */
+int dct_cuda_rgb_to_ycbcr420_dev(int device, const uint8_t *d_rgb, size_t rgb_pitch, const dct_cuda_frame420 *geometry,
+                                 uint8_t *d_y, size_t y_pitch, uint8_t *d_cb, uint8_t *d_cr, size_t c_pitch,
+                                 void *stream);
+int dct_cuda_ycbcr420_to_rgb_dev(int device, const uint8_t *d_y, size_t y_pitch, const uint8_t *d_cb,
+                                 const uint8_t *d_cr, size_t c_pitch, const dct_cuda_frame420 *geometry, uint8_t *d_rgb,
+                                 size_t rgb_pitch, void *stream);
+
+/* Whole RGB frames in host memory: copy, convert, transform all three planes, copy back (and the
+ * reverse).  `luma` and `chroma` are two non-adaptive 8x8 plans on the same GPU (they may be the same
+ * plan); coef_y holds y_width*y_height int16, coef_cb / coef_cr hold c_width*c_height each. */
+int dct_cuda_encode_rgb420(dct_cuda_plan *luma, dct_cuda_plan *chroma, const uint8_t *rgb, size_t rgb_pitch, int width,
+                           int height, int16_t *coef_y, int16_t *coef_cb, int16_t *coef_cr, int layout,
+                           dct_cuda_stats *stats);
+int dct_cuda_decode_rgb420(dct_cuda_plan *luma, dct_cuda_plan *chroma, const int16_t *coef_y, const int16_t *coef_cb,
+                           const int16_t *coef_cr, int width, int height, int layout, uint8_t *rgb, size_t rgb_pitch,
+                           dct_cuda_stats *stats);
+
 /* Waits for the plan's queued work, returns the counters accumulated since the last fetch and
  * clears them.  `stream` is the stream the *_dev calls were queued on. */
 int dct_cuda_stats_fetch(dct_cuda_plan *plan, dct_cuda_stats *stats, void *stream);

@@ -76,6 +76,14 @@ class CpuChecker:
           _P_U8, C.c_size_t, C.c_int, _P_U64)
         f("rle_plane", C.c_size_t, _P_I16, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int32))
         if prefix == "orc_":
+            self.lib.orc_rgb_to_ycbcr420.argtypes = [_P_U8, C.c_size_t, C.c_int, C.c_int, _P_U8, C.c_size_t, C.c_int, C.c_int,
+                                                     _P_U8, _P_U8, C.c_size_t, C.c_int, C.c_int]
+            self.lib.orc_rgb_to_ycbcr420.restype = None
+            self.lib.orc_ycbcr420_to_rgb.argtypes = [_P_U8, C.c_size_t, _P_U8, _P_U8, C.c_size_t, C.c_int, C.c_int, _P_U8,
+                                                     C.c_size_t]
+            self.lib.orc_ycbcr420_to_rgb.restype = None
+            self.lib.orc_pad_edges.argtypes = [_P_U8, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+            self.lib.orc_pad_edges.restype = None
             self.lib.orc_fill_xorshift.argtypes = [_P_U8, C.c_size_t, C.c_uint64, C.c_int, C.c_int]
             self.lib.orc_fill_xorshift.restype = None
             self.lib.orc_fnv_i16.argtypes = [_P_I16, C.c_size_t]
@@ -238,6 +246,36 @@ class CpuChecker:
         self._rle_plane(coef.ctypes.data_as(_P_I16), nb, int(layout), off.ctypes.data_as(C.POINTER(C.c_uint32)),
                         sym.ctypes.data_as(C.POINTER(C.c_int32)))
         return off, sym
+
+    # ---- planar front / back end (oracle only: the reference has none; parity unpinned) ----
+    @staticmethod
+    def frame420_geometry(W, H):
+        up8 = lambda v: (v + 7) // 8 * 8
+        return up8(W), up8(H), up8((W + 1) // 2), up8((H + 1) // 2)
+
+    def rgb_to_ycbcr420(self, rgb):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        H, W = rgb.shape[:2]
+        yw, yh, cw, ch = self.frame420_geometry(W, H)
+        y, cb, cr = np.zeros((yh, yw), np.uint8), np.zeros((ch, cw), np.uint8), np.zeros((ch, cw), np.uint8)
+        self.lib.orc_rgb_to_ycbcr420(rgb.ctypes.data_as(_P_U8), W * 3, W, H, y.ctypes.data_as(_P_U8), yw, yw, yh,
+                                     cb.ctypes.data_as(_P_U8), cr.ctypes.data_as(_P_U8), cw, cw, ch)
+        return y, cb, cr
+
+    def ycbcr420_to_rgb(self, y, cb, cr, W, H):
+        y, cb, cr = (np.ascontiguousarray(a, dtype=np.uint8) for a in (y, cb, cr))
+        rgb = np.zeros((H, W, 3), np.uint8)
+        self.lib.orc_ycbcr420_to_rgb(y.ctypes.data_as(_P_U8), y.shape[1], cb.ctypes.data_as(_P_U8), cr.ctypes.data_as(_P_U8),
+                                     cb.shape[1], W, H, rgb.ctypes.data_as(_P_U8), W * 3)
+        return rgb
+
+    def pad_edges(self, px, Wp, Hp):
+        px = np.ascontiguousarray(px, dtype=np.uint8)
+        H, W = px.shape
+        out = np.zeros((Hp, Wp), np.uint8)
+        out[:H, :W] = px
+        self.lib.orc_pad_edges(out.ctypes.data_as(_P_U8), Wp, W, H, Wp, Hp, 1)
+        return out
 
     # ---- oracle-only helpers ----------------------------------------------------------
     def fill_xorshift(self, H, W, seed=0x9E3779B97F4A7C15, dist=0):

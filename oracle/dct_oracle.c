@@ -436,6 +436,79 @@ size_t orc_rle_plane(const int16_t *coef, size_t nblocks, int layout, uint32_t *
 }
 
 /* ------------------------------------------------------------------------ */
+/* Planar front / back end.                              */
+/* PARITY UNPINNED for this section: the reference has no colour conversion,    */
+/* no subsampling and no edge handling (src/dct.c:109-120 reads out of bounds). */
+/* The convention is ours (dct_b200/csrc/planar.cu states it); this is a        */
+/* second, independent statement of it in signed 64-bit arithmetic with an       */
+/* explicit floor division, anchored only by the published JFIF known answers    */
+/* that tests/test_oracle.py checks (grey stays grey, the primaries).            */
+/* ------------------------------------------------------------------------ */
+static long long floor_div(long long a, long long b) /* b > 0 */
+{
+    long long q = a / b;
+    if ((a % b) != 0 && a < 0) --q;
+    return q;
+}
+static int clamp_u8(long long v) { return v < 0 ? 0 : (v > 255 ? 255 : (int)v); }
+static int imin(int a, int b) { return a < b ? a : b; }
+
+void orc_rgb_to_ycbcr420(const uint8_t *rgb, size_t rgb_pitch, int W, int H, uint8_t *y, size_t y_pitch, int y_w,
+                         int y_h, uint8_t *cb, uint8_t *cr, size_t c_pitch, int c_w, int c_h)
+{
+    if (W <= 0 || H <= 0) return;
+    for (int j = 0; j < y_h; ++j)
+        for (int i = 0; i < y_w; ++i) {
+            const uint8_t *s = rgb + (size_t)imin(j, H - 1) * rgb_pitch + (size_t)imin(i, W - 1) * 3;
+            y[(size_t)j * y_pitch + i] =
+                (uint8_t)floor_div(19595LL * s[0] + 38470LL * s[1] + 7471LL * s[2] + 32768, 65536);
+        }
+    const int cw_img = (W + 1) / 2, ch_img = (H + 1) / 2;
+    for (int j = 0; j < c_h; ++j)
+        for (int i = 0; i < c_w; ++i) {
+            const int sx = 2 * imin(i, cw_img - 1), sy = 2 * imin(j, ch_img - 1);
+            long long sum[3] = {0, 0, 0};
+            for (int dy = 0; dy < 2; ++dy)
+                for (int dx = 0; dx < 2; ++dx) {
+                    const uint8_t *s = rgb + (size_t)imin(sy + dy, H - 1) * rgb_pitch + (size_t)imin(sx + dx, W - 1) * 3;
+                    for (int c = 0; c < 3; ++c) sum[c] += s[c];
+                }
+            const long long bias = 4LL * (128LL << 16) + 4LL * 32768 - 1; /* (128<<18) + (1<<17) - 1 */
+            cb[(size_t)j * c_pitch + i] =
+                (uint8_t)floor_div(-11059LL * sum[0] - 21709LL * sum[1] + 32768LL * sum[2] + bias, 4 * 65536);
+            cr[(size_t)j * c_pitch + i] =
+                (uint8_t)floor_div(32768LL * sum[0] - 27439LL * sum[1] - 5329LL * sum[2] + bias, 4 * 65536);
+        }
+}
+
+void orc_ycbcr420_to_rgb(const uint8_t *y, size_t y_pitch, const uint8_t *cb, const uint8_t *cr, size_t c_pitch, int W,
+                         int H, uint8_t *rgb, size_t rgb_pitch)
+{
+    for (int j = 0; j < H; ++j)
+        for (int i = 0; i < W; ++i) {
+            const long long l = y[(size_t)j * y_pitch + i];
+            const long long u = (long long)cb[(size_t)(j / 2) * c_pitch + i / 2] - 128;
+            const long long v = (long long)cr[(size_t)(j / 2) * c_pitch + i / 2] - 128;
+            uint8_t *o = rgb + (size_t)j * rgb_pitch + (size_t)i * 3;
+            o[0] = (uint8_t)clamp_u8(l + floor_div(91881 * v + 32768, 65536));
+            o[1] = (uint8_t)clamp_u8(l + floor_div(-22554 * u - 46802 * v + 32768, 65536));
+            o[2] = (uint8_t)clamp_u8(l + floor_div(116130 * u + 32768, 65536));
+        }
+}
+
+/* complete a W x H plane of `elem`-byte elements to Wp x Hp in place: last column / row replicated */
+void orc_pad_edges(uint8_t *px, size_t pitch, int W, int H, int Wp, int Hp, int elem)
+{
+    if (W <= 0 || H <= 0) return;
+    for (int j = 0; j < Hp; ++j)
+        for (int i = 0; i < Wp; ++i) {
+            if (i < W && j < H) continue;
+            memcpy(px + (size_t)j * pitch + (size_t)i * elem,
+                   px + (size_t)imin(j, H - 1) * pitch + (size_t)imin(i, W - 1) * elem, (size_t)elem);
+        }
+}
+
+/* ------------------------------------------------------------------------ */
 /* Synthetic inputs and hashes                  */
 /* ------------------------------------------------------------------------ */
 

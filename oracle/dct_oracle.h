@@ -60,6 +60,13 @@ int orc_dequant_idct_plane_n(int n, const int16_t *coef, int W, int H, const dou
 /* ---- run-length symbols (value, run) per record; returns the total, offsets has nblocks+1 entries ---- */
 size_t orc_rle_plane(const int16_t *coef, size_t nblocks, int layout, uint32_t *offsets, int32_t *symbols);
 
+/* ---- planar front / back end: OUR convention, no reference counterpart => parity unpinned (see .c) ---- */
+void orc_rgb_to_ycbcr420(const uint8_t *rgb, size_t rgb_pitch, int W, int H, uint8_t *y, size_t y_pitch, int y_w,
+                         int y_h, uint8_t *cb, uint8_t *cr, size_t c_pitch, int c_w, int c_h);
+void orc_ycbcr420_to_rgb(const uint8_t *y, size_t y_pitch, const uint8_t *cb, const uint8_t *cr, size_t c_pitch, int W,
+                         int H, uint8_t *rgb, size_t rgb_pitch);
+void orc_pad_edges(uint8_t *px, size_t pitch, int W, int H, int Wp, int Hp, int elem);
+
 /* ---- helpers shared by the tests --------------------------------------- */
 void     orc_fill_xorshift(uint8_t *dst, size_t n, uint64_t seed, int dist, int W);
 uint64_t orc_fnv_i16(const int16_t *v, size_t n);

@@ -648,3 +648,170 @@ def test_multi_gpu_entry_point_with_available_devices(api, oracle):
     finally:
         for c in ctxs:
             c.__exit__()
+
+
+# ---------------------------------------------------------------------------------------------
+# planar front / back end.  The reference has none of it, so the checker here is the
+# oracle's own statement of OUR convention (parity unpinned) plus the published JFIF known answers.
+# ---------------------------------------------------------------------------------------------
+CHROMA_K2 = np.full((8, 8), 99.0)                  # ITU-T T.81 Table K.2
+CHROMA_K2[:4, :4] = [[17, 18, 24, 47], [18, 21, 26, 66], [24, 26, 56, 99], [47, 66, 99, 99]]
+
+FRAME_SHAPES = [(64, 64), (16, 512), (1080, 1920), (37, 53), (1, 1), (2, 17), (17, 8), (1081, 1919), (8, 16 * 33 + 5)]
+
+
+def _rgb_dev(api, torch, rgb):
+    d = api._alloc_rgb(rgb.shape[0], rgb.shape[1], "cuda")
+    d.copy_(torch.from_numpy(rgb).cuda())
+    return d
+
+
+@pytest.mark.parametrize("shape", FRAME_SHAPES)
+def test_rgb_to_ycbcr420_and_back_match_the_oracle(api, oracle, torch, shape):
+    H, W = shape
+    rng = np.random.default_rng(H * 10007 + W)
+    rgb = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    if H >= 8 and W >= 16:                              # saturated primaries and greys in the mix
+        rgb[:4, :8] = [[255, 0, 0], [0, 255, 0], [0, 0, 255], [255, 255, 255], [0, 0, 0], [1, 254, 3], [128, 128, 128], [255, 255, 0]]
+    want_y, want_cb, want_cr = oracle.rgb_to_ycbcr420(rgb)
+    y, cb, cr = api.rgb_to_ycbcr420_dev(_rgb_dev(api, torch, rgb))
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), want_y)
+    assert np.array_equal(cb.cpu().numpy(), want_cb)
+    assert np.array_equal(cr.cpu().numpy(), want_cr)
+    # the way back, from arbitrary plane contents (not only from converted images)
+    y2 = torch.from_numpy(rng.integers(0, 256, size=want_y.shape, dtype=np.uint8)).cuda()
+    cb2 = torch.from_numpy(rng.integers(0, 256, size=want_cb.shape, dtype=np.uint8)).cuda()
+    cr2 = torch.from_numpy(rng.integers(0, 256, size=want_cb.shape, dtype=np.uint8)).cuda()
+    for (a, b, c) in ((y, cb, cr), (y2, cb2, cr2)):
+        ya = torch.empty((a.shape[0], (a.shape[1] + 15) // 16 * 16), dtype=torch.uint8, device="cuda")[:, :a.shape[1]]
+        ya.copy_(a)
+        got = api.ycbcr420_to_rgb_dev(ya, b, c, W, H)
+        torch.cuda.synchronize()
+        want = oracle.ycbcr420_to_rgb(a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy(), W, H)
+        assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_colour_conversion_unaligned_views_take_the_scalar_path(api, oracle, torch):
+    rng = np.random.default_rng(5)
+    big = rng.integers(0, 256, size=(70, 90, 3), dtype=np.uint8)
+    d_big = torch.from_numpy(big).cuda()
+    view = d_big[3:67, 1:82]                            # 64 x 81, base pointer and pitch not 16-byte aligned
+    rgb = big[3:67, 1:82]
+    want = oracle.rgb_to_ycbcr420(rgb)
+    got = api.rgb_to_ycbcr420_dev(view)
+    torch.cuda.synchronize()
+    for g, w in zip(got, want):
+        assert np.array_equal(g.cpu().numpy(), w)
+    out = torch.zeros_like(d_big)
+    api.ycbcr420_to_rgb_dev(*got, 81, 64, rgb_out=out[3:67, 1:82])
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    assert np.array_equal(o[3:67, 1:82], oracle.ycbcr420_to_rgb(*want, 81, 64))
+    o[3:67, 1:82] = 0
+    assert not o.any()                                  # nothing written outside the image
+
+
+def test_jfif_known_answers_and_grey_is_a_fixed_point(api, torch):
+    """Published JFIF values of the primaries; R=G=B=v must give (v, 128, 128) and come back unchanged."""
+    rgb = np.zeros((16, 32, 3), np.uint8)
+    rgb[0:2, 0:2] = [255, 0, 0]
+    rgb[0:2, 2:4] = [0, 255, 0]
+    rgb[0:2, 4:6] = [0, 0, 255]
+    grey = np.arange(256, dtype=np.uint8)
+    rgb[2:10] = np.repeat(grey.reshape(8, 32), 3).reshape(8, 32, 3)
+    y, cb, cr = (t.cpu().numpy() for t in api.rgb_to_ycbcr420_dev(_rgb_dev(api, torch, rgb)))
+    assert (y[0, 0], cb[0, 0], cr[0, 0]) == (76, 85, 255)
+    assert (y[0, 2], cb[0, 1], cr[0, 1]) == (150, 44, 21)
+    assert (y[0, 4], cb[0, 2], cr[0, 2]) == (29, 255, 107)
+    assert np.array_equal(y[2:10, :32], grey.reshape(8, 32)) and (cb[1:5, :16] == 128).all() and (cr[1:5, :16] == 128).all()
+    gy = torch.from_numpy(np.ascontiguousarray(y)).cuda()
+    back = api.ycbcr420_to_rgb_dev(gy, torch.from_numpy(cb).cuda(), torch.from_numpy(cr).cuda(), 32, 16).cpu().numpy()
+    assert np.array_equal(back[2:10], rgb[2:10])
+
+
+@pytest.mark.parametrize("shape,pad", [((5, 3), (8, 8)), ((1080, 1913), (1080, 1920)), ((1, 1), (16, 24)), ((16, 16), (16, 16)),
+                                       ((33, 40), (40, 40))])
+def test_pad_edges_matches_the_oracle(api, oracle, torch, shape, pad):
+    rng = np.random.default_rng(shape[0] + shape[1])
+    px = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    want = oracle.pad_edges(px, pad[1], pad[0])
+    assert np.array_equal(want, np.pad(px, ((0, pad[0] - shape[0]), (0, pad[1] - shape[1])), mode="edge"))
+    d = torch.full(pad, 7, dtype=torch.uint8, device="cuda")
+    d[:shape[0], :shape[1]] = torch.from_numpy(px).cuda()
+    api.pad_edges_dev(d, shape[1], shape[0])
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (7, 9), (1081, 1919), (8, 8), (250, 16), (3000, 4001)])
+@pytest.mark.parametrize("adaptive,layout", [(0, 0), (1, 1)])
+def test_planes_of_any_size_through_the_edge_calls(api, oracle, shape, adaptive, layout):
+    """Edge blocks completed by replication == the oracle on the np.pad(mode='edge') plane, cropped on the way back."""
+    H, W = shape
+    rng = np.random.default_rng(H * 31 + W + adaptive)
+    px = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    Hp, Wp = (H + 7) // 8 * 8, (W + 7) // 8 * 8
+    padded = np.pad(px, ((0, Hp - H), (0, Wp - W)), mode="edge")
+    Q = oracle.quant_table(85)
+    want_c, want_v, _ = oracle.fwd_quant_plane(padded, Q, adaptive, layout, nthreads=8)
+    want_p, _ = oracle.dequant_idct_plane(want_c, Wp, Hp, Q, adaptive, layout, want_v, nthreads=8)
+    with Ctx(api, 85, adaptive) as cx:
+        out, st = api.fwd_quant_edge(cx.plan, px, layout, want_stats=True)
+        coef, var = out if adaptive else (out, None)
+        assert coef.shape == want_c.shape and np.array_equal(coef, want_c)
+        if adaptive:
+            assert np.array_equal(bits(var), bits(want_v))
+        assert st["blocks"] == (Hp // 8) * (Wp // 8)
+        rec = api.dequant_idct_edge(cx.plan, coef, W, H, layout, var)
+        assert rec.shape == (H, W) and np.array_equal(rec, want_p[:H, :W])
+        with pytest.raises(api.DctCudaError, match="positive"):
+            api.fwd_quant_edge(cx.plan, np.zeros((0, 8), np.uint8))
+
+
+def test_edge_calls_with_a_generic_block_size(api, oracle):
+    n, H, W = 16, 70, 45
+    px = np.random.default_rng(16).integers(0, 256, size=(H, W), dtype=np.uint8)
+    padded = np.pad(px, ((0, 80 - H), (0, 48 - W)), mode="edge")
+    Q = oracle.quant_table(60, n)
+    want_c, _ = oracle.fwd_quant_plane_n(n, padded, Q, 0, 0, nthreads=2)
+    want_p = oracle.dequant_idct_plane_n(n, want_c, 48, 80, Q, 0, 0, None)
+    d, q = api.dct_init(n), api.quant_init(n, 60, 0)
+    plan = api.Plan(d, q)
+    try:
+        coef = api.fwd_quant_edge(plan, px)
+        assert np.array_equal(coef, want_c)
+        assert np.array_equal(api.dequant_idct_edge(plan, coef, W, H), want_p[:H, :W])
+    finally:
+        plan.close()
+        api.dct_free(d), api.quant_free(q)
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (1081, 1919), (2160, 3840), (9, 7)])
+def test_rgb_frames_encode_and_decode_like_the_oracle_pipeline(api, oracle, shape):
+    """dct_cuda_encode_rgb420 / decode == oracle colour conversion -> oracle K1 per plane (luma table, Annex-K chroma
+    table scaled by the reference's own rule) -> oracle K2 -> oracle conversion back."""
+    H, W = shape
+    rng = np.random.default_rng(H + W)
+    rgb = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    # low-pass the noise a little so that the decode exercises more than saturated pixels
+    rgb = ((rgb.astype(np.uint16) + np.roll(rgb, 1, 0) + np.roll(rgb, 1, 1) + np.roll(rgb, (1, 1), (0, 1))) // 4).astype(np.uint8)
+    Ql = oracle.quant_table(75)
+    Qc = np.clip(CHROMA_K2 * ((200.0 - 2 * 75) / 100.0), 1.0, 255.0)
+    planes = oracle.rgb_to_ycbcr420(rgb)
+    want_k = [oracle.fwd_quant_plane(p, Q, 0, 1, nthreads=8)[0] for p, Q in zip(planes, (Ql, Qc, Qc))]
+    want_planes = [oracle.dequant_idct_plane(k, p.shape[1], p.shape[0], Q, 0, 1, None, nthreads=8)[0]
+                   for k, p, Q in zip(want_k, planes, (Ql, Qc, Qc))]
+    want_rgb = oracle.ycbcr420_to_rgb(*want_planes, W, H)
+    with Ctx(api, 75, 0) as luma, Ctx(api, 75, 0, table=Qc) as chroma:
+        ky, kcb, kcr, st = api.encode_rgb420(luma.plan, chroma.plan, rgb, api.ZIGZAG)
+        for got, want in zip((ky, kcb, kcr), want_k):
+            assert np.array_equal(got, want)
+        assert st["blocks"] == sum(k.shape[0] for k in want_k)
+        back, st2 = api.decode_rgb420(luma.plan, chroma.plan, ky, kcb, kcr, W, H, api.ZIGZAG)
+        assert np.array_equal(back, want_rgb)
+        assert st2["blocks"] == st["blocks"]
+        err = np.abs(back.astype(int) - rgb.astype(int)).mean()
+        assert err < 40, err                            # sanity: it is the same picture (q75 of the reference is lossy, S2)
+        with pytest.raises(api.DctCudaError, match="positive"):
+            api.encode_rgb420(luma.plan, chroma.plan, np.zeros((0, 4, 3), np.uint8))

@@ -214,3 +214,51 @@ def test_generic_block_size_planes_equal_reference(oracle, n):
     if n == 8:
         c8, _, _ = oracle.fwd_quant_plane(px, Q)
         assert np.array_equal(c8, oracle.fwd_quant_plane_n(8, px, Q)[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# planar front / back end: OUR convention (the reference has none) -- parity unpinned; what CAN be
+# anchored are the published JFIF equations and plain numpy restatements.
+# ---------------------------------------------------------------------------------------------
+def test_colour_oracle_against_the_jfif_equations(oracle):
+    rng = np.random.default_rng(601)
+    rgb = rng.integers(0, 256, size=(64, 96, 3), dtype=np.uint8)
+    rgb[0, :6] = [[255, 0, 0], [255, 0, 0], [0, 255, 0], [0, 255, 0], [0, 0, 255], [0, 0, 255]]
+    rgb[1, :6] = rgb[0, :6]
+    y, cb, cr = oracle.rgb_to_ycbcr420(rgb)
+    assert (y[0, 0], cb[0, 0], cr[0, 0]) == (76, 85, 255)       # published JFIF values of the primaries
+    assert (y[0, 2], cb[0, 1], cr[0, 1]) == (150, 44, 21)
+    assert (y[0, 4], cb[0, 2], cr[0, 2]) == (29, 255, 107)
+    f = rgb.astype(np.float64)
+    yf = 0.299 * f[..., 0] + 0.587 * f[..., 1] + 0.114 * f[..., 2]
+    assert np.abs(y - yf).max() <= 0.51                         # 0.5 rounding + 16-bit coefficient error
+    m = f.reshape(32, 2, 48, 2, 3).mean(axis=(1, 3))             # 2x2 box average, then the JFIF chroma equations
+    cbf = -0.168736 * m[..., 0] - 0.331264 * m[..., 1] + 0.5 * m[..., 2] + 128
+    crf = 0.5 * m[..., 0] - 0.418688 * m[..., 1] - 0.081312 * m[..., 2] + 128
+    assert np.abs(cb - np.clip(cbf, 0, 255)).max() <= 0.51 and np.abs(cr - np.clip(crf, 0, 255)).max() <= 0.51
+    back = oracle.ycbcr420_to_rgb(y, cb, cr, 96, 64).astype(np.float64)
+    up = lambda c: np.repeat(np.repeat(c.astype(np.float64), 2, 0), 2, 1) - 128
+    want = np.stack([y + 1.402 * up(cr), y - 0.344136 * up(cb) - 0.714136 * up(cr), y + 1.772 * up(cb)], axis=-1)
+    assert np.abs(back - np.clip(want, 0, 255)).max() <= 1.02   # two roundings (chroma term, then the sum)
+
+
+def test_colour_oracle_grey_and_ragged_frames(oracle):
+    grey = np.repeat(np.arange(256, dtype=np.uint8).reshape(16, 16), 3).reshape(16, 16, 3)
+    y, cb, cr = oracle.rgb_to_ycbcr420(grey)
+    assert np.array_equal(y, grey[..., 0]) and (cb == 128).all() and (cr == 128).all()
+    assert np.array_equal(oracle.ycbcr420_to_rgb(y, cb, cr, 16, 16), grey)
+    # ragged frame == the same conversion of the edge-replicated frame
+    rng = np.random.default_rng(9)
+    rgb = rng.integers(0, 256, size=(13, 21, 3), dtype=np.uint8)
+    y, cb, cr = oracle.rgb_to_ycbcr420(rgb)
+    assert y.shape == (16, 24) and cb.shape == (8, 16)
+    full = np.pad(rgb, ((0, 3), (0, 11), (0, 0)), mode="edge")   # 16 x 32: whole luma AND chroma blocks
+    y2, cb2, cr2 = oracle.rgb_to_ycbcr420(full)
+    assert np.array_equal(y, y2[:, :24]) and np.array_equal(cb, cb2) and np.array_equal(cr, cr2)
+
+
+def test_pad_edges_oracle_is_numpy_edge_padding(oracle):
+    rng = np.random.default_rng(3)
+    for (h, w), (hp, wp) in (((5, 3), (8, 8)), ((1, 1), (8, 16)), ((8, 8), (8, 8)), ((9, 17), (16, 24))):
+        px = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+        assert np.array_equal(oracle.pad_edges(px, wp, hp), np.pad(px, ((0, hp - h), (0, wp - w)), mode="edge"))
