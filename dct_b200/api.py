@@ -131,6 +131,13 @@ _pad_edges = _sig("dct_cuda_pad_edges_dev", C.c_int, C.c_int, C.c_void_p, C.c_si
                   C.c_void_p)
 
 
+_peer_share = _sig("dct_cuda_peer_default_share", C.c_float, C.c_void_p, C.c_int, C.c_int)
+_fwd_peer = _sig("dct_cuda_fwd_quant_u8_peer", C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t, C.c_int,
+                 C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_void_p)
+_inv_peer = _sig("dct_cuda_dequant_idct_u8_peer", C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int,
+                 C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_float), C.c_void_p)
+
+
 class Frame420(C.Structure):  # dct_cuda_frame420
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("y_width", C.c_int), ("y_height", C.c_int),
                 ("c_width", C.c_int), ("c_height", C.c_int)]
@@ -559,6 +566,41 @@ def decode_rgb420(luma, chroma, ky, kcb, kcr, W, H, layout=NATURAL):
     return rgb, st.as_dict()
 
 
+def _shares(share, n):
+    if share is None:
+        return None
+    assert len(share) == n
+    return (C.c_float * n)(*[float(v) for v in share])
+
+
+def fwd_quant_peer(plans, pixels, layout=NATURAL, coef_out=None, var_out=None, share=None, stream=None):
+    """torch cuda plane resident on plans[0]'s GPU; plans[1:] are NVLink peers working on that memory in place."""
+    import torch
+    assert pixels.is_cuda and pixels.dtype == torch.uint8 and pixels.dim() == 2 and pixels.stride(1) == 1
+    H, W = pixels.shape
+    nb = (H // 8) * (W // 8)
+    coef = coef_out if coef_out is not None else torch.empty((nb, 64), dtype=torch.int16, device=pixels.device)
+    var = var_out
+    if plans[0].adaptive and var is None:
+        var = torch.empty(nb, dtype=torch.float64, device=pixels.device)
+    hs = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    with torch.cuda.device(pixels.device):
+        _check(_fwd_peer(hs, len(plans), pixels.data_ptr(), pixels.stride(0), W, H, coef.data_ptr(), layout,
+                         var.data_ptr() if var is not None else None, _shares(share, len(plans)), _stream_ptr(stream)))
+    return (coef, var) if plans[0].adaptive else coef
+
+
+def dequant_idct_peer(plans, coef, W, H, layout=NATURAL, var=None, pixels_out=None, share=None, stream=None):
+    import torch
+    assert coef.is_cuda and coef.dtype == torch.int16 and coef.is_contiguous()
+    px = pixels_out if pixels_out is not None else torch.empty((H, W), dtype=torch.uint8, device=coef.device)
+    hs = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    with torch.cuda.device(coef.device):
+        _check(_inv_peer(hs, len(plans), coef.data_ptr(), W, H, layout, var.data_ptr() if var is not None else None,
+                         px.data_ptr(), px.stride(0), _shares(share, len(plans)), _stream_ptr(stream)))
+    return px
+
+
 def fwd_quant_multi(plans, pixels, layout=NATURAL):
     """One host plane over several GPUs (block-row ranges, no inter-GPU traffic)."""
     H, W = pixels.shape
@@ -598,4 +640,5 @@ def exported_symbols():
             "dct_cuda_block_to_record", "dct_cuda_host_alloc", "dct_cuda_host_free",
             "dct_cuda_fwd_quant_u8_edge", "dct_cuda_dequant_idct_u8_edge", "dct_cuda_pad_edges_dev",
             "dct_cuda_frame420_geometry", "dct_cuda_rgb_to_ycbcr420_dev", "dct_cuda_ycbcr420_to_rgb_dev",
-            "dct_cuda_encode_rgb420", "dct_cuda_decode_rgb420"]
+            "dct_cuda_encode_rgb420", "dct_cuda_decode_rgb420", "dct_cuda_peer_default_share",
+            "dct_cuda_fwd_quant_u8_peer", "dct_cuda_dequant_idct_u8_peer"]

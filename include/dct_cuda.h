@@ -138,6 +138,24 @@ int dct_cuda_dequant_idct_u8_multi(dct_cuda_plan *const *plans, int n_plans, con
                                    int height, int layout, const double *variance, uint8_t *pixels,
                                    size_t pitch, dct_cuda_stats *stats);
 
+/* ---- several GPUs, data resident on ONE of them (NVLink / NVSwitch peers) ----
+ * d_pixels / d_coef / d_variance live on plans[0]'s GPU (the owner); plans[1..] are plans with the same
+ * tables on other GPUs that can map the owner's memory.  Block-row ranges are dealt out -- peer g gets
+ * share[g] of the rows (share[0] is ignored: the owner keeps the rest; NULL = dct_cuda_peer_default_share
+ * each: a split for plans on the fp64 exact path, which are arithmetic-bound, and NOTHING for the
+ * fused fp32 path, which local HBM serves faster than an NVLink port can -- see DESIGN.md for the
+ * measurement) -- and every GPU runs the ordinary kernels on its range: a peer's loads and stores go straight
+ * to the owner's memory over NVLink, inside the kernel, with no staging copy and no collective.  The
+ * whole call is ordered on `stream` (an owner-GPU stream): it starts after the work queued there before
+ * and work queued there afterwards sees every shard.  Per-plan counters: dct_cuda_stats_fetch on each. */
+float dct_cuda_peer_default_share(const dct_cuda_plan *plan, int n_plans, int forward);
+int dct_cuda_fwd_quant_u8_peer(dct_cuda_plan *const *plans, int n_plans, const uint8_t *d_pixels, size_t pitch,
+                               int width, int height, int16_t *d_coef, int layout, double *d_variance,
+                               const float *share, void *stream);
+int dct_cuda_dequant_idct_u8_peer(dct_cuda_plan *const *plans, int n_plans, const int16_t *d_coef, int width,
+                                  int height, int layout, const double *d_variance, uint8_t *d_pixels, size_t pitch,
+                                  const float *share, void *stream);
+
 /* ---- planar front / back end (NOT in the reference, which starts from whole-block grayscale planes;
  * the conventions are ours and are stated in dct_b200/csrc/planar.cu and DESIGN.md) ----
  *   edges    a plane is completed to whole blocks by replicating its last column / row;

@@ -815,3 +815,68 @@ def test_rgb_frames_encode_and_decode_like_the_oracle_pipeline(api, oracle, shap
         assert err < 40, err                            # sanity: it is the same picture (q75 of the reference is lossy, S2)
         with pytest.raises(api.DctCudaError, match="positive"):
             api.encode_rgb420(luma.plan, chroma.plan, np.zeros((0, 4, 3), np.uint8))
+
+
+# ---------------------------------------------------------------------------------------------
+# NVLink peers working on one GPU's memory
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("adaptive,layout", [(0, 0), (1, 1)])
+def test_peer_calls_on_the_available_gpus(api, oracle, torch, adaptive, layout):
+    """Plane and records resident on GPU 0; every other visible GPU works on that memory in place.  With one
+    GPU this is the degenerate case (the owner does everything); run with >= 2 GPUs for the NVLink path."""
+    n = min(api.device_count(), 4)
+    H, W = 1024, 2048
+    rng = np.random.default_rng(77 + adaptive)
+    px = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
+    Q = oracle.quant_table(60)
+    want_c, want_v, _ = oracle.fwd_quant_plane(px, Q, adaptive, layout, nthreads=8)
+    want_p, _ = oracle.dequant_idct_plane(want_c, W, H, Q, adaptive, layout, want_v, nthreads=8)
+    ctxs = [Ctx(api, 60, adaptive, device=g) for g in range(n)]
+    try:
+        plans = [c.plan for c in ctxs]
+        for share in (None, [0.0] + [1.0 / n] * (n - 1), [0.0] + [0.0] * (n - 1)):
+            d_px = torch.zeros((H, W), dtype=torch.uint8, device="cuda:0")
+            d_px.copy_(torch.from_numpy(px), non_blocking=True)      # queued on the same stream, not waited for
+            out = api.fwd_quant_peer(plans, d_px, layout, share=share)
+            coef, var = out if adaptive else (out, None)
+            rec = api.dequant_idct_peer(plans, coef, W, H, layout, var, share=share)
+            got_p = rec.cpu().numpy()                                # stream-ordered read-back: sees every shard
+            assert np.array_equal(coef.cpu().numpy(), want_c)
+            if adaptive:
+                assert np.array_equal(bits(var.cpu().numpy()), bits(want_v))
+            assert np.array_equal(got_p, want_p)
+        blocks = sum(p.stats()["blocks"] for p in plans)
+        assert blocks == 3 * 2 * (H // 8) * (W // 8)
+        if n > 1:
+            with pytest.raises(api.DctCudaError, match="add up|outside"):
+                api.fwd_quant_peer(plans, d_px, share=[0.0] + [0.9] * (n - 1) if n > 2 else [0.0, 1.5])
+        with pytest.raises(api.DctCudaError, match="share GPU"):
+            api.fwd_quant_peer([plans[0], plans[0]], d_px)
+    finally:
+        for c in ctxs:
+            c.__exit__()
+
+
+def test_peer_default_split_for_exact_path_plans(api, oracle, torch):
+    """A table entry below 1.0 puts the plan on the fp64 exact path (arithmetic-bound): the default deals the rows
+    out evenly, and the result is the reference's bit for bit all the same."""
+    n = min(api.device_count(), 4)
+    H, W = 256, 512
+    px = np.random.default_rng(12).integers(0, 256, size=(H, W), dtype=np.uint8)
+    Q = oracle.quant_table(50)
+    Q[7, 7] = 0.75
+    want_c, _, _ = oracle.fwd_quant_plane(px, Q, 0, 0, nthreads=4)
+    want_p, _ = oracle.dequant_idct_plane(want_c, W, H, Q, 0, 0, None, nthreads=4)
+    ctxs = [Ctx(api, 50, 0, table=Q, device=g) for g in range(n)]
+    try:
+        plans = [c.plan for c in ctxs]
+        assert api._peer_share(plans[0]._h, n, 0) == pytest.approx(1.0 / n if n > 1 else 0.0)
+        assert api._peer_share(plans[0]._h, n, 1) == pytest.approx(0.5 / (1 + 0.5 * (n - 1)) if n > 1 else 0.0)
+        coef = api.fwd_quant_peer(plans, torch.from_numpy(px).cuda())
+        rec = api.dequant_idct_peer(plans, coef, W, H)
+        assert np.array_equal(coef.cpu().numpy(), want_c) and np.array_equal(rec.cpu().numpy(), want_p)
+        per_gpu = [p.stats()["blocks"] for p in plans]
+        assert sum(per_gpu) == 2 * (H // 8) * (W // 8) and all(b > 0 for b in per_gpu)
+    finally:
+        for c in ctxs:
+            c.__exit__()
