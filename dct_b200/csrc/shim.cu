@@ -112,6 +112,7 @@ struct dct_cuda_plan {
     uint8_t *d_frame = nullptr;
     size_t frame_cap = 0;
     cudaEvent_t ev_peer = nullptr;              // *_peer calls: "input ready" (owner) / "shard done" (peers)
+    std::mutex mu;                              // serialises the entry points on one plan (lanes and buffers are state)
 };
 
 namespace {
@@ -510,6 +511,7 @@ extern "C" int dct_cuda_plan_refresh(dct_cuda_plan *p)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     CU_TRY(cudaDeviceSynchronize());
     int rc = read_tables(p);
     if (rc) return rc;
@@ -555,6 +557,7 @@ extern "C" int dct_cuda_fwd_quant_u8_dev(dct_cuda_plan *p, const uint8_t *d_px, 
     int rc = check_plane(d_px, d_coef, pitch, W, H, true, p->n);
     if (rc) return rc;
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     return queue_fwd(p, p->lane[0], d_px, pitch, W, H, d_coef, layout, d_var, (cudaStream_t)stream);
 }
 
@@ -567,6 +570,7 @@ extern "C" int dct_cuda_fwd_quant_f32_dev(dct_cuda_plan *p, const float *d_px, s
     if (rc) return rc;
     if (pitch_bytes % 16) return fail(DCT_CUDA_EINVAL, "float planes need a pitch that is a multiple of 16 bytes");
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     return queue_fwd(p, p->lane[0], (const uint8_t *)d_px, pitch_bytes, W, H, d_coef, layout, nullptr, (cudaStream_t)stream, 4);
 }
 
@@ -577,6 +581,7 @@ extern "C" int dct_cuda_dequant_idct_u8_dev(dct_cuda_plan *p, const int16_t *d_c
     int rc = check_plane(d_px, d_coef, pitch, W, H, true, p->n);
     if (rc) return rc;
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     return queue_inv(p, p->lane[0], d_coef, W, H, layout, d_var, d_px, pitch, (cudaStream_t)stream);
 }
 
@@ -607,6 +612,7 @@ extern "C" int dct_cuda_stats_fetch(dct_cuda_plan *p, dct_cuda_stats *stats, voi
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     return collect_stats(p, stats, (cudaStream_t)stream);
 }
 
@@ -614,6 +620,7 @@ extern "C" int dct_cuda_plan_debug_skip_replay(dct_cuda_plan *p, int skip)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     CU_TRY(cudaDeviceSynchronize());
     for (int l = 0; l < kLanes; ++l)   // skipped replays leave their worklist count behind
         CU_TRY(cudaMemset(&p->lane[l].d_ctr->wl_count, 0, 2 * sizeof(unsigned)));
@@ -633,6 +640,7 @@ extern "C" int dct_cuda_profile_fetch(dct_cuda_plan *p, double *fwd_ms, int *fwd
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     CU_TRY(cudaDeviceSynchronize());
     double ms[2] = {0.0, 0.0};
     int n[2] = {0, 0};
@@ -683,6 +691,7 @@ static int fwd_host_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int
     if (elem == 4 && p->adaptive) return fail(DCT_CUDA_EINVAL, "float pixel tiles are supported for non-adaptive plans only");
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     const int Wp = (W + n - 1) / n * n, Hp = (H + n - 1) / n * n;   // == W, H unless ragged
     const int bw = Wp / n, total_rows = Hp / n, rows = strip_rows(Wp, Hp, n);
     if (rows > 0) {
@@ -728,6 +737,7 @@ extern "C" int dct_cuda_plan_wait(dct_cuda_plan *p, dct_cuda_stats *stats)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     for (int l = 0; l < kLanes; ++l) CU_TRY(cudaStreamSynchronize(p->lane[l].stream));
     if (stats) return collect_stats(p, stats, nullptr);
     return DCT_CUDA_OK;
@@ -751,6 +761,7 @@ static int inv_host_async(dct_cuda_plan *p, const int16_t *coef, int W, int H, i
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     if (p->adaptive && !var) return fail(DCT_CUDA_EINVAL, "adaptive plan needs the per-block variance array");
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     const int Wp = (W + n - 1) / n * n, Hp = (H + n - 1) / n * n;   // == W, H unless ragged
     const int bw = Wp / n, total_rows = Hp / n, rows = strip_rows(Wp, Hp, n);
     if (rows > 0) {
@@ -869,6 +880,7 @@ template <typename F> int peer_run(dct_cuda_plan *const *plans, int n, const std
         if (r1 <= r0) continue;
         dct_cuda_plan *p = plans[g];
         DeviceGuard dg(p->device);
+        std::lock_guard<std::mutex> plan_lock(p->mu);
         cudaStream_t s = p->lane[0].stream;
         CU_TRY(cudaStreamWaitEvent(s, own->ev_peer, 0));
         int rc = queue(p, r0, r1, s);
@@ -876,6 +888,7 @@ template <typename F> int peer_run(dct_cuda_plan *const *plans, int n, const std
         CU_TRY(cudaEventRecord(p->ev_peer, s));
     }
     DeviceGuard dg(own->device);
+    std::lock_guard<std::mutex> plan_lock(own->mu);
     if (row_end[0] > 0) {
         int rc = queue(own, 0, row_end[0], stream);
         if (rc) return rc;
@@ -1057,6 +1070,7 @@ int frame_prepare(dct_cuda_plan *luma, dct_cuda_plan *chroma, int W, int H, int 
     if (W <= 0 || H <= 0) return fail(DCT_CUDA_EINVAL, "width and height must be positive (got %dx%d)", W, H);
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     *f = frame_layout(W, H);
+    std::lock_guard<std::mutex> plan_lock(luma->mu);
     if (luma->frame_cap < f->bytes) {
         CU_TRY(cudaDeviceSynchronize());
         if (luma->d_frame) cudaFree(luma->d_frame);
@@ -1091,6 +1105,9 @@ extern "C" int dct_cuda_encode_rgb420(dct_cuda_plan *luma, dct_cuda_plan *chroma
     if (!rgb || !coef_y || !coef_cb || !coef_cr) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
     if (rgb_pitch < (size_t)W * 3) return fail(DCT_CUDA_EINVAL, "pitch %zu must be >= 3 * width", rgb_pitch);
     DeviceGuard dg(luma->device);
+    std::unique_lock<std::mutex> lock_l(luma->mu, std::defer_lock), lock_c(chroma->mu, std::defer_lock);
+    if (chroma != luma) std::lock(lock_l, lock_c);
+    else lock_l.lock();
     uint8_t *base = luma->d_frame;
     cudaStream_t s = luma->lane[0].stream;
     CU_TRY(cudaMemcpy2DAsync(base, f.rgb_pitch, rgb, rgb_pitch, (size_t)W * 3, (size_t)H, cudaMemcpyHostToDevice, s));
@@ -1116,6 +1133,9 @@ extern "C" int dct_cuda_decode_rgb420(dct_cuda_plan *luma, dct_cuda_plan *chroma
     if (!rgb || !coef_y || !coef_cb || !coef_cr) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
     if (rgb_pitch < (size_t)W * 3) return fail(DCT_CUDA_EINVAL, "pitch %zu must be >= 3 * width", rgb_pitch);
     DeviceGuard dg(luma->device);
+    std::unique_lock<std::mutex> lock_l(luma->mu, std::defer_lock), lock_c(chroma->mu, std::defer_lock);
+    if (chroma != luma) std::lock(lock_l, lock_c);
+    else lock_l.lock();
     uint8_t *base = luma->d_frame;
     cudaStream_t s = luma->lane[0].stream;
     int16_t *ky = (int16_t *)(base + f.off_ky), *kcb = (int16_t *)(base + f.off_kcb), *kcr = (int16_t *)(base + f.off_kcr);
@@ -1202,6 +1222,7 @@ extern "C" int dct_cuda_rle_count_dev(dct_cuda_plan *p, const int16_t *d_coef, s
     if (nblocks > (1u << 26)) return fail(DCT_CUDA_EINVAL, "at most 2^26 records per call (32-bit symbol offsets)");
     if ((uintptr_t)d_coef % 16) return fail(DCT_CUDA_EINVAL, "coefficients must be 16-byte aligned");
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     cudaStream_t s = (cudaStream_t)stream;
     if (!p->d_rle_total) CU_TRY(cudaMalloc(&p->d_rle_total, sizeof(unsigned long long)));
     const size_t ctas = (nblocks + 255) / 256;
@@ -1235,6 +1256,7 @@ extern "C" int dct_cuda_rle_emit_dev(dct_cuda_plan *p, const int16_t *d_coef, si
     if (((uintptr_t)d_coef % 16) || ((uintptr_t)d_symbols % 8)) return fail(DCT_CUDA_EINVAL, "misaligned buffer");
     if (nblocks == 0) return DCT_CUDA_OK;
     DeviceGuard g(p->device);
+    std::lock_guard<std::mutex> plan_lock(p->mu);
     CU_TRY(launch_rle_emit(d_coef, (uint32_t)nblocks, layout, d_offsets, d_symbols, (cudaStream_t)stream));
     return DCT_CUDA_OK;
 }
@@ -1286,6 +1308,7 @@ struct BlockScratch {
     double *h = nullptr;      // pinned: 3 * 1024 doubles
     int *h_int = nullptr;     // pinned: 1024 ints
     cudaStream_t stream = nullptr;
+    int device = 0;           // the device that was current on first use; every later call switches to it
 };
 std::mutex g_block_mu;
 BlockScratch g_block;
@@ -1304,6 +1327,7 @@ BlockScratch g_block;
 BlockScratch &scratch()
 {
     if (!g_block.ready) {
+        CU_DIE(cudaGetDevice(&g_block.device));
         CU_DIE(cudaMalloc(&g_block.d_tab, 1024 * sizeof(double)));
         CU_DIE(cudaMalloc(&g_block.d_in, 1024 * sizeof(double)));
         CU_DIE(cudaMalloc(&g_block.d_out, 1024 * sizeof(double)));
@@ -1330,6 +1354,7 @@ void block_transform(DCTContext *ctx, double **input, double **output, int inver
     check_n(n);
     std::lock_guard<std::mutex> lk(g_block_mu);
     BlockScratch &s = scratch();
+    DeviceGuard dg(s.device);
     double *hD = s.h, *hI = s.h + 1024, *hO = s.h + 2048;
     for (int i = 0; i < n; ++i) {
         memcpy(hD + i * n, ctx->dct_matrix[i], n * sizeof(double));   // rows are separate mallocs
@@ -1355,6 +1380,7 @@ extern "C" void quantize(QuantContext *ctx, double **dct_coeffs, int **quant_coe
     check_n(n);
     std::lock_guard<std::mutex> lk(g_block_mu);
     BlockScratch &s = scratch();
+    DeviceGuard dg(s.device);
     double *hQ = s.h, *hC = s.h + 1024;
     for (int i = 0; i < n; ++i) {
         memcpy(hQ + i * n, ctx->quant_matrix[i], n * sizeof(double));
@@ -1375,6 +1401,7 @@ extern "C" void dequantize(QuantContext *ctx, int **quant_coeffs, double **dct_c
     check_n(n);
     std::lock_guard<std::mutex> lk(g_block_mu);
     BlockScratch &s = scratch();
+    DeviceGuard dg(s.device);
     double *hR = s.h, *hO = s.h + 2048;
     for (int i = 0; i < n; ++i) {
         memcpy(hR + i * n, ctx->dequant_matrix[i], n * sizeof(double));

@@ -880,3 +880,42 @@ def test_peer_default_split_for_exact_path_plans(api, oracle, torch):
     finally:
         for c in ctxs:
             c.__exit__()
+
+
+# ---------------------------------------------------------------------------------------------
+# threading: the reference has no globals, so concurrent calls on shared contexts are legal there
+# ---------------------------------------------------------------------------------------------
+def test_concurrent_callers_on_shared_contexts_and_plans(api, oracle):
+    import threading
+    rng = np.random.default_rng(99)
+    Q = oracle.quant_table(50)
+    blocks = [rng.uniform(-128, 127, size=(8, 8)) for _ in range(6)]
+    want_blocks = [(oracle.dct_forward(b), oracle.quantize(Q, oracle.dct_forward(b))) for b in blocks]
+    planes = [rng.integers(0, 256, size=(256 + 8 * t, 512), dtype=np.uint8) for t in range(6)]
+    want_planes = [oracle.fwd_quant_plane(p, Q, 0, 0, nthreads=2)[0] for p in planes]
+    errors = []
+    with Ctx(api, 50, 0) as shared:
+        own = [Ctx(api, 50, 0) for _ in range(3)]
+
+        def worker(t):
+            try:
+                for it in range(10):
+                    c = api.dct_forward(shared.d, blocks[t])                    # per-block calls, shared contexts
+                    assert np.array_equal(bits(c), bits(want_blocks[t][0]))
+                    assert np.array_equal(api.quantize(shared.q, c), want_blocks[t][1])
+                    plan = shared.plan if t < 3 else own[t - 3].plan            # three threads share ONE plan
+                    got = plan.fwd_quant(planes[t])
+                    assert np.array_equal(got, want_planes[t])
+                    rec = plan.dequant_idct(got, planes[t].shape[1], planes[t].shape[0])
+                    assert rec.shape == planes[t].shape
+            except BaseException as e:  # noqa: BLE001 - reported below
+                errors.append((t, repr(e)))
+
+        threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        for c in own:
+            c.__exit__()
+    assert not errors, errors
