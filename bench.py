@@ -269,14 +269,14 @@ def main():
     # pixels and leaves int16 records in pinned memory (where the untouched host entropy coder would
     # take them), inverse reads those records from pinned memory and leaves pixels in pinned memory.
     #   sync      : the two synchronous C-ABI calls back to back (forward is D2H-bound, inverse H2D-bound)
-    #   pipelined : the asynchronous forms on two plans; forward of step i overlaps inverse of step i-1,
-    #               so both PCIe directions are busy.  K steps take K+1 slots (fill + drain are timed).
+    #   pipelined : the asynchronous forms on two plans; forward of step i+1 overlaps inverse of step i,
+    #               so both PCIe directions are busy (fill + drain are timed).
     e2e_frames = min(frames, 32)
     e_rows = e2e_frames * H
     e_px, e_nb = e_rows * W, e_rows * W // 64
     h_px = torch.empty((e_rows, W), dtype=torch.uint8).pin_memory()
     h_px.copy_(px[:e_rows].cpu())
-    h_coef = [torch.empty((e_nb, 64), dtype=torch.int16).pin_memory() for _ in range(2)]
+    h_coef = [torch.empty((e_nb, 64), dtype=torch.int16).pin_memory() for _ in range(3)]
     h_rec = torch.empty((e_rows, W), dtype=torch.uint8).pin_memory()
 
     e2e = None
@@ -288,13 +288,16 @@ def main():
             plan_inv.dequant_idct_ptr(h_coef[0].data_ptr(), W, e_rows, h_rec.data_ptr(), W, args.layout)
 
         def e2e_pipelined(n):
-            for i in range(n + 1):
-                if i < n:
-                    plan.fwd_quant_ptr_async(h_px.data_ptr(), W, W, e_rows, h_coef[i & 1].data_ptr(), args.layout)
-                if i > 0:
-                    plan_inv.dequant_idct_ptr_async(h_coef[(i - 1) & 1].data_ptr(), W, e_rows, h_rec.data_ptr(), W, args.layout)
-                plan.wait()
-                plan_inv.wait()
+            # three record buffers decouple the two plans: forward i+1 is queued as soon as forward i is home,
+            # inverse i as soon as inverse i-1 is; neither waits for the other beyond the data dependency
+            plan.fwd_quant_ptr_async(h_px.data_ptr(), W, W, e_rows, h_coef[0].data_ptr(), args.layout)
+            for i in range(n):
+                plan.wait()                                            # records of step i are in h_coef[i % 3]
+                if i + 1 < n:
+                    plan.fwd_quant_ptr_async(h_px.data_ptr(), W, W, e_rows, h_coef[(i + 1) % 3].data_ptr(), args.layout)
+                plan_inv.wait()                                        # inverse i-1 is home (frees h_rec)
+                plan_inv.dequant_idct_ptr_async(h_coef[i % 3].data_ptr(), W, e_rows, h_rec.data_ptr(), W, args.layout)
+            plan_inv.wait()
 
         def timed(fn):
             barrier()

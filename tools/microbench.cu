@@ -76,6 +76,32 @@ struct OpDFMA { static __device__ __forceinline__ void run(double &r) { asm vola
 struct OpDADD { static __device__ __forceinline__ void run(double &r) { asm volatile("add.rn.f64 %0, %0, %0;" : "+d"(r)); } };
 struct OpDMUL { static __device__ __forceinline__ void run(double &r) { asm volatile("mul.rn.f64 %0, %0, %0;" : "+d"(r)); } };
 
+// mixed issue: 8 packed chains + S scalar chains per iteration -- do scalar FP32 / integer instructions overlap with
+// the packed ones (separate pipe) or queue behind them (same pipe)?
+template <typename OpS, int S> __global__ void __launch_bounds__(256) kmix(unsigned long long *out, unsigned long long seed)
+{
+    unsigned long long r[8];
+    uint32_t q[S > 0 ? S : 1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = seed + threadIdx.x * 8 + i;
+#pragma unroll
+    for (int i = 0; i < S; ++i) q[i] = (uint32_t)seed + threadIdx.x * 3 + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(r[i]));
+#pragma unroll
+            for (int j = 0; j < S / 8; ++j) OpS::run(q[i * (S / 8) + j]);
+        }
+    }
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc ^= r[i];
+#pragma unroll
+    for (int i = 0; i < S; ++i) acc ^= q[i];
+    if (acc == 0x12345678ull) out[threadIdx.x] = acc;
+}
+
 template <typename F> static void timeit(const char *name, F launch, double ops_per_thread, int sms, double mhz)
 {
     cudaEvent_t e0, e1;
@@ -115,5 +141,22 @@ int main()
     printf("-- packed fp32x2 (each instruction = 2 fp32 operations per lane; rate below counts instructions)\n");
 #define TL(OP) timeit(#OP, [&] { kl<OP><<<grid, block>>>((unsigned long long *)outd, 1ull); }, 8.0 * ITERS, sms, mhz)
     TL(OpFFMA2); TL(OpFADD2); TL(OpFMUL2);
+    printf("-- 8 FFMA2 + S other instructions per iteration; clk per iteration per SMSP with 8 warps resident (8 FFMA2 alone ~ 134)\n");
+#define TM(OP, S)                                                                                                        \
+    do {                                                                                                                 \
+        cudaEvent_t e0, e1;                                                                                              \
+        cudaEventCreate(&e0), cudaEventCreate(&e1);                                                                      \
+        kmix<OP, S><<<grid, block>>>((unsigned long long *)outd, 1ull);                                                  \
+        cudaDeviceSynchronize();                                                                                         \
+        cudaEventRecord(e0);                                                                                             \
+        kmix<OP, S><<<grid, block>>>((unsigned long long *)outd, 1ull);                                                  \
+        cudaEventRecord(e1);                                                                                             \
+        cudaEventSynchronize(e1);                                                                                        \
+        float ms;                                                                                                        \
+        cudaEventElapsedTime(&ms, e0, e1);                                                                               \
+        printf("8 FFMA2 + %2d %-9s %8.3f ms  %7.1f clk per iteration per SMSP\n", S, #OP, ms, ms * 1e-3 * mhz * 1e6 / ITERS); \
+    } while (0)
+    TM(OpFFMA, 0); TM(OpFFMA, 8); TM(OpFFMA, 16); TM(OpFADD, 8); TM(OpPRMT, 8); TM(OpPRMT, 16); TM(OpIADD, 8); TM(OpIADD, 16);
+    TM(OpFMNMX, 8); TM(OpLOP3, 16);
     return 0;
 }
