@@ -919,3 +919,29 @@ def test_concurrent_callers_on_shared_contexts_and_plans(api, oracle):
         for c in own:
             c.__exit__()
     assert not errors, errors
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded random sweep: shapes x qualities x modes x content, every case bit-exact against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(24))
+def test_random_configurations_round_trip_bit_exact(api, oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    H, W = 8 * int(rng.integers(1, 60)), 8 * int(rng.integers(1, 90))
+    quality, adaptive, layout = int(rng.integers(1, 101)), int(rng.integers(0, 2)), int(rng.integers(0, 2))
+    kind = seed % 6
+    yy, xx = np.mgrid[0:H, 0:W]
+    if kind == 0:
+        px = rng.integers(0, 256, size=(H, W))
+    elif kind == 1:                                        # smooth gradient + faint noise
+        px = 128 + 100 * np.sin(0.05 * xx) * np.cos(0.03 * yy) + rng.integers(-4, 5, size=(H, W))
+    elif kind == 2:                                        # flat blocks with block sums on tie positions (forced DC ties)
+        px = np.repeat(np.repeat(rng.integers(0, 256, size=(H // 8, W // 8)), 8, 0), 8, 1)
+    elif kind == 3:                                        # saturated checkerboard: the largest AC amplitudes
+        px = 255 * ((xx + yy) & 1)
+    elif kind == 4:                                        # sparse impulses on black
+        px = np.where(rng.random((H, W)) < 0.02, 255, 0)
+    else:                                                  # low-amplitude noise around mid-grey: many zeros after quantisation
+        px = 128 + rng.integers(-3, 4, size=(H, W))
+    px = np.clip(px, 0, 255).astype(np.uint8)
+    roundtrip_check(api, oracle, px, quality, adaptive, layout, nthreads=4)
