@@ -131,6 +131,16 @@ _pad_edges = _sig("dct_cuda_pad_edges_dev", C.c_int, C.c_int, C.c_void_p, C.c_si
                   C.c_void_p)
 
 
+_fits_i8 = _sig("dct_cuda_plan_records_fit_i8", C.c_int, C.c_void_p)
+_fwd_i8 = _sig("dct_cuda_fwd_quant_u8_i8", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+               C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Stats))
+_inv_i8 = _sig("dct_cuda_dequant_idct_i8_u8", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+               C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Stats))
+_fwd_i8_async = _sig("dct_cuda_fwd_quant_u8_i8_async", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                     C.c_void_p, C.c_int, C.c_void_p)
+_inv_i8_async = _sig("dct_cuda_dequant_idct_i8_u8_async", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                     C.c_void_p, C.c_void_p, C.c_size_t)
+_rec8_to_block = _sig("dct_cuda_record8_to_block", None, C.POINTER(C.c_int8), C.c_int, _PP_I)
 _peer_share = _sig("dct_cuda_peer_default_share", C.c_float, C.c_void_p, C.c_int, C.c_int)
 _fwd_peer = _sig("dct_cuda_fwd_quant_u8_peer", C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t, C.c_int,
                  C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_void_p)
@@ -295,6 +305,13 @@ def set_quant_table(qctx, table):
             qctx.contents.dequant_matrix[i][j] = 1.0 / t[i, j]
 
 
+def record8_to_block(record8, layout=NATURAL):
+    rec = np.ascontiguousarray(record8, dtype=np.int8)
+    blk = _Ragged(8, C.c_int)
+    _rec8_to_block(rec.ctypes.data_as(C.POINTER(C.c_int8)), layout, blk.ptr)
+    return blk.numpy()
+
+
 def record_to_block(record, layout=NATURAL):
     rec = np.ascontiguousarray(record, dtype=np.int16)
     b = _Ragged(8, C.c_int)
@@ -408,6 +425,40 @@ class Plan:
 
     def dequant_idct_ptr_async(self, coef_ptr, W, H, px_ptr, pitch, layout=NATURAL, var_ptr=None):
         _check(_inv_host_async(self._h, coef_ptr, W, H, layout, var_ptr, px_ptr, pitch))
+
+    # -- int8 records over PCIe (host arrays; only when records_fit_i8) --------------------------
+    @property
+    def records_fit_i8(self) -> bool:
+        return bool(_fits_i8(self._h))
+
+    def fwd_quant_i8(self, pixels, layout=NATURAL, want_stats=False):
+        assert pixels.dtype == np.uint8 and pixels.ndim == 2 and pixels.strides[1] == 1
+        H, W = pixels.shape
+        n = self.n
+        nb = (H // n) * (W // n)
+        coef = np.empty((nb, n * n), dtype=np.int8)
+        var = np.empty(nb, dtype=np.float64) if self.adaptive else None
+        st = Stats()
+        _check(_fwd_i8(self._h, pixels.ctypes.data, pixels.strides[0], W, H, coef.ctypes.data, layout,
+                       var.ctypes.data if var is not None else None, C.byref(st)))
+        out = (coef, var) if self.adaptive else coef
+        return (out, st.as_dict()) if want_stats else out
+
+    def dequant_idct_i8(self, coef8, W, H, layout=NATURAL, var=None, want_stats=False):
+        coef8 = np.ascontiguousarray(coef8, dtype=np.int8)
+        px = np.empty((H, W), dtype=np.uint8)
+        if var is not None:
+            var = np.ascontiguousarray(var, dtype=np.float64)
+        st = Stats()
+        _check(_inv_i8(self._h, coef8.ctypes.data, W, H, layout, var.ctypes.data if var is not None else None,
+                       px.ctypes.data, px.strides[0], C.byref(st)))
+        return (px, st.as_dict()) if want_stats else px
+
+    def fwd_quant_i8_ptr_async(self, px_ptr, pitch, W, H, coef_ptr, layout=NATURAL, var_ptr=None):
+        _check(_fwd_i8_async(self._h, px_ptr, pitch, W, H, coef_ptr, layout, var_ptr))
+
+    def dequant_idct_i8_ptr_async(self, coef_ptr, W, H, px_ptr, pitch, layout=NATURAL, var_ptr=None):
+        _check(_inv_i8_async(self._h, coef_ptr, W, H, layout, var_ptr, px_ptr, pitch))
 
     def wait(self, want_stats=False):
         st = Stats()
@@ -641,4 +692,6 @@ def exported_symbols():
             "dct_cuda_fwd_quant_u8_edge", "dct_cuda_dequant_idct_u8_edge", "dct_cuda_pad_edges_dev",
             "dct_cuda_frame420_geometry", "dct_cuda_rgb_to_ycbcr420_dev", "dct_cuda_ycbcr420_to_rgb_dev",
             "dct_cuda_encode_rgb420", "dct_cuda_decode_rgb420", "dct_cuda_peer_default_share",
-            "dct_cuda_fwd_quant_u8_peer", "dct_cuda_dequant_idct_u8_peer"]
+            "dct_cuda_fwd_quant_u8_peer", "dct_cuda_dequant_idct_u8_peer", "dct_cuda_plan_records_fit_i8",
+            "dct_cuda_fwd_quant_u8_i8", "dct_cuda_dequant_idct_i8_u8", "dct_cuda_fwd_quant_u8_i8_async",
+            "dct_cuda_dequant_idct_i8_u8_async", "dct_cuda_record8_to_block"]

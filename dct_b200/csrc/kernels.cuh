@@ -136,6 +136,10 @@ cudaError_t launch_rgb_to_ycbcr420(const PlanarParams &p, cudaStream_t s);
 cudaError_t launch_ycbcr420_to_rgb(const PlanarParams &p, cudaStream_t s);
 cudaError_t launch_pad_edges(uint8_t *px, long long pitch, int W, int H, int Wp, int Hp, int elem, cudaStream_t s);
 
+// int16 <-> int8 records for the PCIe-bound host-plane calls (narrow.cu); n = coefficients, a multiple of 64
+cudaError_t launch_narrow_records(const int16_t *d_in, int8_t *d_out, size_t n, Counters *ctr, cudaStream_t s);
+cudaError_t launch_widen_records(const int8_t *d_in, int16_t *d_out, size_t n, cudaStream_t s);
+
 // generic-N single block kernels behind the per-block drop-in API (K4/K6)
 cudaError_t launch_block_dct_f64(int n, const double *d_D, const double *d_in, double *d_out, int inverse,
                                  cudaStream_t s);

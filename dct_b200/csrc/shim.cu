@@ -112,6 +112,7 @@ struct dct_cuda_plan {
     uint8_t *d_frame = nullptr;
     size_t frame_cap = 0;
     cudaEvent_t ev_peer = nullptr;              // *_peer calls: "input ready" (owner) / "shard done" (peers)
+    bool fits_i8 = false;                       // every quantised value of a uint8 plane fits int8 (narrow.cu)
     std::mutex mu;                              // serialises the entry points on one plan (lanes and buffers are state)
 };
 
@@ -140,6 +141,12 @@ int read_tables(dct_cuda_plan *p)
                     d->block_size, q->block_size);
     p->n = d->block_size;
     p->adaptive = q->adaptive ? 1 : 0;
+    // |c| <= n * 128 for centred 8-bit pixels (orthonormal transform), so |round(c / Q)| <= 127 whenever every
+    // Q >= n * 128 / 127.5; the adaptive table only grows (Q * (2 - nv) >= Q, DC untouched)
+    p->fits_i8 = true;
+    for (int i = 0; i < p->n; ++i)
+        for (int j = 0; j < p->n; ++j)
+            if (!(q->quant_matrix[i][j] >= p->n * 128.0 / 127.5)) p->fits_i8 = false;
     if (p->n != 8) return DCT_CUDA_OK;   // K6 reads the contexts' tables as they are (upload_generic_tables)
     bool exotic = false;
     for (int i = 0; i < 8; ++i)
@@ -421,8 +428,8 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
     return DCT_CUDA_OK;
 }
 
-// device strip buffers of one lane, sized in pixels: `pixels * elem` bytes of pixels, 2 bytes of record per
-// pixel, one variance per block
+// device strip buffers of one lane, sized in pixels: `pixels * elem` bytes of pixels, 2 + 1 bytes of record per
+// pixel (int16 and int8 form), one variance per block
 int ensure_strip_buffers(dct_cuda_plan *p, Lane &ln, size_t pixels, int elem = 1)
 {
     const size_t need = pixels * (size_t)elem;
@@ -433,7 +440,7 @@ int ensure_strip_buffers(dct_cuda_plan *p, Lane &ln, size_t pixels, int elem = 1
     if (ln.d_var) cudaFree(ln.d_var);
     ln.d_px = nullptr, ln.d_coef = nullptr, ln.d_var = nullptr, ln.cap_blocks = 0;
     CU_TRY(cudaMalloc(&ln.d_px, need));
-    CU_TRY(cudaMalloc(&ln.d_coef, need * 2));
+    CU_TRY(cudaMalloc(&ln.d_coef, need * 3));      // int16 records, then their int8 form (narrow.cu)
     if (p->adaptive) CU_TRY(cudaMalloc(&ln.d_var, (need / ((size_t)p->n * p->n) + 1) * sizeof(double)));
     ln.cap_blocks = need;
     return DCT_CUDA_OK;
@@ -681,10 +688,13 @@ static int strip_rows(int W, int H, int n = 8)
 
 // `ragged`: W and H are any positive sizes; the strips are completed to whole blocks on the device by
 // replicating the last column / row (planar.cu), so the records cover ceil(W/n) x ceil(H/n) blocks
-static int fwd_host_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H, int16_t *coef, int layout,
-                          double *var, int elem, bool ragged = false)
+static int fwd_host_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H, void *coef, int layout,
+                          double *var, int elem, bool ragged = false, bool rec8 = false)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
+    if (rec8 && !p->fits_i8)
+        return fail(DCT_CUDA_EINVAL, "int8 records need every table entry >= %.3f (dct_cuda_plan_records_fit_i8)",
+                    p->n * 128.0 / 127.5);
     const int n = p->n, nn = n * n;
     int rc = ragged ? check_ragged(px, coef, pitch / elem, W, H, n) : check_plane(px, coef, pitch / elem, W, H, false, n);
     if (rc) return rc;
@@ -709,7 +719,13 @@ static int fwd_host_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int
             if (Wp != W || have != nr * n)
                 CU_TRY(launch_pad_edges(ln.d_px, (long long)dev_pitch, W, have, Wp, nr * n, elem, ln.stream));
             if ((rc = queue_fwd(p, ln, ln.d_px, dev_pitch, Wp, nr * n, ln.d_coef, layout, ln.d_var, ln.stream, elem))) return rc;
-            CU_TRY(cudaMemcpyAsync(coef + b0 * nn, ln.d_coef, nb * nn * 2, cudaMemcpyDeviceToHost, ln.stream));
+            if (rec8) {
+                int8_t *d8 = reinterpret_cast<int8_t *>(ln.d_coef) + ln.cap_blocks * 2;
+                CU_TRY(launch_narrow_records(ln.d_coef, d8, nb * nn, ln.d_ctr, ln.stream));
+                CU_TRY(cudaMemcpyAsync((int8_t *)coef + b0 * nn, d8, nb * nn, cudaMemcpyDeviceToHost, ln.stream));
+            } else {
+                CU_TRY(cudaMemcpyAsync((int16_t *)coef + b0 * nn, ln.d_coef, nb * nn * 2, cudaMemcpyDeviceToHost, ln.stream));
+            }
             if (p->adaptive && var)
                 CU_TRY(cudaMemcpyAsync(var + b0, ln.d_var, nb * sizeof(double), cudaMemcpyDeviceToHost, ln.stream));
         }
@@ -751,8 +767,8 @@ extern "C" int dct_cuda_fwd_quant_u8(dct_cuda_plan *p, const uint8_t *px, size_t
     return dct_cuda_plan_wait(p, stats);
 }
 
-static int inv_host_async(dct_cuda_plan *p, const int16_t *coef, int W, int H, int layout, const double *var, uint8_t *px,
-                          size_t pitch, bool ragged = false)
+static int inv_host_async(dct_cuda_plan *p, const void *coef, int W, int H, int layout, const double *var, uint8_t *px,
+                          size_t pitch, bool ragged = false, bool rec8 = false)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     const int n = p->n, nn = n * n;
@@ -773,7 +789,13 @@ static int inv_host_async(dct_cuda_plan *p, const int16_t *coef, int W, int H, i
             const int nr = std::min(rows, total_rows - r0);
             const int have = std::min(nr * n, H - r0 * n);               // image rows in this strip
             const size_t nb = (size_t)nr * bw, b0 = (size_t)r0 * bw;
-            CU_TRY(cudaMemcpyAsync(ln.d_coef, coef + b0 * nn, nb * nn * 2, cudaMemcpyHostToDevice, ln.stream));
+            if (rec8) {
+                int8_t *d8 = reinterpret_cast<int8_t *>(ln.d_coef) + ln.cap_blocks * 2;
+                CU_TRY(cudaMemcpyAsync(d8, (const int8_t *)coef + b0 * nn, nb * nn, cudaMemcpyHostToDevice, ln.stream));
+                CU_TRY(launch_widen_records(d8, ln.d_coef, nb * nn, ln.stream));
+            } else {
+                CU_TRY(cudaMemcpyAsync(ln.d_coef, (const int16_t *)coef + b0 * nn, nb * nn * 2, cudaMemcpyHostToDevice, ln.stream));
+            }
             if (p->adaptive)
                 CU_TRY(cudaMemcpyAsync(ln.d_var, var + b0, nb * sizeof(double), cudaMemcpyHostToDevice, ln.stream));
             if ((rc = queue_inv(p, ln, ln.d_coef, Wp, nr * n, layout, ln.d_var, ln.d_px, (size_t)Wp, ln.stream))) return rc;
@@ -1149,6 +1171,45 @@ extern "C" int dct_cuda_decode_rgb420(dct_cuda_plan *luma, dct_cuda_plan *chroma
                                                 base + f.off_cr, f.c_pitch), s));
     CU_TRY(cudaMemcpy2DAsync(rgb, rgb_pitch, base, f.rgb_pitch, (size_t)W * 3, (size_t)H, cudaMemcpyDeviceToHost, s));
     return frame_stats(luma, chroma, s, stats);
+}
+
+// ---- int8 records over PCIe (narrow.cu): same calls, half the record bytes, when the table allows it ----
+extern "C" int dct_cuda_plan_records_fit_i8(const dct_cuda_plan *p) { return p && p->fits_i8 ? 1 : 0; }
+
+extern "C" int dct_cuda_fwd_quant_u8_i8_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H,
+                                              int8_t *coef8, int layout, double *var)
+{
+    return fwd_host_async(p, px, pitch, W, H, coef8, layout, var, 1, false, true);
+}
+
+extern "C" int dct_cuda_dequant_idct_i8_u8_async(dct_cuda_plan *p, const int8_t *coef8, int W, int H, int layout,
+                                                 const double *var, uint8_t *px, size_t pitch)
+{
+    return inv_host_async(p, coef8, W, H, layout, var, px, pitch, false, true);
+}
+
+extern "C" int dct_cuda_fwd_quant_u8_i8(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H, int8_t *coef8,
+                                        int layout, double *var, dct_cuda_stats *stats)
+{
+    int rc = dct_cuda_fwd_quant_u8_i8_async(p, px, pitch, W, H, coef8, layout, var);
+    if (rc) return rc;
+    return dct_cuda_plan_wait(p, stats);
+}
+
+extern "C" int dct_cuda_dequant_idct_i8_u8(dct_cuda_plan *p, const int8_t *coef8, int W, int H, int layout,
+                                           const double *var, uint8_t *px, size_t pitch, dct_cuda_stats *stats)
+{
+    int rc = dct_cuda_dequant_idct_i8_u8_async(p, coef8, W, H, layout, var, px, pitch);
+    if (rc) return rc;
+    return dct_cuda_plan_wait(p, stats);
+}
+
+extern "C" void dct_cuda_record8_to_block(const int8_t *rec, int layout, int **block)
+{
+    for (int k = 0; k < 64; ++k) {
+        const int nat = layout == DCT_CUDA_ZIGZAG ? kZigZag.nat[k] : k;
+        block[nat >> 3][nat & 7] = rec[k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -138,6 +138,26 @@ int dct_cuda_dequant_idct_u8_multi(dct_cuda_plan *const *plans, int n_plans, con
                                    int height, int layout, const double *variance, uint8_t *pixels,
                                    size_t pitch, dct_cuda_stats *stats);
 
+/* ---- int8 records for the host-plane calls ----
+ * The host-plane calls are bound by the PCIe link, and two of their three bytes per pixel are records.
+ * When every entry of the plan's table is >= block_size * 128 / 127.5 (8.03 for 8x8: quality <= ~56 with the
+ * reference's luminance table) no quantised value of an 8-bit plane can leave [-127, 127], so the same
+ * record fits 64 BYTES: these calls are dct_cuda_fwd_quant_u8 / dct_cuda_dequant_idct_u8 with int8 records
+ * on the host side (same order, same values) and half the record traffic.  The forward calls fail with
+ * DCT_CUDA_EINVAL when dct_cuda_plan_records_fit_i8(plan) is 0; decoding int8 records works with any table.
+ * On the device the records stay int16. */
+int dct_cuda_plan_records_fit_i8(const dct_cuda_plan *plan);
+int dct_cuda_fwd_quant_u8_i8(dct_cuda_plan *plan, const uint8_t *pixels, size_t pitch, int width, int height,
+                             int8_t *coef8, int layout, double *variance, dct_cuda_stats *stats);
+int dct_cuda_dequant_idct_i8_u8(dct_cuda_plan *plan, const int8_t *coef8, int width, int height, int layout,
+                                const double *variance, uint8_t *pixels, size_t pitch, dct_cuda_stats *stats);
+int dct_cuda_fwd_quant_u8_i8_async(dct_cuda_plan *plan, const uint8_t *pixels, size_t pitch, int width, int height,
+                                   int8_t *coef8, int layout, double *variance);
+int dct_cuda_dequant_idct_i8_u8_async(dct_cuda_plan *plan, const int8_t *coef8, int width, int height, int layout,
+                                      const double *variance, uint8_t *pixels, size_t pitch);
+/* widen one 64-byte record into a ragged 8x8 int block in NATURAL order (cf. dct_cuda_record_to_block) */
+void dct_cuda_record8_to_block(const int8_t *record, int layout, int **block);
+
 /* ---- several GPUs, data resident on ONE of them (NVLink / NVSwitch peers) ----
  * d_pixels / d_coef / d_variance live on plans[0]'s GPU (the owner); plans[1..] are plans with the same
  * tables on other GPUs that can map the owner's memory.  Block-row ranges are dealt out -- peer g gets

@@ -945,3 +945,43 @@ def test_random_configurations_round_trip_bit_exact(api, oracle, seed):
         px = 128 + rng.integers(-3, 4, size=(H, W))
     px = np.clip(px, 0, 255).astype(np.uint8)
     roundtrip_check(api, oracle, px, quality, adaptive, layout, nthreads=4)
+
+
+# ---------------------------------------------------------------------------------------------
+# int8 records over PCIe: same values as the int16 records whenever the table allows them
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("quality,adaptive,layout", [(50, 0, 0), (10, 0, 1), (55, 1, 1), (30, 1, 0)])
+def test_int8_records_equal_the_int16_records(api, oracle, quality, adaptive, layout):
+    rng = np.random.default_rng(quality)
+    H, W = 1080, 1920
+    px = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
+    px[:8, :16] = 0                                        # DC = -1024: the largest magnitude there is
+    px[8:16, :8] = 255
+    px[16:24, :16] = np.tile(np.array([[0, 255], [255, 0]], np.uint8), (4, 8))
+    Q = oracle.quant_table(quality)
+    want_c, want_v, _ = oracle.fwd_quant_plane(px, Q, adaptive, layout, nthreads=8)
+    want_p, _ = oracle.dequant_idct_plane(want_c, W, H, Q, adaptive, layout, want_v, nthreads=8)
+    assert np.abs(want_c).max() <= 127
+    with Ctx(api, quality, adaptive) as cx:
+        assert cx.plan.records_fit_i8
+        out, st = cx.plan.fwd_quant_i8(px, layout, want_stats=True)
+        c8, var = out if adaptive else (out, None)
+        assert c8.dtype == np.int8 and np.array_equal(c8.astype(np.int16), want_c)
+        assert st["saturated"] == 0 and st["blocks"] == (H // 8) * (W // 8)
+        rec = cx.plan.dequant_idct_i8(c8, W, H, layout, var)
+        assert np.array_equal(rec, want_p)
+        b = 7
+        assert np.array_equal(api.record8_to_block(c8[b], layout), api.record_to_block(want_c[b], layout))
+
+
+def test_int8_records_are_refused_when_a_value_could_overflow(api, oracle):
+    with Ctx(api, 60, 0) as cx:                            # q60: table entries below 8.03
+        assert oracle.quant_table(60).min() < 8.03 and not cx.plan.records_fit_i8
+        with pytest.raises(api.DctCudaError, match="int8 records"):
+            cx.plan.fwd_quant_i8(np.zeros((8, 8), np.uint8))
+        # decoding is always possible: arbitrary int8 input decodes like the same values as int16
+        rng = np.random.default_rng(8)
+        c8 = rng.integers(-128, 128, size=(40 * 30, 64), dtype=np.int8)
+        Q = oracle.quant_table(60)
+        want, _ = oracle.dequant_idct_plane(c8.astype(np.int16), 320, 240, Q, 0, 0, None, nthreads=4)
+        assert np.array_equal(cx.plan.dequant_idct_i8(c8, 320, 240), want)
