@@ -1,37 +1,22 @@
-// shim.cu -- the C ABI of libdct_cuda: plans, plane calls, and the per-block compute calls of
-// include/dct.h / include/quantization.h (dct_forward, dct_inverse, quantize, dequantize).
+// shim.cu -- the C ABI of libdct_cuda, part 1: plans, device-plane and host-plane calls, statistics,
+// the multi-GPU host helpers and the run-length entry points.  (shim_blocks.cu: the per-block calls of
+// include/dct.h / include/quantization.h; shim_frames.cu: colour / edges / RGB frames; shim_peer.cu:
+// NVLink peers.)
 //
-// Reference interfaces replaced: include/dct.h:51,61 and include/quantization.h:69,79 (per
-// block), and the block loop a caller of those would write (tests/test_entropy.c:302-316,
-// :370-384) for the plane calls.  No CPU arithmetic happens on these paths; if CUDA is not
-// usable they fail (stderr + exit for the reference-style void calls, error code otherwise).
-#include <dct_cuda.h>
-
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <string>
-#include <thread>
-#include <vector>
-
-#include "band_tables.h"
-#include "butterfly.cuh"
-#include "kernels.cuh"
+// Reference interface replaced here: the block loop a caller of the reference's per-block functions
+// writes (tests/test_entropy.c:302-316, :370-384).  No CPU arithmetic happens on these paths; if CUDA
+// is not usable they fail with an error code.
+#include "plan.cuh"
 
 using namespace dctb;
+using namespace dctb::shim;
 
 // ------------------------------------------------------------------------------------------
 // errors
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char *fmt, ...)
+int dctb::shim::fail(int code, const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -39,14 +24,6 @@ static int fail(int code, const char *fmt, ...)
     va_end(ap);
     return code;
 }
-
-#define CU_TRY(expr)                                                                                 \
-    do {                                                                                             \
-        cudaError_t e_ = (expr);                                                                     \
-        if (e_ != cudaSuccess)                                                                       \
-            return fail(DCT_CUDA_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),      \
-                        __FILE__, __LINE__);                                                         \
-    } while (0)
 
 extern "C" const char *dct_cuda_last_error(void) { return g_err; }
 
@@ -60,77 +37,9 @@ extern "C" int dct_cuda_device_count(void)
     return n;
 }
 
-// ------------------------------------------------------------------------------------------
-// plan
-// ------------------------------------------------------------------------------------------
-namespace {
+namespace dctb {
+namespace shim {
 
-constexpr int kLanes = 3;                       // depth of the host-plane pipeline
-constexpr size_t kStripPixels = 16u << 20;      // ~16 Mpx per strip
-
-struct Lane {
-    cudaStream_t stream = nullptr;
-    Counters *d_ctr = nullptr;
-    uint32_t *d_wl = nullptr;
-    uint32_t wl_cap = 0;
-    // strip buffers of the host-plane pipeline
-    uint8_t *d_px = nullptr;
-    int16_t *d_coef = nullptr;
-    double *d_var = nullptr;
-    size_t cap_blocks = 0;
-    uint64_t blocks = 0;                        // blocks queued since the last stats fetch
-    // optional per-kernel timing (dct_cuda_plan_profile): event pairs around K1 / K2 launches
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_fwd, ev_inv;
-};
-
-}  // namespace
-
-struct dct_cuda_plan {
-    int device = 0;
-    const DCTContext *dct = nullptr;
-    const QuantContext *quant = nullptr;
-    int adaptive = 0;
-    int n = 8;                                  // block size; != 8 routes every plane call to K6 (generic_n.cu)
-    double *d_gen = nullptr;                    // K6 tables: D, Q, R (n*n doubles each)
-    int *d_gen_pos = nullptr;                   // K6: zigzag position of each natural index
-    bool exotic = false;                        // tables outside the fast path's proven domain
-    ExactTables h_tab;
-    ExactTables *d_tab = nullptr;
-    float r[64], thr[64], thr_min;              // K1
-    float thr_f32[64];                          // K1 from float pixel tiles
-    int uniform_band;
-    float rs[64], gain[64], band_floor;         // K2
-    Lane lane[kLanes];
-    Counters *h_ctr = nullptr;                  // pinned, kLanes entries
-    bool profile = false;
-    uint32_t *d_rle_sums = nullptr;             // K5 workspace: per-CTA symbol totals + the grand total
-    size_t rle_sums_cap = 0;
-    unsigned long long *d_rle_total = nullptr;
-    bool force_fp32_inverse = false;            // DCT_CUDA_INV_FP32=1: keep the fp32 inverse for adaptive plans too
-    bool skip_replay = false;                   // test hook: leave K1/K2's fast-path values unpatched
-    // whole-frame RGB 4:2:0 calls (luma plan only): device copy of the frame, its planes and records
-    uint8_t *d_frame = nullptr;
-    size_t frame_cap = 0;
-    cudaEvent_t ev_peer = nullptr;              // *_peer calls: "input ready" (owner) / "shard done" (peers)
-    bool fits_i8 = false;                       // every quantised value of a uint8 plane fits int8 (narrow.cu)
-    std::mutex mu;                              // serialises the entry points on one plan (lanes and buffers are state)
-};
-
-namespace {
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev)
-    {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard()
-    {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
 
 int read_tables(dct_cuda_plan *p)
 {
@@ -277,7 +186,7 @@ int ensure_worklist(Lane &ln, size_t nblocks)
 }
 
 // `dev`: the pitch is used by the kernels directly (8-byte rows); host planes are re-packed by the copy
-int check_plane(const void *a, const void *b, size_t pitch, int W, int H, bool dev, int n = 8)
+int check_plane(const void *a, const void *b, size_t pitch, int W, int H, bool dev, int n)
 {
     if (!a || !b) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
     if (W < 0 || H < 0 || (W % n) || (H % n))
@@ -301,7 +210,7 @@ int check_ragged(const void *a, const void *b, size_t pitch, int W, int H, int n
 // queue K1 (+K3) for one device-resident plane on lane `ln`, stream `s`
 // elem: bytes per pixel of the source plane -- 1 (uint8) or 4 (float tiles); pitch is in bytes
 int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int W, int H, int16_t *d_coef,
-              int layout, double *d_var, cudaStream_t s, int elem = 1)
+              int layout, double *d_var, cudaStream_t s, int elem)
 {
     if (p->n != 8) {
         if (elem != 1) return fail(DCT_CUDA_EINVAL, "float pixel tiles are 8x8 only");
@@ -430,7 +339,7 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
 
 // device strip buffers of one lane, sized in pixels: `pixels * elem` bytes of pixels, 2 + 1 bytes of record per
 // pixel (int16 and int8 form), one variance per block
-int ensure_strip_buffers(dct_cuda_plan *p, Lane &ln, size_t pixels, int elem = 1)
+int ensure_strip_buffers(dct_cuda_plan *p, Lane &ln, size_t pixels, int elem)
 {
     const size_t need = pixels * (size_t)elem;
     if (ln.cap_blocks >= need) return DCT_CUDA_OK;
@@ -466,7 +375,8 @@ int collect_stats(dct_cuda_plan *p, dct_cuda_stats *out, cudaStream_t user_strea
     return DCT_CUDA_OK;
 }
 
-}  // namespace
+}  // namespace shim
+}  // namespace dctb
 
 extern "C" dct_cuda_plan *dct_cuda_plan_create(const DCTContext *dct, const QuantContext *quant, int device)
 {
@@ -838,341 +748,6 @@ extern "C" int dct_cuda_dequant_idct_u8(dct_cuda_plan *p, const int16_t *coef, i
     return dct_cuda_plan_wait(p, stats);
 }
 
-// ------------------------------------------------------------------------------------------
-// several GPUs, data resident on ONE of them: peers work on the owner's memory through NVLink.
-// There is no staging copy and no collective: a peer's K1 / K2 / K3 load their shard straight from the
-// owner's HBM and store their results straight into it (peer-mapped addresses), so the transfer is
-// part of the kernel's own load / store stream and overlaps its arithmetic tile by tile.
-// ------------------------------------------------------------------------------------------
-namespace {
-
-int peer_prepare(dct_cuda_plan *const *plans, int n, int H, const float *share, int forward, std::vector<int> *row_end)
-{
-    if (!plans || n <= 0 || !plans[0]) return fail(DCT_CUDA_EINVAL, "no plans");
-    const int owner = plans[0]->device;
-    for (int g = 0; g < n; ++g) {
-        dct_cuda_plan *p = plans[g];
-        if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan %d", g);
-        if (p->n != 8) return fail(DCT_CUDA_EINVAL, "the peer calls are 8x8 only");
-        if (p->adaptive != plans[0]->adaptive) return fail(DCT_CUDA_EINVAL, "plans differ in their adaptive flag");
-        for (int h = 0; h < g; ++h)
-            if (plans[h]->device == p->device) return fail(DCT_CUDA_EINVAL, "plans %d and %d share GPU %d", h, g, p->device);
-        DeviceGuard dg(p->device);
-        if (!p->ev_peer) CU_TRY(cudaEventCreateWithFlags(&p->ev_peer, cudaEventDisableTiming));
-        if (g == 0) continue;
-        int ok = 0;
-        CU_TRY(cudaDeviceCanAccessPeer(&ok, p->device, owner));
-        if (!ok) return fail(DCT_CUDA_EINVAL, "GPU %d cannot map the memory of GPU %d", p->device, owner);
-        cudaError_t e = cudaDeviceEnablePeerAccess(owner, 0);
-        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-        else if (e != cudaSuccess) return fail(DCT_CUDA_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
-    }
-    // block-row ranges: peers get `share[g]` of the rows each (default: dct_cuda_peer_default_share), the owner the rest
-    const int total = H / 8;
-    row_end->assign(n, total);
-    double acc = 0.0;
-    for (int g = 1; g < n; ++g) {
-        const double sh = share ? (double)share[g] : (double)dct_cuda_peer_default_share(plans[0], n, forward);
-        if (!(sh >= 0.0) || sh > 1.0) return fail(DCT_CUDA_EINVAL, "share[%d] = %g outside [0, 1]", g, sh);
-        acc += sh;
-    }
-    if (acc > 1.0 + 1e-6) return fail(DCT_CUDA_EINVAL, "the peers' shares add up to %g > 1", acc);
-    // the owner's rows come first, then peer 1, 2, ...
-    double edge = 1.0 - acc;
-    int prev = 0;
-    for (int g = 0; g < n; ++g) {
-        int end = g == n - 1 ? total : (int)llround(edge * total);
-        end = std::max(prev, std::min(end, total));
-        (*row_end)[g] = end;
-        prev = end;
-        if (g + 1 < n) edge += share ? (double)share[g + 1] : (double)dct_cuda_peer_default_share(plans[0], n, forward);
-    }
-    return DCT_CUDA_OK;
-}
-
-template <typename F> int peer_run(dct_cuda_plan *const *plans, int n, const std::vector<int> &row_end, cudaStream_t stream, F &&queue)
-{
-    dct_cuda_plan *own = plans[0];
-    {
-        DeviceGuard dg(own->device);
-        CU_TRY(cudaEventRecord(own->ev_peer, stream));            // the data the caller queued before us is ready
-    }
-    for (int g = 1; g < n; ++g) {
-        const int r0 = row_end[g - 1], r1 = row_end[g];
-        if (r1 <= r0) continue;
-        dct_cuda_plan *p = plans[g];
-        DeviceGuard dg(p->device);
-        std::lock_guard<std::mutex> plan_lock(p->mu);
-        cudaStream_t s = p->lane[0].stream;
-        CU_TRY(cudaStreamWaitEvent(s, own->ev_peer, 0));
-        int rc = queue(p, r0, r1, s);
-        if (rc) return rc;
-        CU_TRY(cudaEventRecord(p->ev_peer, s));
-    }
-    DeviceGuard dg(own->device);
-    std::lock_guard<std::mutex> plan_lock(own->mu);
-    if (row_end[0] > 0) {
-        int rc = queue(own, 0, row_end[0], stream);
-        if (rc) return rc;
-    }
-    for (int g = 1; g < n; ++g)
-        if (row_end[g] > row_end[g - 1]) CU_TRY(cudaStreamWaitEvent(stream, plans[g]->ev_peer, 0));
-    return DCT_CUDA_OK;
-}
-
-}  // namespace
-
-// Default share of each peer.  Measured on 2 x B200 over NV18 (profiles/peer_r1f.json): through the owner's
-// NVLink port a peer's K1 sustains ~270 Gpixel/s and its K2 ~370 Gpixel/s (0.8 - 1.1 TB/s of port traffic, both
-// directions together) while the owner alone runs 1500 - 1700 Gpixel/s out of local HBM, and every row handed to a
-// peer also costs the owner HBM bandwidth -- so for the fused fp32 path the best split is "all rows to the owner".
-// Plans on the exact path (tables outside the fast path's domain: every block goes through the fp64 replay) are
-// arithmetic- and latency-bound far below the port's rate (owner alone: ~21 Gpixel/s); there the rows are dealt
-// out: evenly for the inverse (measured 1.96x on 2 GPUs), with half weight per peer for the forward, whose
-// 8-byte row loads feel the NVLink latency (a peer runs it at about half the owner's rate).
-extern "C" float dct_cuda_peer_default_share(const dct_cuda_plan *plan, int n_plans, int forward)
-{
-    if (!plan || n_plans <= 1 || !plan->exotic) return 0.0f;
-    const float w = forward ? 0.5f : 1.0f;
-    return w / (1.0f + w * (float)(n_plans - 1));
-}
-
-extern "C" int dct_cuda_fwd_quant_u8_peer(dct_cuda_plan *const *plans, int n, const uint8_t *d_px, size_t pitch, int W,
-                                          int H, int16_t *d_coef, int layout, double *d_var, const float *share,
-                                          void *stream)
-{
-    int rc = check_plane(d_px, d_coef, pitch, W, H, true);
-    if (rc) return rc;
-    std::vector<int> row_end;
-    if ((rc = peer_prepare(plans, n, H, share, 1, &row_end))) return rc;
-    const size_t bw = (size_t)W / 8;
-    return peer_run(plans, n, row_end, (cudaStream_t)stream, [&](dct_cuda_plan *p, int r0, int r1, cudaStream_t s) {
-        return queue_fwd(p, p->lane[0], d_px + (size_t)r0 * 8 * pitch, pitch, W, (r1 - r0) * 8, d_coef + (size_t)r0 * bw * 64,
-                         layout, d_var ? d_var + (size_t)r0 * bw : nullptr, s);
-    });
-}
-
-extern "C" int dct_cuda_dequant_idct_u8_peer(dct_cuda_plan *const *plans, int n, const int16_t *d_coef, int W, int H,
-                                             int layout, const double *d_var, uint8_t *d_px, size_t pitch,
-                                             const float *share, void *stream)
-{
-    int rc = check_plane(d_px, d_coef, pitch, W, H, true);
-    if (rc) return rc;
-    if (plans && n > 0 && plans[0] && plans[0]->adaptive && !d_var)
-        return fail(DCT_CUDA_EINVAL, "adaptive plan needs the per-block variance array");
-    std::vector<int> row_end;
-    if ((rc = peer_prepare(plans, n, H, share, 0, &row_end))) return rc;
-    const size_t bw = (size_t)W / 8;
-    return peer_run(plans, n, row_end, (cudaStream_t)stream, [&](dct_cuda_plan *p, int r0, int r1, cudaStream_t s) {
-        return queue_inv(p, p->lane[0], d_coef + (size_t)r0 * bw * 64, W, (r1 - r0) * 8, layout,
-                         d_var ? d_var + (size_t)r0 * bw : nullptr, d_px + (size_t)r0 * 8 * pitch, pitch, s);
-    });
-}
-
-// ------------------------------------------------------------------------------------------
-// planar front / back end (planar.cu): colour conversion + 4:2:0, edge completion.  Not in the reference.
-// ------------------------------------------------------------------------------------------
-static int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-extern "C" void dct_cuda_frame420_geometry(int width, int height, dct_cuda_frame420 *g)
-{
-    if (!g) return;
-    g->width = width, g->height = height;
-    g->y_width = round_up(width, 8), g->y_height = round_up(height, 8);
-    g->c_width = round_up((width + 1) / 2, 8), g->c_height = round_up((height + 1) / 2, 8);
-}
-
-static int check_frame(const dct_cuda_frame420 *g, int device)
-{
-    if (!g) return fail(DCT_CUDA_EINVAL, "NULL geometry");
-    dct_cuda_frame420 want;
-    dct_cuda_frame420_geometry(g->width, g->height, &want);
-    if (g->width <= 0 || g->height <= 0 || memcmp(&want, g, sizeof want))
-        return fail(DCT_CUDA_EINVAL, "geometry does not come from dct_cuda_frame420_geometry (%dx%d)", g->width, g->height);
-    const int ndev = dct_cuda_device_count();
-    if (ndev <= 0) return fail(DCT_CUDA_ENODEV, "no CUDA device available (libdct_cuda has no CPU fallback)");
-    if (device < 0 || device >= ndev) return fail(DCT_CUDA_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
-    return DCT_CUDA_OK;
-}
-
-static PlanarParams planar_params(const dct_cuda_frame420 *g, const uint8_t *rgb_in, uint8_t *rgb_out, size_t rgb_pitch,
-                                  const uint8_t *y, size_t y_pitch, const uint8_t *cb, const uint8_t *cr, size_t c_pitch)
-{
-    PlanarParams pp{};
-    pp.rgb = rgb_in, pp.rgb_out = rgb_out, pp.rgb_pitch = (long long)rgb_pitch;
-    pp.W = g->width, pp.H = g->height;
-    pp.y = const_cast<uint8_t *>(y), pp.cb = const_cast<uint8_t *>(cb), pp.cr = const_cast<uint8_t *>(cr);
-    pp.y_pitch = (long long)y_pitch, pp.c_pitch = (long long)c_pitch;
-    pp.y_w = g->y_width, pp.y_h = g->y_height, pp.c_w = g->c_width, pp.c_h = g->c_height;
-    const uintptr_t rgbp = (uintptr_t)(rgb_in ? rgb_in : rgb_out);
-    pp.vec_ok = !(rgbp % 16) && !(rgb_pitch % 16) && !((uintptr_t)y % 16) && !(y_pitch % 16) && !((uintptr_t)cb % 8) &&
-                !((uintptr_t)cr % 8) && !(c_pitch % 8);
-    return pp;
-}
-
-extern "C" int dct_cuda_rgb_to_ycbcr420_dev(int device, const uint8_t *d_rgb, size_t rgb_pitch, const dct_cuda_frame420 *g,
-                                            uint8_t *d_y, size_t y_pitch, uint8_t *d_cb, uint8_t *d_cr, size_t c_pitch,
-                                            void *stream)
-{
-    int rc = check_frame(g, device);
-    if (rc) return rc;
-    if (!d_rgb || !d_y || !d_cb || !d_cr) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
-    if (rgb_pitch < (size_t)g->width * 3 || y_pitch < (size_t)g->y_width || c_pitch < (size_t)g->c_width)
-        return fail(DCT_CUDA_EINVAL, "pitch smaller than a row");
-    DeviceGuard dg(device);
-    CU_TRY(launch_rgb_to_ycbcr420(planar_params(g, d_rgb, nullptr, rgb_pitch, d_y, y_pitch, d_cb, d_cr, c_pitch),
-                                  (cudaStream_t)stream));
-    return DCT_CUDA_OK;
-}
-
-extern "C" int dct_cuda_ycbcr420_to_rgb_dev(int device, const uint8_t *d_y, size_t y_pitch, const uint8_t *d_cb,
-                                            const uint8_t *d_cr, size_t c_pitch, const dct_cuda_frame420 *g, uint8_t *d_rgb,
-                                            size_t rgb_pitch, void *stream)
-{
-    int rc = check_frame(g, device);
-    if (rc) return rc;
-    if (!d_rgb || !d_y || !d_cb || !d_cr) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
-    if (rgb_pitch < (size_t)g->width * 3 || y_pitch < (size_t)g->y_width || c_pitch < (size_t)g->c_width)
-        return fail(DCT_CUDA_EINVAL, "pitch smaller than a row");
-    DeviceGuard dg(device);
-    CU_TRY(launch_ycbcr420_to_rgb(planar_params(g, nullptr, d_rgb, rgb_pitch, d_y, y_pitch, d_cb, d_cr, c_pitch),
-                                  (cudaStream_t)stream));
-    return DCT_CUDA_OK;
-}
-
-extern "C" int dct_cuda_pad_edges_dev(int device, uint8_t *d_px, size_t pitch, int W, int H, int W_pad, int H_pad,
-                                      void *stream)
-{
-    if (!d_px) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
-    if (W <= 0 || H <= 0 || W_pad < W || H_pad < H || pitch < (size_t)W_pad)
-        return fail(DCT_CUDA_EINVAL, "bad sizes %dx%d -> %dx%d, pitch %zu", W, H, W_pad, H_pad, pitch);
-    const int ndev = dct_cuda_device_count();
-    if (ndev <= 0) return fail(DCT_CUDA_ENODEV, "no CUDA device available (libdct_cuda has no CPU fallback)");
-    if (device < 0 || device >= ndev) return fail(DCT_CUDA_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
-    DeviceGuard dg(device);
-    CU_TRY(launch_pad_edges(d_px, (long long)pitch, W, H, W_pad, H_pad, 1, (cudaStream_t)stream));
-    return DCT_CUDA_OK;
-}
-
-// whole RGB frames from / to host memory: H2D, colour conversion, K1 on the three planes, D2H (and back)
-namespace {
-struct FrameLayout {
-    dct_cuda_frame420 g;
-    size_t rgb_pitch, y_pitch, c_pitch;
-    size_t off_y, off_cb, off_cr, off_ky, off_kcb, off_kcr, bytes;   // offsets into plan->d_frame
-    size_t ny, nc;                                                    // samples per luma / chroma plane
-};
-
-FrameLayout frame_layout(int W, int H)
-{
-    FrameLayout f{};
-    dct_cuda_frame420_geometry(W, H, &f.g);
-    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-    f.rgb_pitch = ((size_t)W * 3 + 15) / 16 * 16;
-    f.y_pitch = ((size_t)f.g.y_width + 15) / 16 * 16;
-    f.c_pitch = (size_t)f.g.c_width;
-    f.ny = (size_t)f.g.y_width * f.g.y_height, f.nc = (size_t)f.g.c_width * f.g.c_height;
-    size_t o = up(f.rgb_pitch * H);
-    f.off_y = o, o += up(f.y_pitch * f.g.y_height);
-    f.off_cb = o, o += up(f.c_pitch * f.g.c_height);
-    f.off_cr = o, o += up(f.c_pitch * f.g.c_height);
-    f.off_ky = o, o += up(f.ny * 2);
-    f.off_kcb = o, o += up(f.nc * 2);
-    f.off_kcr = o, o += up(f.nc * 2);
-    f.bytes = o;
-    return f;
-}
-
-int frame_prepare(dct_cuda_plan *luma, dct_cuda_plan *chroma, int W, int H, int layout, FrameLayout *f)
-{
-    if (!luma || !chroma) return fail(DCT_CUDA_EINVAL, "NULL plan");
-    if (luma->n != 8 || chroma->n != 8 || luma->adaptive || chroma->adaptive)
-        return fail(DCT_CUDA_EINVAL, "the RGB 4:2:0 frame calls need two non-adaptive 8x8 plans");
-    if (luma->device != chroma->device) return fail(DCT_CUDA_EINVAL, "both plans must live on the same GPU");
-    if (W <= 0 || H <= 0) return fail(DCT_CUDA_EINVAL, "width and height must be positive (got %dx%d)", W, H);
-    if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
-    *f = frame_layout(W, H);
-    std::lock_guard<std::mutex> plan_lock(luma->mu);
-    if (luma->frame_cap < f->bytes) {
-        CU_TRY(cudaDeviceSynchronize());
-        if (luma->d_frame) cudaFree(luma->d_frame);
-        luma->d_frame = nullptr, luma->frame_cap = 0;
-        CU_TRY(cudaMalloc(&luma->d_frame, f->bytes));
-        luma->frame_cap = f->bytes;
-    }
-    return DCT_CUDA_OK;
-}
-
-int frame_stats(dct_cuda_plan *luma, dct_cuda_plan *chroma, cudaStream_t s, dct_cuda_stats *stats)
-{
-    dct_cuda_stats a{}, b{};
-    int rc = collect_stats(luma, &a, s);
-    if (rc) return rc;
-    if (chroma != luma && (rc = collect_stats(chroma, &b, s))) return rc;
-    if (stats) {
-        stats->blocks = a.blocks + b.blocks, stats->replayed_blocks = a.replayed_blocks + b.replayed_blocks;
-        stats->near_ties = a.near_ties + b.near_ties, stats->saturated = a.saturated + b.saturated;
-    }
-    return DCT_CUDA_OK;
-}
-}  // namespace
-
-extern "C" int dct_cuda_encode_rgb420(dct_cuda_plan *luma, dct_cuda_plan *chroma, const uint8_t *rgb, size_t rgb_pitch,
-                                      int W, int H, int16_t *coef_y, int16_t *coef_cb, int16_t *coef_cr, int layout,
-                                      dct_cuda_stats *stats)
-{
-    FrameLayout f;
-    int rc = frame_prepare(luma, chroma, W, H, layout, &f);
-    if (rc) return rc;
-    if (!rgb || !coef_y || !coef_cb || !coef_cr) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
-    if (rgb_pitch < (size_t)W * 3) return fail(DCT_CUDA_EINVAL, "pitch %zu must be >= 3 * width", rgb_pitch);
-    DeviceGuard dg(luma->device);
-    std::unique_lock<std::mutex> lock_l(luma->mu, std::defer_lock), lock_c(chroma->mu, std::defer_lock);
-    if (chroma != luma) std::lock(lock_l, lock_c);
-    else lock_l.lock();
-    uint8_t *base = luma->d_frame;
-    cudaStream_t s = luma->lane[0].stream;
-    CU_TRY(cudaMemcpy2DAsync(base, f.rgb_pitch, rgb, rgb_pitch, (size_t)W * 3, (size_t)H, cudaMemcpyHostToDevice, s));
-    CU_TRY(launch_rgb_to_ycbcr420(planar_params(&f.g, base, nullptr, f.rgb_pitch, base + f.off_y, f.y_pitch, base + f.off_cb,
-                                                base + f.off_cr, f.c_pitch), s));
-    int16_t *ky = (int16_t *)(base + f.off_ky), *kcb = (int16_t *)(base + f.off_kcb), *kcr = (int16_t *)(base + f.off_kcr);
-    if ((rc = queue_fwd(luma, luma->lane[0], base + f.off_y, f.y_pitch, f.g.y_width, f.g.y_height, ky, layout, nullptr, s))) return rc;
-    if ((rc = queue_fwd(chroma, chroma->lane[0], base + f.off_cb, f.c_pitch, f.g.c_width, f.g.c_height, kcb, layout, nullptr, s))) return rc;
-    if ((rc = queue_fwd(chroma, chroma->lane[0], base + f.off_cr, f.c_pitch, f.g.c_width, f.g.c_height, kcr, layout, nullptr, s))) return rc;
-    CU_TRY(cudaMemcpyAsync(coef_y, ky, f.ny * 2, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(coef_cb, kcb, f.nc * 2, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(coef_cr, kcr, f.nc * 2, cudaMemcpyDeviceToHost, s));
-    return frame_stats(luma, chroma, s, stats);
-}
-
-extern "C" int dct_cuda_decode_rgb420(dct_cuda_plan *luma, dct_cuda_plan *chroma, const int16_t *coef_y,
-                                      const int16_t *coef_cb, const int16_t *coef_cr, int W, int H, int layout,
-                                      uint8_t *rgb, size_t rgb_pitch, dct_cuda_stats *stats)
-{
-    FrameLayout f;
-    int rc = frame_prepare(luma, chroma, W, H, layout, &f);
-    if (rc) return rc;
-    if (!rgb || !coef_y || !coef_cb || !coef_cr) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
-    if (rgb_pitch < (size_t)W * 3) return fail(DCT_CUDA_EINVAL, "pitch %zu must be >= 3 * width", rgb_pitch);
-    DeviceGuard dg(luma->device);
-    std::unique_lock<std::mutex> lock_l(luma->mu, std::defer_lock), lock_c(chroma->mu, std::defer_lock);
-    if (chroma != luma) std::lock(lock_l, lock_c);
-    else lock_l.lock();
-    uint8_t *base = luma->d_frame;
-    cudaStream_t s = luma->lane[0].stream;
-    int16_t *ky = (int16_t *)(base + f.off_ky), *kcb = (int16_t *)(base + f.off_kcb), *kcr = (int16_t *)(base + f.off_kcr);
-    CU_TRY(cudaMemcpyAsync(ky, coef_y, f.ny * 2, cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(kcb, coef_cb, f.nc * 2, cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(kcr, coef_cr, f.nc * 2, cudaMemcpyHostToDevice, s));
-    if ((rc = queue_inv(luma, luma->lane[0], ky, f.g.y_width, f.g.y_height, layout, nullptr, base + f.off_y, f.y_pitch, s))) return rc;
-    if ((rc = queue_inv(chroma, chroma->lane[0], kcb, f.g.c_width, f.g.c_height, layout, nullptr, base + f.off_cb, f.c_pitch, s))) return rc;
-    if ((rc = queue_inv(chroma, chroma->lane[0], kcr, f.g.c_width, f.g.c_height, layout, nullptr, base + f.off_cr, f.c_pitch, s))) return rc;
-    CU_TRY(launch_ycbcr420_to_rgb(planar_params(&f.g, nullptr, base, f.rgb_pitch, base + f.off_y, f.y_pitch, base + f.off_cb,
-                                                base + f.off_cr, f.c_pitch), s));
-    CU_TRY(cudaMemcpy2DAsync(rgb, rgb_pitch, base, f.rgb_pitch, (size_t)W * 3, (size_t)H, cudaMemcpyDeviceToHost, s));
-    return frame_stats(luma, chroma, s, stats);
-}
-
 // ---- int8 records over PCIe (narrow.cu): same calls, half the record bytes, when the table allows it ----
 extern "C" int dct_cuda_plan_records_fit_i8(const dct_cuda_plan *p) { return p && p->fits_i8 ? 1 : 0; }
 
@@ -1322,157 +897,3 @@ extern "C" int dct_cuda_rle_emit_dev(dct_cuda_plan *p, const int16_t *d_coef, si
     return DCT_CUDA_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// adapters for the host consumer
-// ------------------------------------------------------------------------------------------
-extern "C" void dct_cuda_record_to_block(const int16_t *rec, int layout, int **block)
-{
-    for (int k = 0; k < 64; ++k) {
-        const int nat = layout == DCT_CUDA_ZIGZAG ? kZigZag.nat[k] : k;
-        block[nat >> 3][nat & 7] = rec[k];
-    }
-}
-
-extern "C" void dct_cuda_block_to_record(int **block, int layout, int16_t *rec)
-{
-    for (int k = 0; k < 64; ++k) {
-        const int nat = layout == DCT_CUDA_ZIGZAG ? kZigZag.nat[k] : k;
-        rec[k] = (int16_t)block[nat >> 3][nat & 7];
-    }
-}
-
-extern "C" void *dct_cuda_host_alloc(size_t bytes)
-{
-    void *p = nullptr;
-    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
-        fail(DCT_CUDA_ENOMEM, "cudaMallocHost(%zu) failed", bytes);
-        cudaGetLastError();
-        return nullptr;
-    }
-    return p;
-}
-
-extern "C" void dct_cuda_host_free(void *p)
-{
-    if (p) cudaFreeHost(p);
-}
-
-// ------------------------------------------------------------------------------------------
-// per-block drop-in calls: include/dct.h:51,61  include/quantization.h:69,79
-// ------------------------------------------------------------------------------------------
-namespace {
-
-struct BlockScratch {
-    bool ready = false;
-    double *d_tab = nullptr, *d_in = nullptr, *d_out = nullptr;
-    int *d_int = nullptr;
-    double *h = nullptr;      // pinned: 3 * 1024 doubles
-    int *h_int = nullptr;     // pinned: 1024 ints
-    cudaStream_t stream = nullptr;
-    int device = 0;           // the device that was current on first use; every later call switches to it
-};
-std::mutex g_block_mu;
-BlockScratch g_block;
-
-[[noreturn]] void die(const char *what, cudaError_t e)
-{
-    fprintf(stderr, "libdct_cuda: %s failed: %s (no CPU fallback)\n", what, cudaGetErrorString(e));
-    exit(EXIT_FAILURE);
-}
-#define CU_DIE(expr)                                  \
-    do {                                              \
-        cudaError_t e_ = (expr);                      \
-        if (e_ != cudaSuccess) die(#expr, e_);        \
-    } while (0)
-
-BlockScratch &scratch()
-{
-    if (!g_block.ready) {
-        CU_DIE(cudaGetDevice(&g_block.device));
-        CU_DIE(cudaMalloc(&g_block.d_tab, 1024 * sizeof(double)));
-        CU_DIE(cudaMalloc(&g_block.d_in, 1024 * sizeof(double)));
-        CU_DIE(cudaMalloc(&g_block.d_out, 1024 * sizeof(double)));
-        CU_DIE(cudaMalloc(&g_block.d_int, 1024 * sizeof(int)));
-        CU_DIE(cudaMallocHost(&g_block.h, 3 * 1024 * sizeof(double)));
-        CU_DIE(cudaMallocHost(&g_block.h_int, 1024 * sizeof(int)));
-        CU_DIE(cudaStreamCreateWithFlags(&g_block.stream, cudaStreamNonBlocking));
-        g_block.ready = true;
-    }
-    return g_block;
-}
-
-void check_n(int n)
-{
-    if (n < 1 || n > 32) {
-        fprintf(stderr, "libdct_cuda: block_size %d unsupported (1..32)\n", n);
-        exit(EXIT_FAILURE);
-    }
-}
-
-void block_transform(DCTContext *ctx, double **input, double **output, int inverse)
-{
-    const int n = ctx->block_size;
-    check_n(n);
-    std::lock_guard<std::mutex> lk(g_block_mu);
-    BlockScratch &s = scratch();
-    DeviceGuard dg(s.device);
-    double *hD = s.h, *hI = s.h + 1024, *hO = s.h + 2048;
-    for (int i = 0; i < n; ++i) {
-        memcpy(hD + i * n, ctx->dct_matrix[i], n * sizeof(double));   // rows are separate mallocs
-        memcpy(hI + i * n, input[i], n * sizeof(double));
-    }
-    const size_t bytes = (size_t)n * n * sizeof(double);
-    CU_DIE(cudaMemcpyAsync(s.d_tab, hD, bytes, cudaMemcpyHostToDevice, s.stream));
-    CU_DIE(cudaMemcpyAsync(s.d_in, hI, bytes, cudaMemcpyHostToDevice, s.stream));
-    CU_DIE(launch_block_dct_f64(n, s.d_tab, s.d_in, s.d_out, inverse, s.stream));
-    CU_DIE(cudaMemcpyAsync(hO, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
-    CU_DIE(cudaStreamSynchronize(s.stream));
-    for (int i = 0; i < n; ++i) memcpy(output[i], hO + i * n, n * sizeof(double));
-}
-
-}  // namespace
-
-extern "C" void dct_forward(DCTContext *ctx, double **input, double **output) { block_transform(ctx, input, output, 0); }
-extern "C" void dct_inverse(DCTContext *ctx, double **input, double **output) { block_transform(ctx, input, output, 1); }
-
-extern "C" void quantize(QuantContext *ctx, double **dct_coeffs, int **quant_coeffs, double block_variance)
-{
-    const int n = ctx->block_size;
-    check_n(n);
-    std::lock_guard<std::mutex> lk(g_block_mu);
-    BlockScratch &s = scratch();
-    DeviceGuard dg(s.device);
-    double *hQ = s.h, *hC = s.h + 1024;
-    for (int i = 0; i < n; ++i) {
-        memcpy(hQ + i * n, ctx->quant_matrix[i], n * sizeof(double));
-        memcpy(hC + i * n, dct_coeffs[i], n * sizeof(double));
-    }
-    const size_t bytes = (size_t)n * n * sizeof(double);
-    CU_DIE(cudaMemcpyAsync(s.d_tab, hQ, bytes, cudaMemcpyHostToDevice, s.stream));
-    CU_DIE(cudaMemcpyAsync(s.d_in, hC, bytes, cudaMemcpyHostToDevice, s.stream));
-    CU_DIE(launch_block_quantize_f64(n, s.d_tab, ctx->adaptive, block_variance, s.d_in, s.d_int, s.stream));
-    CU_DIE(cudaMemcpyAsync(s.h_int, s.d_int, (size_t)n * n * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-    CU_DIE(cudaStreamSynchronize(s.stream));
-    for (int i = 0; i < n; ++i) memcpy(quant_coeffs[i], s.h_int + i * n, n * sizeof(int));
-}
-
-extern "C" void dequantize(QuantContext *ctx, int **quant_coeffs, double **dct_coeffs, double block_variance)
-{
-    const int n = ctx->block_size;
-    check_n(n);
-    std::lock_guard<std::mutex> lk(g_block_mu);
-    BlockScratch &s = scratch();
-    DeviceGuard dg(s.device);
-    double *hR = s.h, *hO = s.h + 2048;
-    for (int i = 0; i < n; ++i) {
-        memcpy(hR + i * n, ctx->dequant_matrix[i], n * sizeof(double));
-        memcpy(s.h_int + i * n, quant_coeffs[i], n * sizeof(int));
-    }
-    const size_t bytes = (size_t)n * n * sizeof(double);
-    CU_DIE(cudaMemcpyAsync(s.d_tab, hR, bytes, cudaMemcpyHostToDevice, s.stream));
-    CU_DIE(cudaMemcpyAsync(s.d_int, s.h_int, (size_t)n * n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-    CU_DIE(launch_block_dequantize_f64(n, s.d_tab, ctx->adaptive, block_variance, s.d_int, s.d_out, s.stream));
-    CU_DIE(cudaMemcpyAsync(hO, s.d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
-    CU_DIE(cudaStreamSynchronize(s.stream));
-    for (int i = 0; i < n; ++i) memcpy(dct_coeffs[i], hO + i * n, n * sizeof(double));
-}
