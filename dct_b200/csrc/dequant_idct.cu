@@ -81,8 +81,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8(const __grid_co
         s = adaptive_scale(var);
     }
 
+    // ADAPTIVE: v = (q * s) * rs, then the plain butterfly.  Otherwise v holds the converted q themselves and the
+    // multiplication happens inside the first butterfly stage (idct8_dequant: one FMA gives v_a +- q_b * rs_b).
     float v[64];
-    float bound = 0.f;   // sum gain_k * |v_k|
+    float bound = 0.f;   // >= sum gain_k * |v_k|
     static_for<0, 32>([&](auto M) {
         constexpr int m = decltype(M)::value;
         constexpr int k0 = storage_to_natural<LAYOUT>(2 * m), k1 = storage_to_natural<LAYOUT>(2 * m + 1);
@@ -90,11 +92,15 @@ __global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8(const __grid_co
         if constexpr (ADAPTIVE) {
             if (k0 != 0) f0 = __fmul_rn(f0, s);
             f1 = __fmul_rn(f1, s);
+            v[k0] = __fmul_rn(f0, p.rs[k0]);
+            v[k1] = __fmul_rn(f1, p.rs[k1]);
+            bound = __fmaf_rn(fabsf(v[k0]), p.gain[k0], bound);
+            bound = __fmaf_rn(fabsf(v[k1]), p.gain[k1], bound);
+        } else {
+            v[k0] = f0, v[k1] = f1;
+            bound = __fmaf_rn(fabsf(f0), p.rg[k0], bound);
+            bound = __fmaf_rn(fabsf(f1), p.rg[k1], bound);
         }
-        v[k0] = __fmul_rn(f0, p.rs[k0]);
-        v[k1] = __fmul_rn(f1, p.rs[k1]);
-        bound = __fmaf_rn(fabsf(v[k0]), p.gain[k0], bound);
-        bound = __fmaf_rn(fabsf(v[k1]), p.gain[k1], bound);
     });
     // |fp32 pixel - exact pixel| <= 2^-24 * bound (derive_bands.py) ; + floor for the residual's own rounding
     const float thr = pixel_threshold(bound, p.band_floor);
@@ -110,7 +116,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8(const __grid_co
     for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) cpv[c][i] = make_float2(v[8 * i + kPairA[c]], v[8 * i + kPairB[c]]);
-        idct8<float2, 1>(cpv[c]);
+        if constexpr (ADAPTIVE) idct8<float2, 1>(cpv[c]);
+        else idct8_dequant<float2, 1>(cpv[c], p.ma[c], p.mb[c]);
     }
 
     const uint32_t bb = valid ? b : p.nblocks - 1;

@@ -31,8 +31,9 @@ struct ExactTables {
     float thr32f[64];   // K1 from float pixel tiles: 0.5 - band_k (wider: inputs carry a rounding error)
     float rs32[64];     // K2: dequantisation multiplier * a_u a_v / 8
     float gain32[64];   // K2: error gain per unit |input|
+    float rg32[64];     // K2 (non-adaptive): rs32 * gain32 rounded up
     float band_floor;   // K2
-    float pad_;
+    float pad_[3];
 };
 
 // K1: forward DCT + quantise.  One thread per 8x8 block.
@@ -53,6 +54,13 @@ struct FwdParams {
     int uniform_band;      // 1: test max_k |residual| >= thr_min (cheaper, slightly more replays)
 };
 
+struct alignas(16) PosNeg2 {
+    float2 pos, neg;
+};
+struct PosNeg1 {
+    float pos, neg;
+};
+
 // K2: dequantise + inverse DCT.  One thread per 8x8 block.
 struct InvParams {
     const int16_t *coef;
@@ -67,6 +75,12 @@ struct InvParams {
     float rs[64];          // natural index: dequant multiplier * a_u a_v / 8
     float gain[64];        // natural index: error gain of the butterfly per unit |input|
     float band_floor;
+    // the non-adaptive kernel's folded first stage (butterfly.cuh idct8_dequant): for column pair c = (A_c, B_c) of
+    // (0,4) (2,6) (5,3) (1,7) and first-stage pair j of rows (0,4) (2,6) (5,3) (1,7):
+    //   ma[c][j] = (rs[8 a_j + A_c], rs[8 a_j + B_c]),  mb[c][j] = (same for row b_j, and its negation)
+    float2 ma[4][4];
+    PosNeg2 mb[4][4];
+    float rg[64];          // natural index: rs * gain, rounded up (bound on the raw quantised values)
 };
 
 // K3: exact fp64 replay of the blocks on the worklist (or of every block when wl == null).

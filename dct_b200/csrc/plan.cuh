@@ -78,6 +78,7 @@ struct dct_cuda_plan {
     float thr_f32[64];                          // K1 from float pixel tiles
     int uniform_band;
     float rs[64], gain[64], band_floor;         // K2
+    float rg[64];                               // K2: rs * gain rounded up
     Lane lane[kLanes];
     Counters *h_ctr = nullptr;                  // pinned, kLanes entries
     bool profile = false;

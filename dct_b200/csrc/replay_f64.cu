@@ -344,18 +344,37 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
         if (!replay_all) {
             float x[8];
             float bound = 0.0f;
+            if (p.adaptive) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int k = 8 * i + r;
-                float f;
-                asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(q[i]));
-                if (p.adaptive && k != 0) f = __fmul_rn(f, s32);
-                x[i] = __fmul_rn(f, tab.rs32[k]);
-                bound = __fmaf_rn(fabsf(x[i]), tab.gain32[k], bound);
+                for (int i = 0; i < 8; ++i) {
+                    const int k = 8 * i + r;
+                    float f;
+                    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(q[i]));
+                    if (k != 0) f = __fmul_rn(f, s32);
+                    x[i] = __fmul_rn(f, tab.rs32[k]);
+                    bound = __fmaf_rn(fabsf(x[i]), tab.gain32[k], bound);
+                }
+                idct8<float, 1>(x);                       // column r
+            } else {
+                // K2's folded first stage (idct8_dequant), scalar: same operations on the same operands
+                constexpr int ra[4] = {0, 2, 5, 1}, rb[4] = {4, 6, 3, 7};
+                float ma[4];
+                PosNeg1 mb[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ma[j] = tab.rs32[8 * ra[j] + r];
+                    mb[j].pos = tab.rs32[8 * rb[j] + r];
+                    mb[j].neg = -mb[j].pos;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(x[i]) : "r"(q[i]));
+                    bound = __fmaf_rn(fabsf(x[i]), tab.rg32[8 * i + r], bound);
+                }
+                idct8_dequant<float, 1>(x, ma, mb);       // column r
             }
 #pragma unroll
             for (int d = 1; d < 8; d <<= 1) bound += __shfl_xor_sync(0xffffffffu, bound, d);
-            idct8<float, 1>(x);                           // column r
 #pragma unroll
             for (int i = 0; i < 8; ++i) T[i][r] = x[i];
             __syncwarp();

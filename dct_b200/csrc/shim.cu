@@ -93,6 +93,8 @@ int read_tables(dct_cuda_plan *p)
         const double mult = p->adaptive ? 1.0 / R : R;
         p->rs[k] = (float)(mult * kInvPrescale[k]);
         p->gain[k] = exotic ? 1e30f : kInvGain[k] * 1.02f;
+        // bound on the raw quantised value: |q| * rg >= gain * |q * rs| with room for the fp32 product's rounding
+        p->rg[k] = exotic ? 1e30f : std::nextafterf((float)((double)std::fabs(p->rs[k]) * (double)p->gain[k] * (1.0 + 1e-6)), INFINITY);
         p->h_tab.mp64[k] = mult * kInvPrescale[k];
     }
     p->band_floor = 1.0e-6f;
@@ -107,8 +109,9 @@ int read_tables(dct_cuda_plan *p)
     memcpy(p->h_tab.thr32f, p->thr_f32, sizeof p->thr_f32);
     memcpy(p->h_tab.rs32, p->rs, sizeof p->rs);
     memcpy(p->h_tab.gain32, p->gain, sizeof p->gain);
+    memcpy(p->h_tab.rg32, p->rg, sizeof p->rg);
     p->h_tab.band_floor = p->band_floor;
-    p->h_tab.pad_ = 0.f;
+    p->h_tab.pad_[0] = p->h_tab.pad_[1] = p->h_tab.pad_[2] = 0.f;
     return DCT_CUDA_OK;
 }
 
@@ -316,7 +319,18 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
         ip.ctr = ln.d_ctr;
         memcpy(ip.rs, p->rs, sizeof ip.rs);
         memcpy(ip.gain, p->gain, sizeof ip.gain);
+        memcpy(ip.rg, p->rg, sizeof ip.rg);
         ip.band_floor = p->band_floor;
+        {   // multipliers of the folded first stage, in the kernel's pair order
+            static const int colA[4] = {0, 2, 5, 1}, colB[4] = {4, 6, 3, 7};
+            for (int c = 0; c < 4; ++c)
+                for (int j = 0; j < 4; ++j) {
+                    const int ra = colA[j], rb = colB[j];                  // first-stage row pair (a_j, b_j)
+                    ip.ma[c][j] = make_float2(p->rs[8 * ra + colA[c]], p->rs[8 * ra + colB[c]]);
+                    ip.mb[c][j].pos = make_float2(p->rs[8 * rb + colA[c]], p->rs[8 * rb + colB[c]]);
+                    ip.mb[c][j].neg = make_float2(-ip.mb[c][j].pos.x, -ip.mb[c][j].pos.y);
+                }
+        }
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (p->profile) {
             CU_TRY(cudaEventCreate(&e0));
