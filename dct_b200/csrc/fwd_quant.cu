@@ -200,9 +200,19 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
 
     if (ballot != 0) {
         const unsigned base = __shfl_sync(0xffffffffu, wl_base, __ffs(ballot) - 1);
-        if (ballot & (1u << lane)) {
-            const unsigned pos = base + __popc(ballot & ((1u << lane) - 1u));
-            if (pos < p.wl_cap) p.worklist[pos] = b;
+        // One round per flagged block (usually a single one): lane 8 appends the worklist entry, lanes 0-7 copy one
+        // pixel row each from this tile's input stage to the 64 bytes that go with the entry (K3 reads those instead
+        // of eight scattered rows of the plane).
+        unsigned pos = base;
+        for (unsigned todo = ballot; todo != 0; todo &= todo - 1, ++pos) {
+            const unsigned f = __ffs(todo) - 1;
+            if (lane < 8) {
+                if (pos < p.side_cap)
+                    reinterpret_cast<uint2 *>(p.side + (size_t)pos * 64)[lane] =
+                        *reinterpret_cast<const uint2 *>(wsm + stage * kInWordsPerStage + lane * 64 + f * 2);
+            } else if (lane == 8 && pos < p.wl_cap) {
+                p.worklist[pos] = warp_base + f;
+            }
         }
     }
     __syncwarp();   // the output stage is rewritten by the next tile

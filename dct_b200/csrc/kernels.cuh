@@ -52,6 +52,10 @@ struct FwdParams {
     uint32_t step_q, step_r;   // divmod(blocks between a warp's consecutive tiles, bw): set by the launcher
     float thr_min;         // min_k thr[k]: the single threshold of the uniform-band variant
     int uniform_band;      // 1: test max_k |residual| >= thr_min (cheaper, slightly more replays)
+    // Optional: the pixels of the flagged blocks, copied next to their worklist entry (64 bytes at side + 64 * slot
+    // for slot < side_cap), so that K3 reads a compact, L2-resident array instead of 8 scattered rows per block.
+    uint8_t *side;
+    uint32_t side_cap;
 };
 
 struct alignas(16) PosNeg2 {
@@ -96,6 +100,8 @@ struct ReplayParams {
     long long pitch;
     const uint8_t *px_in;       // forward (uint8 pixels; float pixels when px_is_f32)
     int px_is_f32;
+    const uint8_t *side;        // forward: K1's copy of the flagged blocks' pixels (see FwdParams), or null
+    uint32_t side_cap;
     int16_t *coef_out;
     double *var_out;
     const int16_t *coef_in;     // inverse

@@ -46,6 +46,8 @@ struct Lane {
     Counters *d_ctr = nullptr;
     uint32_t *d_wl = nullptr;
     uint32_t wl_cap = 0;
+    uint8_t *d_side = nullptr;                  // pixels of the flagged blocks, 64 B per worklist slot (first side_cap slots)
+    uint32_t side_cap = 0;
     // strip buffers of the host-plane pipeline
     uint8_t *d_px = nullptr;
     int16_t *d_coef = nullptr;

@@ -274,6 +274,151 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K3 forward, common case (uint8 pixels, non-adaptive table, worklist mode): ONE LANE PER FLAGGED BLOCK.
+// The 8-lanes-per-block kernel above spends ~125 warp instructions per block, most of them on the
+// shared-memory transposes of its re-flagging phase and on a replay phase that keeps 8 lanes busy with
+// one value.  Here a lane repeats K1's fp32 arithmetic for its whole block in registers (the same
+// fast_core.cuh functions, the same operation order per element, hence the same bits), the warp
+// compacts the flagged (block, coefficient) pairs into a list, and then every lane replays ONE
+// value on its own: the reference's 64 + 8 non-contracted fp64 multiply-adds in its own order
+// (src/dct.c:57-74), true division, half-away rounding (src/quantization.c:122-126).
+// ------------------------------------------------------------------------------------------
+constexpr int kLaneThreads = 128;
+constexpr int kLaneWarps = kLaneThreads / 32;
+constexpr int kPairsPerRound = 4;                  // pairs one lane may append per round
+
+struct LaneShared {
+    ExactTables tab;
+    uint2 px[kLaneWarps][32][9];                   // [warp][block][row + pad]: the blocks' pixels for the replay phase
+    unsigned blk[kLaneWarps][32];
+    unsigned short pairs[kLaneWarps][32 * kPairsPerRound];   // (source lane << 6) | natural index
+};
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kLaneThreads, 4) k_replay_fwd_lane(const ReplayParams p)
+{
+    __shared__ LaneShared sh;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.tab);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(ExactTables) / 4); i += kLaneThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    const ExactTables &tab = sh.tab;
+    unsigned count = p.ctr->wl_count;
+    if (count > p.wl_cap) count = p.wl_cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned tiles = (count + 31) / 32, warps_per_grid = gridDim.x * kLaneWarps;
+    unsigned ties = 0, sat = 0;
+
+    for (unsigned tile = blockIdx.x * kLaneWarps + warp; tile < tiles; tile += warps_per_grid) {
+        const unsigned slot = tile * 32 + lane;
+        const bool active = slot < count;
+        const unsigned b = active ? p.worklist[slot] : 0;
+        const unsigned by = b / p.bw, bx = b - by * p.bw;
+        const uint8_t *src = p.px_in + (long long)by * 8 * p.pitch + (long long)bx * 8;
+        uint2 row[8];
+        if (slot < p.side_cap && active) {        // K1 left the block's 64 pixels next to its worklist entry
+            const uint4 *sd = reinterpret_cast<const uint4 *>(p.side + (size_t)slot * 64);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint4 v = sd[i];
+                row[2 * i] = make_uint2(v.x, v.y), row[2 * i + 1] = make_uint2(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                row[i] = active ? *reinterpret_cast<const uint2 *>(src + i * p.pitch) : make_uint2(0x80808080u, 0x80808080u);
+        }
+
+        // ---- phase 1: K1's fp32 arithmetic for the whole block (rows, then columns), find the flagged coefficients
+        float c[64];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fdct8_row_from_bytes(&c[8 * i], row[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fdct8<float, 8>(&c[j]);          // c[8u + j] = scaled coefficient (u, j)
+        unsigned need_lo = 0, need_hi = 0;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            float t, e;
+            quant_residual(c[k], tab.r32[k], t, e);
+            if (fabsf(e) >= tab.thr32[k]) (k < 32 ? need_lo : need_hi) |= 1u << (k & 31);
+        }
+        if (!active) need_lo = need_hi = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sh.px[warp][lane][i] = row[i];
+        sh.blk[warp][lane] = b;
+
+        // ---- phase 2: rounds of (compact the pairs, one lane replays one value) until no lane has any left
+        while (__any_sync(0xffffffffu, (need_lo | need_hi) != 0)) {
+            const int mine = min(__popc(need_lo) + __popc(need_hi), kPairsPerRound);
+            int before = mine;                                       // inclusive prefix sum over the lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, before, d);
+                if (lane >= d) before += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, before, 31);
+            before -= mine;
+            for (int n = 0; n < mine; ++n) {
+                int k;
+                if (need_lo) {
+                    k = __ffs(need_lo) - 1;
+                    need_lo &= need_lo - 1;
+                } else {
+                    k = 32 + __ffs(need_hi) - 1;
+                    need_hi &= need_hi - 1;
+                }
+                sh.pairs[warp][before + n] = (unsigned short)((lane << 6) | k);
+            }
+            __syncwarp();
+            for (int pi = lane; pi < total; pi += 32) {
+                const unsigned pr = sh.pairs[warp][pi];
+                const int sl = pr >> 6, k = pr & 63, i = k >> 3, j = k & 7;
+                const double *Dj = &tab.D[j * 8], *Di = &tab.D[i * 8];
+                double dj[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) dj[m] = Dj[m];
+                double out = 0.0;    // out[i][j] = sum_kk D[i][kk] * temp[kk][j]  (src/dct.c:67-74), kk ascending
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint2 raw = sh.px[warp][sl][kk];
+                    double temp = 0.0;   // temp[kk][j] = sum_m X[kk][m] * D[j][m]  (src/dct.c:57-64), m ascending
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) temp = __dadd_rn(temp, __dmul_rn(byte_centered(raw, m), dj[m]));
+                    out = __dadd_rn(out, __dmul_rn(Di[kk], temp));
+                }
+                const double y = __ddiv_rn(out, tab.Q[k]);           // src/quantization.c:124
+                const double rr = round_half_away(y);
+                int q = (int)rr;
+                if (rr > 32767.0) q = 32767, ++sat;
+                if (rr < -32768.0) q = -32768, ++sat;
+                ties += near_half(y);
+                const int pos = LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[k] : k;
+                p.coef_out[(size_t)sh.blk[warp][sl] * 64 + pos] = (int16_t)q;
+            }
+            __syncwarp();
+        }
+    }
+
+    ties = __reduce_add_sync(0xffffffffu, ties);
+    sat = __reduce_add_sync(0xffffffffu, sat);
+    if (lane == 0) {
+        if (ties) atomicAdd(&p.ctr->near_ties, (unsigned long long)ties);
+        if (sat) atomicAdd(&p.ctr->saturated, (unsigned long long)sat);
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
+    __syncthreads();
+    if (threadIdx.x == 0) {                 // the last CTA empties the worklist (see k_replay_fwd)
+        __threadfence();
+        if (atomicAdd(&p.ctr->done_ctas, 1u) == gridDim.x - 1) {
+            p.ctr->wl_count = 0;
+            p.ctr->done_ctas = 0;
+        }
+    }
+}
+
 // the reference's dequantised value of natural index k (src/quantization.c:133-151)
 __device__ __forceinline__ double exact_dequant(const ExactTables &tab, int adaptive, double inv_two_minus_nv, int k, int q)
 {
@@ -561,6 +706,11 @@ template <typename K> static cudaError_t launch_replay(K kernel, const ReplayPar
 
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s)
 {
+    if (!p.px_is_f32 && !p.adaptive && p.worklist != nullptr) {      // the common case: one lane per flagged block
+        if (p.layout == LAYOUT_ZIGZAG) k_replay_fwd_lane<LAYOUT_ZIGZAG><<<148 * 4, kLaneThreads, 0, s>>>(p);
+        else k_replay_fwd_lane<LAYOUT_NATURAL><<<148 * 4, kLaneThreads, 0, s>>>(p);
+        return cudaGetLastError();
+    }
     if (p.px_is_f32)
         return p.layout == LAYOUT_ZIGZAG ? launch_replay(k_replay_fwd<LAYOUT_ZIGZAG, true>, p, s)
                                          : launch_replay(k_replay_fwd<LAYOUT_NATURAL, true>, p, s);

@@ -180,11 +180,16 @@ int ensure_worklist(Lane &ln, size_t nblocks)
         CU_TRY(cudaStreamSynchronize(ln.stream));
         CU_TRY(cudaDeviceSynchronize());
         CU_TRY(cudaFree(ln.d_wl));
-        ln.d_wl = nullptr;
-        ln.wl_cap = 0;
+        if (ln.d_side) CU_TRY(cudaFree(ln.d_side));
+        ln.d_wl = nullptr, ln.d_side = nullptr;
+        ln.wl_cap = 0, ln.side_cap = 0;
     }
     CU_TRY(cudaMalloc(&ln.d_wl, nblocks * sizeof(uint32_t)));
     ln.wl_cap = (uint32_t)nblocks;
+    // room for the pixels of one block in eight (uniform noise at q50 flags 2.7 %); later slots fall back to the plane
+    const size_t side = nblocks / 8 + 1024;
+    CU_TRY(cudaMalloc(&ln.d_side, side * 64));
+    ln.side_cap = (uint32_t)side;
     return DCT_CUDA_OK;
 }
 
@@ -242,6 +247,9 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
     rp.pitch = (long long)pitch;
     rp.px_in = d_px;
     rp.px_is_f32 = elem == 4;
+    const bool use_side = elem == 1 && !p->adaptive;      // the one-lane-per-block replay kernel reads it
+    rp.side = use_side ? ln.d_side : nullptr;
+    rp.side_cap = use_side ? ln.side_cap : 0;
     rp.coef_out = d_coef;
     rp.var_out = p->adaptive ? d_var : nullptr;
     if (!p->exotic) {
@@ -259,6 +267,8 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
         memcpy(fp.thr, elem == 4 ? p->thr_f32 : p->thr, sizeof fp.thr);
         fp.thr_min = p->thr_min;
         fp.uniform_band = p->uniform_band;
+        fp.side = use_side ? ln.d_side : nullptr;
+        fp.side_cap = use_side ? ln.side_cap : 0;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (p->profile) {
             CU_TRY(cudaEventCreate(&e0));
@@ -460,6 +470,7 @@ extern "C" void dct_cuda_plan_destroy(dct_cuda_plan *p)
         Lane &ln = p->lane[l];
         if (ln.d_ctr) cudaFree(ln.d_ctr);
         if (ln.d_wl) cudaFree(ln.d_wl);
+        if (ln.d_side) cudaFree(ln.d_side);
         if (ln.d_px) cudaFree(ln.d_px);
         if (ln.d_coef) cudaFree(ln.d_coef);
         if (ln.d_var) cudaFree(ln.d_var);
