@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
 }
 
 // ------------------------------------------------------------------------------------------
-// K3 forward, common case (uint8 pixels, non-adaptive table, worklist mode): ONE LANE PER FLAGGED BLOCK.
+// K3 forward, common case (uint8 pixels, worklist mode; adaptive tables included): ONE LANE PER FLAGGED BLOCK.
 // The 8-lanes-per-block kernel above spends ~125 warp instructions per block, most of them on the
 // shared-memory transposes of its re-flagging phase and on a replay phase that keeps 8 lanes busy with
 // one value.  Here a lane repeats K1's fp32 arithmetic for its whole block in registers (the same
@@ -292,6 +292,7 @@ struct LaneShared {
     ExactTables tab;
     uint2 px[kLaneWarps][32][9];                   // [warp][block][row + pad]: the blocks' pixels for the replay phase
     unsigned blk[kLaneWarps][32];
+    double scale[kLaneWarps][32];                  // adaptive: 2 - nv of each block
     unsigned short pairs[kLaneWarps][32 * kPairsPerRound];   // (source lane << 6) | natural index
 };
 
@@ -338,14 +339,29 @@ __global__ void __launch_bounds__(kLaneThreads, 4) k_replay_fwd_lane(const Repla
         for (int i = 0; i < 8; ++i) fdct8_row_from_bytes(&c[8 * i], row[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) fdct8<float, 8>(&c[j]);          // c[8u + j] = scaled coefficient (u, j)
+        // adaptive tables: the block's variance from exact integer moments, as in K1 (src/quantization.c:153-190)
+        float inv_s = 1.0f;
+        double scale = 1.0;
+        if (p.adaptive) {
+            int isum = 0, isq = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) row_moments(row[i], isum, isq);
+            const double mean = __ddiv_rn((double)isum, 64.0);
+            const double var = __dsub_rn(__ddiv_rn((double)isq, 64.0), __dmul_rn(mean, mean));
+            scale = __dsub_rn(2.0, norm_variance(var));   // src/quantization.c:190
+            inv_s = adaptive_inv_scale(64 * isq - isum * isum);
+        }
         unsigned need_lo = 0, need_hi = 0;
 #pragma unroll
         for (int k = 0; k < 64; ++k) {
             float t, e;
-            quant_residual(c[k], tab.r32[k], t, e);
+            float rk = tab.r32[k];
+            if (k != 0) rk = __fmul_rn(rk, inv_s);        // inv_s == 1.0f exactly when the table is not adaptive
+            quant_residual(c[k], rk, t, e);
             if (fabsf(e) >= tab.thr32[k]) (k < 32 ? need_lo : need_hi) |= 1u << (k & 31);
         }
         if (!active) need_lo = need_hi = 0;
+        if (p.adaptive) sh.scale[warp][lane] = scale;
 #pragma unroll
         for (int i = 0; i < 8; ++i) sh.px[warp][lane][i] = row[i];
         sh.blk[warp][lane] = b;
@@ -389,7 +405,12 @@ __global__ void __launch_bounds__(kLaneThreads, 4) k_replay_fwd_lane(const Repla
                     for (int m = 0; m < 8; ++m) temp = __dadd_rn(temp, __dmul_rn(byte_centered(raw, m), dj[m]));
                     out = __dadd_rn(out, __dmul_rn(Di[kk], temp));
                 }
-                const double y = __ddiv_rn(out, tab.Q[k]);           // src/quantization.c:124
+                double mq = tab.Q[k];
+                if (p.adaptive && k != 0) {                          // src/quantization.c:196-204
+                    mq = __dmul_rn(mq, sh.scale[warp][sl]);
+                    if (mq < 1.0) mq = 1.0;
+                }
+                const double y = __ddiv_rn(out, mq);                 // src/quantization.c:124
                 const double rr = round_half_away(y);
                 int q = (int)rr;
                 if (rr > 32767.0) q = 32767, ++sat;
@@ -706,7 +727,7 @@ template <typename K> static cudaError_t launch_replay(K kernel, const ReplayPar
 
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s)
 {
-    if (!p.px_is_f32 && !p.adaptive && p.worklist != nullptr) {      // the common case: one lane per flagged block
+    if (!p.px_is_f32 && p.worklist != nullptr) {      // uint8 planes on the fast path: one lane per flagged block
         if (p.layout == LAYOUT_ZIGZAG) k_replay_fwd_lane<LAYOUT_ZIGZAG><<<148 * 4, kLaneThreads, 0, s>>>(p);
         else k_replay_fwd_lane<LAYOUT_NATURAL><<<148 * 4, kLaneThreads, 0, s>>>(p);
         return cudaGetLastError();

@@ -247,7 +247,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
     rp.pitch = (long long)pitch;
     rp.px_in = d_px;
     rp.px_is_f32 = elem == 4;
-    const bool use_side = elem == 1 && !p->adaptive;      // the one-lane-per-block replay kernel reads it
+    const bool use_side = elem == 1;                      // the one-lane-per-block replay kernel reads it
     rp.side = use_side ? ln.d_side : nullptr;
     rp.side_cap = use_side ? ln.side_cap : 0;
     rp.coef_out = d_coef;
