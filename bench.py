@@ -8,12 +8,14 @@ Workload (BASELINE.json configs[1]): 3840x2160 8-bit grayscale frames, quality 5
 NATURAL layout.  One STEP = one pass of the hot path over one batch of `--frames` synthetic frames:
 K1 (u8 pixels -> int16 records) followed by K2 (records -> u8 pixels), both through libdct_cuda's
 C ABI.  The batch (64 frames = 531 MB of pixels + 1.06 GB of records) is larger than the 126 MB
-L2, so no flush is needed between iterations.  `value` counts every pixel once per direction:
+L2, so no flush is needed between iterations.  (Larger batches gain ~1 % and run into the software
+power cap within a 100-step region: 128 frames 1 692, 256 frames 1 698 Gpixel/s against 1 677.)  `value` counts every pixel once per direction:
     value = 2 * frames * W * H * n_gpus / step_time           [Gpixel/s, device-resident]
 `e2e` is the same metric through the host-plane calls with PINNED HOST buffers, the H2D and D2H
 copies inside the timed region.  `roofline` is for K1 (the dominant kernel): 192 algorithmic bytes
-per 8x8 block (64 B of pixels in, 128 B of records out) over the K1 launches' own
-CUDA-event time, against the measured copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` times
+per 8x8 block (64 B of pixels in, 128 B of records out) over the K1 phase's own
+CUDA-event time (the library cuts a plane of more than ~12 M blocks into several K1 launches; the
+events bracket all of them and the bytes are the whole plane's), against the measured copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` times
 the reference's own C code (oracle/_ref, else the oracle port) on this box's host cores.
 
 Multi-GPU: every rank owns its own batch (weak scaling), no data-path collective; torch.distributed
@@ -237,22 +239,23 @@ def main():
     sampler.start()
     time.sleep(0.15)
     plan.profile(True)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    launches0 = plan.kernel_launches()
     barrier()
     t_wall0 = time.perf_counter()
     ev[0].record()
     for i in range(args.steps):
         plan.fwd_quant_dev(px, args.layout, coef, var)
-        ev[3 * i + 1].record()
+        ev[2 * i + 1].record()
         plan.dequant_idct_dev(coef, W, rows, args.layout, var, rec)
-        ev[3 * i + 2].record()
-        ev[3 * i + 3].record()
+        ev[2 * i + 2].record()
     barrier()
     t_wall1 = time.perf_counter()
+    gpu_launches = plan.kernel_launches() - launches0        # counted by the library: K1 (cut into ~12 M-block launches), K3, K2, K3
     plan.profile(False)
-    total_ms = ev[0].elapsed_time(ev[3 * args.steps])
-    fwd_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps))
-    inv_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps))
+    total_ms = ev[0].elapsed_time(ev[2 * args.steps])
+    fwd_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps))
+    inv_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps))
     prof = plan.profile_fetch()
     stats = plan.stats()
     clocks = sampler.stop(t_wall0, t_wall1)
@@ -384,7 +387,7 @@ def main():
                    "sharding": "one batch per GPU, no collective on the data path"},
         "fwd_gpixel_per_s_per_gpu": npx / (fwd_ms / args.steps * 1e-3) / 1e9,
         "inv_gpixel_per_s_per_gpu": npx / (inv_ms / args.steps * 1e-3) / 1e9,
-        "e2e": e2e, "gpu_launches": 4 * args.steps,
+        "e2e": e2e, "gpu_launches": gpu_launches,
         "launches_per_step": "K1 k_fwd_quant_u8, K3 k_replay_fwd, K2 k_dequant_idct_u8, K3 k_replay_inv",
         "roofline": roofline, "clocks": clocks,
         "replay": {"blocks": stats["blocks"], "replayed_blocks": stats["replayed_blocks"],

@@ -131,6 +131,7 @@ _pad_edges = _sig("dct_cuda_pad_edges_dev", C.c_int, C.c_int, C.c_void_p, C.c_si
                   C.c_void_p)
 
 
+_kernel_launches = _sig("dct_cuda_plan_kernel_launches", C.c_uint64, C.c_void_p)
 _fits_i8 = _sig("dct_cuda_plan_records_fit_i8", C.c_int, C.c_void_p)
 _fwd_i8 = _sig("dct_cuda_fwd_quant_u8_i8", C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Stats))
@@ -460,6 +461,9 @@ class Plan:
     def dequant_idct_i8_ptr_async(self, coef_ptr, W, H, px_ptr, pitch, layout=NATURAL, var_ptr=None):
         _check(_inv_i8_async(self._h, coef_ptr, W, H, layout, var_ptr, px_ptr, pitch))
 
+    def kernel_launches(self) -> int:
+        return int(_kernel_launches(self._h))
+
     def wait(self, want_stats=False):
         st = Stats()
         _check(_plan_wait(self._h, C.byref(st) if want_stats else None))
@@ -692,6 +696,6 @@ def exported_symbols():
             "dct_cuda_fwd_quant_u8_edge", "dct_cuda_dequant_idct_u8_edge", "dct_cuda_pad_edges_dev",
             "dct_cuda_frame420_geometry", "dct_cuda_rgb_to_ycbcr420_dev", "dct_cuda_ycbcr420_to_rgb_dev",
             "dct_cuda_encode_rgb420", "dct_cuda_decode_rgb420", "dct_cuda_peer_default_share",
-            "dct_cuda_fwd_quant_u8_peer", "dct_cuda_dequant_idct_u8_peer", "dct_cuda_plan_records_fit_i8",
+            "dct_cuda_fwd_quant_u8_peer", "dct_cuda_dequant_idct_u8_peer", "dct_cuda_plan_records_fit_i8", "dct_cuda_plan_kernel_launches",
             "dct_cuda_fwd_quant_u8_i8", "dct_cuda_dequant_idct_i8_u8", "dct_cuda_fwd_quant_u8_i8_async",
             "dct_cuda_dequant_idct_i8_u8_async", "dct_cuda_record8_to_block"]

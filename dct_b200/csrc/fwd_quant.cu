@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
                     reinterpret_cast<uint2 *>(p.side + (size_t)pos * 64)[lane] =
                         *reinterpret_cast<const uint2 *>(wsm + stage * kInWordsPerStage + lane * 64 + f * 2);
             } else if (lane == 8 && pos < p.wl_cap) {
-                p.worklist[pos] = warp_base + f;
+                p.worklist[pos] = p.block_base + warp_base + f;
             }
         }
     }
@@ -324,14 +324,14 @@ static int sm_count()
     return cached[dev];
 }
 
-template <typename K> static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t s)
+constexpr unsigned kChunkBlocks = 12u << 20;   // ~97 4K frames per launch
+
+template <typename K> static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t s, unsigned *launches)
 {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    const unsigned ntiles = (p.nblocks + 31) / 32;
-    const unsigned want = (ntiles + kWarps - 1) / kWarps;
     static int per_sm = 0;   // resident CTAs per SM for this instantiation (3 by design: registers and shared memory)
     if (per_sm == 0) {
         int n = 0;
@@ -340,19 +340,43 @@ template <typename K> static cudaError_t launch_persistent(K kernel, const FwdPa
         if (getenv("DCT_CUDA_DEBUG")) fprintf(stderr, "libdct_cuda: %s: %d CTAs/SM, %d B smem\n", __FILE__, n, kSmemBytes);
     }
     const unsigned resident = (unsigned)sm_count() * (unsigned)per_sm;
-    const unsigned grid = want < resident ? want : resident;
-    FwdParams q = p;
-    const unsigned step = grid * kWarps * 32;                  // blocks between consecutive tiles of a warp
-    q.step_q = step / p.bw;
-    q.step_r = step - q.step_q * p.bw;
-    kernel<<<grid, kThreads, kSmemBytes, s>>>(q);
-    return cudaGetLastError();
+    // The warps of a persistent launch walk fixed tile sequences and nothing re-aligns them, so over a very long
+    // launch the fast ones run ahead of the slow ones and the working set in flight (DRAM pages, TLB entries)
+    // grows: measured, K1 needs 292 us per 64 4K frames up to ~256 frames per launch and 420-480 us beyond 384.
+    // Planes larger than kChunkBlocks are therefore cut into block-row ranges, one launch each, back to back on the
+    // stream; worklist entries carry the plane-wide block index (block_base).
+    static const unsigned chunk_blocks = getenv("DCT_CUDA_K1_CHUNK") ? (unsigned)atol(getenv("DCT_CUDA_K1_CHUNK")) : kChunkBlocks;
+    const unsigned total_rows = p.nblocks / p.bw;
+    unsigned rows_per_launch = total_rows;
+    if (p.nblocks > chunk_blocks && p.nblocks % p.bw == 0) rows_per_launch = chunk_blocks / p.bw > 0 ? chunk_blocks / p.bw : 1;
+    for (unsigned r0 = 0; r0 < total_rows || r0 == 0; r0 += rows_per_launch) {
+        FwdParams q = p;
+        if (rows_per_launch < total_rows) {
+            const unsigned nr = total_rows - r0 < rows_per_launch ? total_rows - r0 : rows_per_launch;
+            q.px = p.px + (long long)r0 * 8 * p.pitch;
+            q.coef = p.coef + (size_t)r0 * p.bw * 64;
+            if (p.var_out) q.var_out = p.var_out + (size_t)r0 * p.bw;
+            q.nblocks = nr * p.bw;
+            q.block_base = r0 * p.bw;
+        }
+        const unsigned ntiles = (q.nblocks + 31) / 32;
+        const unsigned want = (ntiles + kWarps - 1) / kWarps;
+        const unsigned grid = want < resident ? want : resident;
+        const unsigned step = grid * kWarps * 32;                  // blocks between consecutive tiles of a warp
+        q.step_q = step / p.bw;
+        q.step_r = step - q.step_q * p.bw;
+        kernel<<<grid, kThreads, kSmemBytes, s>>>(q);
+        if (launches) ++*launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess || rows_per_launch >= total_rows) return e;
+    }
+    return cudaSuccess;
 }
 
-template <int LAYOUT, bool ADAPTIVE> static cudaError_t launch_k1(const FwdParams &p, cudaStream_t s)
+template <int LAYOUT, bool ADAPTIVE> static cudaError_t launch_k1(const FwdParams &p, cudaStream_t s, unsigned *launches)
 {
-    return p.uniform_band ? launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, true>, p, s)
-                          : launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, false>, p, s);
+    return p.uniform_band ? launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, true>, p, s, launches)
+                          : launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, false>, p, s, launches);
 }
 
 cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s)
@@ -364,12 +388,13 @@ cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s)
+cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s, unsigned *launches)
 {
+    if (launches) *launches = 0;
     if (p.nblocks == 0) return cudaSuccess;
     if (layout == LAYOUT_ZIGZAG)
-        return adaptive ? launch_k1<LAYOUT_ZIGZAG, true>(p, s) : launch_k1<LAYOUT_ZIGZAG, false>(p, s);
-    return adaptive ? launch_k1<LAYOUT_NATURAL, true>(p, s) : launch_k1<LAYOUT_NATURAL, false>(p, s);
+        return adaptive ? launch_k1<LAYOUT_ZIGZAG, true>(p, s, launches) : launch_k1<LAYOUT_ZIGZAG, false>(p, s, launches);
+    return adaptive ? launch_k1<LAYOUT_NATURAL, true>(p, s, launches) : launch_k1<LAYOUT_NATURAL, false>(p, s, launches);
 }
 
 }  // namespace dctb

@@ -50,6 +50,7 @@ struct FwdParams {
     float r[64];           // natural index: 1 / (Q_k * 8 a_u a_v)
     float thr[64];         // natural index: 0.5 - band_k ; |residual| >= thr  => replay in fp64
     uint32_t step_q, step_r;   // divmod(blocks between a warp's consecutive tiles, bw): set by the launcher
+    uint32_t block_base;       // plane-wide index of this launch's first block (large planes are cut into launches)
     float thr_min;         // min_k thr[k]: the single threshold of the uniform-band variant
     int uniform_band;      // 1: test max_k |residual| >= thr_min (cheaper, slightly more replays)
     // Optional: the pixels of the flagged blocks, copied next to their worklist entry (64 bytes at side + 64 * slot
@@ -109,7 +110,8 @@ struct ReplayParams {
     uint8_t *px_out;
 };
 
-cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s);
+// `launches` (optional) receives the number of kernel launches made: planes beyond ~12 M blocks are cut into several
+cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s, unsigned *launches = nullptr);
 cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s);
 cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s);
 cudaError_t launch_dequant_idct_u8_f64(const InvParams &p, const ExactTables *d_tab, int layout, cudaStream_t s);

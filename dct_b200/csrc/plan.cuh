@@ -93,6 +93,7 @@ struct dct_cuda_plan {
     uint8_t *d_frame = nullptr;
     size_t frame_cap = 0;
     cudaEvent_t ev_peer = nullptr;              // *_peer calls: "input ready" (owner) / "shard done" (peers)
+    uint64_t launches = 0;                      // kernels launched for this plan (dct_cuda_plan_kernel_launches)
     bool fits_i8 = false;                       // every quantised value of a uint8 plane fits int8 (narrow.cu)
     std::mutex mu;                              // serialises the entry points on one plan (lanes and buffers are state)
 };

@@ -247,7 +247,8 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
     rp.pitch = (long long)pitch;
     rp.px_in = d_px;
     rp.px_is_f32 = elem == 4;
-    const bool use_side = elem == 1;                      // the one-lane-per-block replay kernel reads it
+    static const bool no_side = getenv("DCT_CUDA_NO_SIDE") != nullptr;   // debugging aid: K3 reads the plane instead
+    const bool use_side = elem == 1 && !no_side;          // the one-lane-per-block replay kernel reads it
     rp.side = use_side ? ln.d_side : nullptr;
     rp.side_cap = use_side ? ln.side_cap : 0;
     rp.coef_out = d_coef;
@@ -275,15 +276,20 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
             CU_TRY(cudaEventCreate(&e1));
             CU_TRY(cudaEventRecord(e0, s));
         }
+        unsigned k1_launches = 1;
         if (elem == 4) CU_TRY(launch_fwd_quant_f32(fp, layout, s));
-        else CU_TRY(launch_fwd_quant_u8(fp, layout, p->adaptive, s));
+        else CU_TRY(launch_fwd_quant_u8(fp, layout, p->adaptive, s, &k1_launches));
+        p->launches += k1_launches;
         if (p->profile) {
             CU_TRY(cudaEventRecord(e1, s));
             ln.ev_fwd.emplace_back(e0, e1);
         }
         rp.worklist = ln.d_wl;
     }
-    if (!p->skip_replay || p->exotic) CU_TRY(launch_replay_fwd(rp, s));
+    if (!p->skip_replay || p->exotic) {
+        CU_TRY(launch_replay_fwd(rp, s));
+        ++p->launches;
+    }
     ln.blocks += nblocks;
     return DCT_CUDA_OK;
 }
@@ -350,13 +356,17 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
         // adaptive plans decode full-scale values: the fp64 butterfly keeps the replay list short
         if (p->adaptive && !p->force_fp32_inverse) CU_TRY(launch_dequant_idct_u8_f64(ip, p->d_tab, layout, s));
         else CU_TRY(launch_dequant_idct_u8(ip, layout, p->adaptive, s));
+        ++p->launches;
         if (p->profile) {
             CU_TRY(cudaEventRecord(e1, s));
             ln.ev_inv.emplace_back(e0, e1);
         }
         rp.worklist = ln.d_wl;
     }
-    if (!p->skip_replay || p->exotic) CU_TRY(launch_replay_inv(rp, s));
+    if (!p->skip_replay || p->exotic) {
+        CU_TRY(launch_replay_inv(rp, s));
+        ++p->launches;
+    }
     ln.blocks += nblocks;
     return DCT_CUDA_OK;
 }
@@ -488,6 +498,8 @@ extern "C" void dct_cuda_plan_destroy(dct_cuda_plan *p)
 }
 
 extern "C" int dct_cuda_plan_device(const dct_cuda_plan *p) { return p ? p->device : -1; }
+
+extern "C" uint64_t dct_cuda_plan_kernel_launches(const dct_cuda_plan *p) { return p ? p->launches : 0; }
 
 // ------------------------------------------------------------------------------------------
 // device-resident planes
@@ -657,6 +669,7 @@ static int fwd_host_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int
             if (rec8) {
                 int8_t *d8 = reinterpret_cast<int8_t *>(ln.d_coef) + ln.cap_blocks * 2;
                 CU_TRY(launch_narrow_records(ln.d_coef, d8, nb * nn, ln.d_ctr, ln.stream));
+                ++p->launches;
                 CU_TRY(cudaMemcpyAsync((int8_t *)coef + b0 * nn, d8, nb * nn, cudaMemcpyDeviceToHost, ln.stream));
             } else {
                 CU_TRY(cudaMemcpyAsync((int16_t *)coef + b0 * nn, ln.d_coef, nb * nn * 2, cudaMemcpyDeviceToHost, ln.stream));
@@ -728,6 +741,7 @@ static int inv_host_async(dct_cuda_plan *p, const void *coef, int W, int H, int 
                 int8_t *d8 = reinterpret_cast<int8_t *>(ln.d_coef) + ln.cap_blocks * 2;
                 CU_TRY(cudaMemcpyAsync(d8, (const int8_t *)coef + b0 * nn, nb * nn, cudaMemcpyHostToDevice, ln.stream));
                 CU_TRY(launch_widen_records(d8, ln.d_coef, nb * nn, ln.stream));
+                ++p->launches;
             } else {
                 CU_TRY(cudaMemcpyAsync(ln.d_coef, (const int16_t *)coef + b0 * nn, nb * nn * 2, cudaMemcpyHostToDevice, ln.stream));
             }
