@@ -14,8 +14,8 @@ power cap within a 100-step region: 128 frames 1 692, 256 frames 1 698 Gpixel/s 
 `e2e` is the same metric through the host-plane calls with PINNED HOST buffers, the H2D and D2H
 copies inside the timed region.  `roofline` is for K1 (the dominant kernel): 192 algorithmic bytes
 per 8x8 block (64 B of pixels in, 128 B of records out) over the K1 phase's own
-CUDA-event time (the library cuts a plane of more than ~12 M blocks into several K1 launches; the
-events bracket all of them and the bytes are the whole plane's), against the measured copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` times
+CUDA-event time (the library cuts a plane of more than ~12 M blocks into several K1 + K3 passes; their
+K1 times are summed and the bytes are the whole plane's), against the measured copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` times
 the reference's own C code (oracle/_ref, else the oracle port) on this box's host cores.
 
 Multi-GPU: every rank owns its own batch (weak scaling), no data-path collective; torch.distributed
@@ -251,7 +251,7 @@ def main():
         ev[2 * i + 2].record()
     barrier()
     t_wall1 = time.perf_counter()
-    gpu_launches = plan.kernel_launches() - launches0        # counted by the library: K1 (cut into ~12 M-block launches), K3, K2, K3
+    gpu_launches = plan.kernel_launches() - launches0        # counted by the library: K1, K3, K2, K3 per step
     plan.profile(False)
     total_ms = ev[0].elapsed_time(ev[2 * args.steps])
     fwd_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps))
@@ -358,8 +358,8 @@ def main():
 
     # ---- roofline of the dominant kernel (K1) -----------------------------------------------------
     peak, peak_src = measured_peak()
-    k1_ms = prof["fwd_ms"] / max(prof["fwd_launches"], 1)
-    k2_ms = prof["inv_ms"] / max(prof["inv_launches"], 1)
+    k1_ms = prof["fwd_ms"] / max(args.steps, 1)        # K1 time per step (planes beyond 12 M blocks take several launches)
+    k2_ms = prof["inv_ms"] / max(args.steps, 1)
     alg_bytes = 192.0 * nblocks
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_fwd_quant_u8 (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",

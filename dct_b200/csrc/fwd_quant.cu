@@ -65,8 +65,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
     uint32_t *wstage = wsm + kInStages * kInWordsPerStage;                       // output stage
     const uint32_t in_addr = (uint32_t)__cvta_generic_to_shared(wsm) + lane * 8;   // + stage*2048 + row*256
 
-    const uint32_t ntiles = (p.nblocks + 31) >> 5;
-    const uint32_t tile_stride = gridDim.x * kWarps;
+    // loop bounds straight from the parameter bank (set by the launcher): no registers held for them
+#define ntiles p.ntiles
+#define tile_stride p.tile_stride
     uint32_t tile = blockIdx.x * kWarps + warp;
 
     // Each lane copies the 8 rows of its own block (lane-private data: no cross-lane hazard on the
@@ -90,6 +91,11 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
         nby += p.step_q;
         if (nbx >= p.bw) nbx -= p.bw, ++nby;
     };
+
+    // entries this warp has appended to its worklist segment: kept in a padding word of the warp's output stage
+    // (words 32..35 of a record row are never written), not in a register -- the kernel sits on its 80-register budget
+    if (lane == 0) wstage[32] = 0;
+    __syncwarp();
 
     int stage = 0;
     if (tile < ntiles) issue(0);
@@ -172,11 +178,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
 
     if constexpr (UNIFORM) flag = emax >= p.thr_min;
 
-    // Warp-aggregated reservation of worklist slots.  The atomicAdd is issued here and its result (an
-    // L2 round trip) is consumed after the record stores below, so most of its latency is covered.
     const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
-    unsigned wl_base = 0;
-    if (ballot != 0 && (int)lane == __ffs(ballot) - 1) wl_base = atomicAdd(&p.ctr->wl_count, (unsigned)__popc(ballot));
 
     // stage: lane-major padded records in shared memory, then 512-byte contiguous warp stores
 #pragma unroll
@@ -199,26 +201,34 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
     }
 
     if (ballot != 0) {
-        const unsigned base = __shfl_sync(0xffffffffu, wl_base, __ffs(ballot) - 1);
-        // One round per flagged block (usually a single one): lane 8 appends the worklist entry, lanes 0-7 copy one
-        // pixel row each from this tile's input stage to the 64 bytes that go with the entry (K3 reads those instead
-        // of eight scattered rows of the plane).
-        unsigned pos = base;
-        for (unsigned todo = ballot; todo != 0; todo &= todo - 1, ++pos) {
+        // The warp appends to its own segment of the worklist: no global atomic (a same-address atomic per flagged
+        // tile was measured to cost ~5 us per tile once a process had several GB of planes in play).  One round per
+        // flagged block (usually a single one): lane 8 writes the entry, lanes 0-7 copy one pixel row each from this
+        // tile's input stage to the 64 bytes that go with the entry (K3 reads those instead of eight scattered
+        // rows of the plane).
+        const uint32_t gwarp = blockIdx.x * kWarps + warp;
+        uint32_t wl_n = wstage[32];
+        __syncwarp();
+        if (lane == 0) wstage[32] = wl_n + __popc(ballot);
+        for (unsigned todo = ballot; todo != 0; todo &= todo - 1, ++wl_n) {
             const unsigned f = __ffs(todo) - 1;
             if (lane < 8) {
-                if (pos < p.side_cap)
-                    reinterpret_cast<uint2 *>(p.side + (size_t)pos * 64)[lane] =
+                if (wl_n < p.side_seg_cap)
+                    reinterpret_cast<uint2 *>(p.side + ((size_t)gwarp * p.side_seg_cap + wl_n) * 64)[lane] =
                         *reinterpret_cast<const uint2 *>(wsm + stage * kInWordsPerStage + lane * 64 + f * 2);
-            } else if (lane == 8 && pos < p.wl_cap) {
-                p.worklist[pos] = p.block_base + warp_base + f;
+            } else if (lane == 8) {
+                p.worklist[(size_t)gwarp * p.seg_cap + wl_n] = warp_base + f;
             }
         }
     }
     __syncwarp();   // the output stage is rewritten by the next tile
     }   // tile loop
+    if (lane == 0) p.seg_count[blockIdx.x * kWarps + warp] = wstage[32];   // < seg_cap by construction (32 per tile)
 }
 
+
+#undef ntiles
+#undef tile_stride
 
 // ------------------------------------------------------------------------------------------
 // K1 from FLOAT pixel tiles (north_star: "8-bit or float pixel tiles"): block = (double)p - 128.0
@@ -324,9 +334,8 @@ static int sm_count()
     return cached[dev];
 }
 
-constexpr unsigned kChunkBlocks = 12u << 20;   // ~97 4K frames per launch
-
-template <typename K> static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t s, unsigned *launches)
+template <typename K>
+static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
 {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -340,43 +349,32 @@ template <typename K> static cudaError_t launch_persistent(K kernel, const FwdPa
         if (getenv("DCT_CUDA_DEBUG")) fprintf(stderr, "libdct_cuda: %s: %d CTAs/SM, %d B smem\n", __FILE__, n, kSmemBytes);
     }
     const unsigned resident = (unsigned)sm_count() * (unsigned)per_sm;
-    // The warps of a persistent launch walk fixed tile sequences and nothing re-aligns them, so over a very long
-    // launch the fast ones run ahead of the slow ones and the working set in flight (DRAM pages, TLB entries)
-    // grows: measured, K1 needs 292 us per 64 4K frames up to ~256 frames per launch and 420-480 us beyond 384.
-    // Planes larger than kChunkBlocks are therefore cut into block-row ranges, one launch each, back to back on the
-    // stream; worklist entries carry the plane-wide block index (block_base).
-    static const unsigned chunk_blocks = getenv("DCT_CUDA_K1_CHUNK") ? (unsigned)atol(getenv("DCT_CUDA_K1_CHUNK")) : kChunkBlocks;
-    const unsigned total_rows = p.nblocks / p.bw;
-    unsigned rows_per_launch = total_rows;
-    if (p.nblocks > chunk_blocks && p.nblocks % p.bw == 0) rows_per_launch = chunk_blocks / p.bw > 0 ? chunk_blocks / p.bw : 1;
-    for (unsigned r0 = 0; r0 < total_rows || r0 == 0; r0 += rows_per_launch) {
-        FwdParams q = p;
-        if (rows_per_launch < total_rows) {
-            const unsigned nr = total_rows - r0 < rows_per_launch ? total_rows - r0 : rows_per_launch;
-            q.px = p.px + (long long)r0 * 8 * p.pitch;
-            q.coef = p.coef + (size_t)r0 * p.bw * 64;
-            if (p.var_out) q.var_out = p.var_out + (size_t)r0 * p.bw;
-            q.nblocks = nr * p.bw;
-            q.block_base = r0 * p.bw;
-        }
-        const unsigned ntiles = (q.nblocks + 31) / 32;
-        const unsigned want = (ntiles + kWarps - 1) / kWarps;
-        const unsigned grid = want < resident ? want : resident;
-        const unsigned step = grid * kWarps * 32;                  // blocks between consecutive tiles of a warp
-        q.step_q = step / p.bw;
-        q.step_r = step - q.step_q * p.bw;
-        kernel<<<grid, kThreads, kSmemBytes, s>>>(q);
-        if (launches) ++*launches;
-        e = cudaGetLastError();
-        if (e != cudaSuccess || rows_per_launch >= total_rows) return e;
-    }
-    return cudaSuccess;
+    const unsigned ntiles = (p.nblocks + 31) / 32;
+    const unsigned want = (ntiles + kWarps - 1) / kWarps;
+    const unsigned grid = want < resident ? want : resident;
+    FwdParams q = p;
+    const unsigned step = grid * kWarps * 32;                  // blocks between consecutive tiles of a warp
+    q.step_q = step / p.bw;
+    q.step_r = step - q.step_q * p.bw;
+    q.ntiles = ntiles;
+    q.tile_stride = grid * kWarps;
+    // one worklist / side-array segment per warp of the grid
+    const unsigned n_segs = grid * kWarps;
+    const unsigned tiles_per_warp = (ntiles + n_segs - 1) / n_segs;
+    q.seg_cap = p.wl_cap / n_segs;
+    q.side_seg_cap = p.side ? p.side_cap / n_segs : 0;
+    if (n_segs > kMaxWorklistSegments - 128 || q.seg_cap < tiles_per_warp * 32 || p.seg_count == nullptr) return cudaErrorInvalidValue;
+    if (segments) *segments = WorklistSegments{n_segs, q.seg_cap, q.side_seg_cap};
+    kernel<<<grid, kThreads, kSmemBytes, s>>>(q);
+    if (launches) ++*launches;
+    return cudaGetLastError();
 }
 
-template <int LAYOUT, bool ADAPTIVE> static cudaError_t launch_k1(const FwdParams &p, cudaStream_t s, unsigned *launches)
+template <int LAYOUT, bool ADAPTIVE>
+static cudaError_t launch_k1(const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
 {
-    return p.uniform_band ? launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, true>, p, s, launches)
-                          : launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, false>, p, s, launches);
+    return p.uniform_band ? launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, true>, p, s, launches, segments)
+                          : launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, false>, p, s, launches, segments);
 }
 
 cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s)
@@ -388,13 +386,17 @@ cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s)
     return cudaGetLastError();
 }
 
-cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s, unsigned *launches)
+cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s, unsigned *launches,
+                                WorklistSegments *segments)
 {
     if (launches) *launches = 0;
+    if (segments) *segments = WorklistSegments{0, 0, 0};
     if (p.nblocks == 0) return cudaSuccess;
     if (layout == LAYOUT_ZIGZAG)
-        return adaptive ? launch_k1<LAYOUT_ZIGZAG, true>(p, s, launches) : launch_k1<LAYOUT_ZIGZAG, false>(p, s, launches);
-    return adaptive ? launch_k1<LAYOUT_NATURAL, true>(p, s, launches) : launch_k1<LAYOUT_NATURAL, false>(p, s, launches);
+        return adaptive ? launch_k1<LAYOUT_ZIGZAG, true>(p, s, launches, segments)
+                        : launch_k1<LAYOUT_ZIGZAG, false>(p, s, launches, segments);
+    return adaptive ? launch_k1<LAYOUT_NATURAL, true>(p, s, launches, segments)
+                    : launch_k1<LAYOUT_NATURAL, false>(p, s, launches, segments);
 }
 
 }  // namespace dctb

@@ -50,13 +50,23 @@ struct FwdParams {
     float r[64];           // natural index: 1 / (Q_k * 8 a_u a_v)
     float thr[64];         // natural index: 0.5 - band_k ; |residual| >= thr  => replay in fp64
     uint32_t step_q, step_r;   // divmod(blocks between a warp's consecutive tiles, bw): set by the launcher
-    uint32_t block_base;       // plane-wide index of this launch's first block (large planes are cut into launches)
+    uint32_t ntiles, tile_stride;   // ceil(nblocks / 32); warps in the grid: set by the launcher
     float thr_min;         // min_k thr[k]: the single threshold of the uniform-band variant
     int uniform_band;      // 1: test max_k |residual| >= thr_min (cheaper, slightly more replays)
     // Optional: the pixels of the flagged blocks, copied next to their worklist entry (64 bytes at side + 64 * slot
     // for slot < side_cap), so that K3 reads a compact, L2-resident array instead of 8 scattered rows per block.
     uint8_t *side;
     uint32_t side_cap;
+    // k_fwd_quant_u8 only: every warp of the persistent grid appends to its OWN segment of the worklist (and of the
+    // side array) and leaves its count in seg_count[warp] -- no global atomic on the path.  Set by the launcher.
+    uint32_t *seg_count;       // one entry per warp of the grid
+    uint32_t seg_cap;          // worklist entries per segment (>= 32 * tiles per warp)
+    uint32_t side_seg_cap;     // side slots per segment (entries beyond it have no pixel copy)
+};
+
+// geometry of the segmented worklist a k_fwd_quant_u8 launch produced (consumed by k_replay_fwd_lane)
+struct WorklistSegments {
+    uint32_t n_segs, seg_cap, side_seg_cap;
 };
 
 struct alignas(16) PosNeg2 {
@@ -103,6 +113,8 @@ struct ReplayParams {
     int px_is_f32;
     const uint8_t *side;        // forward: K1's copy of the flagged blocks' pixels (see FwdParams), or null
     uint32_t side_cap;
+    const uint32_t *seg_count;  // forward, segmented worklist (see FwdParams): counts per segment, or null
+    WorklistSegments seg;
     int16_t *coef_out;
     double *var_out;
     const int16_t *coef_in;     // inverse
@@ -110,8 +122,10 @@ struct ReplayParams {
     uint8_t *px_out;
 };
 
-// `launches` (optional) receives the number of kernel launches made: planes beyond ~12 M blocks are cut into several
-cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s, unsigned *launches = nullptr);
+// `launches` (optional) is incremented by the number of kernel launches made
+cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s, unsigned *launches = nullptr,
+                                WorklistSegments *segments = nullptr);
+constexpr uint32_t kMaxWorklistSegments = 4096;   // warps of the largest persistent grid this library launches
 cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s);
 cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s);
 cudaError_t launch_dequant_idct_u8_f64(const InvParams &p, const ExactTables *d_tab, int layout, cudaStream_t s);

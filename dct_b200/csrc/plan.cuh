@@ -48,6 +48,7 @@ struct Lane {
     uint32_t wl_cap = 0;
     uint8_t *d_side = nullptr;                  // pixels of the flagged blocks, 64 B per worklist slot (first side_cap slots)
     uint32_t side_cap = 0;
+    uint32_t *d_seg_count = nullptr;            // K1's per-warp worklist counts (kMaxWorklistSegments entries)
     // strip buffers of the host-plane pipeline
     uint8_t *d_px = nullptr;
     int16_t *d_coef = nullptr;

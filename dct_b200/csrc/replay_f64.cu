@@ -294,6 +294,7 @@ struct LaneShared {
     unsigned blk[kLaneWarps][32];
     double scale[kLaneWarps][32];                  // adaptive: 2 - nv of each block
     unsigned short pairs[kLaneWarps][32 * kPairsPerRound];   // (source lane << 6) | natural index
+    unsigned prefix[kMaxWorklistSegments + 1];     // exclusive prefix sums of K1's per-warp worklist counts
 };
 
 template <int LAYOUT>
@@ -307,20 +308,49 @@ __global__ void __launch_bounds__(kLaneThreads, 4) k_replay_fwd_lane(const Repla
     }
     __syncthreads();
     const ExactTables &tab = sh.tab;
-    unsigned count = p.ctr->wl_count;
-    if (count > p.wl_cap) count = p.wl_cap;
+    // K1 left one worklist segment per warp of its grid and the segments' counts; entry e of the concatenation lives
+    // in the segment s with prefix[s] <= e < prefix[s + 1].  Every CTA builds the prefix sums for itself.
+    const unsigned n_segs = p.seg.n_segs;
+    {
+        const unsigned per = (n_segs + kLaneThreads - 1) / kLaneThreads, first = threadIdx.x * per;
+        unsigned sum = 0;
+        for (unsigned i = first; i < first + per && i < n_segs; ++i) sum += p.seg_count[i];
+        sh.prefix[kMaxWorklistSegments - kLaneThreads + threadIdx.x] = sum;   // parked at the far end, consumed below
+        __syncthreads();
+        unsigned base = 0;
+        for (unsigned t = 0; t < threadIdx.x; ++t) base += sh.prefix[kMaxWorklistSegments - kLaneThreads + t];
+        __syncthreads();
+        for (unsigned i = first; i < first + per && i < n_segs; ++i) {
+            sh.prefix[i] = base;
+            base += p.seg_count[i];
+        }
+        if (first + per >= n_segs && first <= n_segs) sh.prefix[n_segs] = base;   // exactly one thread ends at n_segs
+        __syncthreads();
+    }
+    const unsigned count = sh.prefix[n_segs];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned tiles = (count + 31) / 32, warps_per_grid = gridDim.x * kLaneWarps;
     unsigned ties = 0, sat = 0;
 
     for (unsigned tile = blockIdx.x * kLaneWarps + warp; tile < tiles; tile += warps_per_grid) {
-        const unsigned slot = tile * 32 + lane;
-        const bool active = slot < count;
-        const unsigned b = active ? p.worklist[slot] : 0;
+        const unsigned entry = tile * 32 + lane;
+        const bool active = entry < count;
+        unsigned seg = 0, local = 0;
+        if (active) {                                     // binary search: largest seg with prefix[seg] <= entry
+            unsigned lo = 0, hi = n_segs;
+            while (hi - lo > 1) {
+                const unsigned mid = (lo + hi) >> 1;
+                if (sh.prefix[mid] <= entry) lo = mid;
+                else hi = mid;
+            }
+            seg = lo, local = entry - sh.prefix[lo];
+        }
+        const unsigned slot = local < p.seg.side_seg_cap ? seg * p.seg.side_seg_cap + local : 0xffffffffu;   // side slot
+        const unsigned b = active ? p.worklist[(size_t)seg * p.seg.seg_cap + local] : 0;
         const unsigned by = b / p.bw, bx = b - by * p.bw;
         const uint8_t *src = p.px_in + (long long)by * 8 * p.pitch + (long long)bx * 8;
         uint2 row[8];
-        if (slot < p.side_cap && active) {        // K1 left the block's 64 pixels next to its worklist entry
+        if (slot != 0xffffffffu && active) {      // K1 left the block's 64 pixels next to its worklist entry
             const uint4 *sd = reinterpret_cast<const uint4 *>(p.side + (size_t)slot * 64);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -430,14 +460,7 @@ __global__ void __launch_bounds__(kLaneThreads, 4) k_replay_fwd_lane(const Repla
         if (sat) atomicAdd(&p.ctr->saturated, (unsigned long long)sat);
     }
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
-    __syncthreads();
-    if (threadIdx.x == 0) {                 // the last CTA empties the worklist (see k_replay_fwd)
-        __threadfence();
-        if (atomicAdd(&p.ctr->done_ctas, 1u) == gridDim.x - 1) {
-            p.ctr->wl_count = 0;
-            p.ctr->done_ctas = 0;
-        }
-    }
+    // nothing to reset: the next K1 overwrites every segment count
 }
 
 // the reference's dequantised value of natural index k (src/quantization.c:133-151)
@@ -727,7 +750,7 @@ template <typename K> static cudaError_t launch_replay(K kernel, const ReplayPar
 
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s)
 {
-    if (!p.px_is_f32 && p.worklist != nullptr) {      // uint8 planes on the fast path: one lane per flagged block
+    if (!p.px_is_f32 && p.worklist != nullptr && p.seg_count != nullptr) {      // uint8 planes on the fast path: one lane per flagged block
         if (p.layout == LAYOUT_ZIGZAG) k_replay_fwd_lane<LAYOUT_ZIGZAG><<<148 * 4, kLaneThreads, 0, s>>>(p);
         else k_replay_fwd_lane<LAYOUT_NATURAL><<<148 * 4, kLaneThreads, 0, s>>>(p);
         return cudaGetLastError();

@@ -175,7 +175,10 @@ int queue_generic(dct_cuda_plan *p, Lane &ln, int forward, const uint8_t *px_in,
 
 int ensure_worklist(Lane &ln, size_t nblocks)
 {
-    if (ln.wl_cap >= nblocks) return DCT_CUDA_OK;
+    // K1 appends to one segment per warp of its grid, each sized for all the blocks that warp visits, so the
+    // worklist holds nblocks entries plus up to 64 of slack per segment
+    const size_t want = nblocks + (size_t)kMaxWorklistSegments * 64;
+    if (ln.wl_cap >= want) return DCT_CUDA_OK;
     if (ln.d_wl) {
         CU_TRY(cudaStreamSynchronize(ln.stream));
         CU_TRY(cudaDeviceSynchronize());
@@ -184,10 +187,15 @@ int ensure_worklist(Lane &ln, size_t nblocks)
         ln.d_wl = nullptr, ln.d_side = nullptr;
         ln.wl_cap = 0, ln.side_cap = 0;
     }
-    CU_TRY(cudaMalloc(&ln.d_wl, nblocks * sizeof(uint32_t)));
-    ln.wl_cap = (uint32_t)nblocks;
-    // room for the pixels of one block in eight (uniform noise at q50 flags 2.7 %); later slots fall back to the plane
-    const size_t side = nblocks / 8 + 1024;
+    if (!ln.d_seg_count) {
+        CU_TRY(cudaMalloc(&ln.d_seg_count, kMaxWorklistSegments * sizeof(uint32_t)));
+        CU_TRY(cudaMemset(ln.d_seg_count, 0, kMaxWorklistSegments * sizeof(uint32_t)));
+    }
+    CU_TRY(cudaMalloc(&ln.d_wl, want * sizeof(uint32_t)));
+    ln.wl_cap = (uint32_t)want;
+    // room for the pixels of one block in eight (uniform noise at q50 flags 2.7 %), divided among the segments
+    // like the worklist; entries beyond a segment's share fall back to the plane
+    const size_t side = nblocks / 8 + (size_t)kMaxWorklistSegments * 32;
     CU_TRY(cudaMalloc(&ln.d_side, side * 64));
     ln.side_cap = (uint32_t)side;
     return DCT_CUDA_OK;
@@ -270,6 +278,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
         fp.uniform_band = p->uniform_band;
         fp.side = use_side ? ln.d_side : nullptr;
         fp.side_cap = use_side ? ln.side_cap : 0;
+        fp.seg_count = ln.d_seg_count;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (p->profile) {
             CU_TRY(cudaEventCreate(&e0));
@@ -277,8 +286,12 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
             CU_TRY(cudaEventRecord(e0, s));
         }
         unsigned k1_launches = 1;
-        if (elem == 4) CU_TRY(launch_fwd_quant_f32(fp, layout, s));
-        else CU_TRY(launch_fwd_quant_u8(fp, layout, p->adaptive, s, &k1_launches));
+        if (elem == 4) {
+            CU_TRY(launch_fwd_quant_f32(fp, layout, s));
+        } else {
+            CU_TRY(launch_fwd_quant_u8(fp, layout, p->adaptive, s, &k1_launches, &rp.seg));
+            rp.seg_count = ln.d_seg_count;
+        }
         p->launches += k1_launches;
         if (p->profile) {
             CU_TRY(cudaEventRecord(e1, s));
@@ -481,6 +494,7 @@ extern "C" void dct_cuda_plan_destroy(dct_cuda_plan *p)
         if (ln.d_ctr) cudaFree(ln.d_ctr);
         if (ln.d_wl) cudaFree(ln.d_wl);
         if (ln.d_side) cudaFree(ln.d_side);
+        if (ln.d_seg_count) cudaFree(ln.d_seg_count);
         if (ln.d_px) cudaFree(ln.d_px);
         if (ln.d_coef) cudaFree(ln.d_coef);
         if (ln.d_var) cudaFree(ln.d_var);
