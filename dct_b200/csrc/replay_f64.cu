@@ -312,19 +312,32 @@ __global__ void __launch_bounds__(kLaneThreads, 4) k_replay_fwd_lane(const Repla
     // in the segment s with prefix[s] <= e < prefix[s + 1].  Every CTA builds the prefix sums for itself.
     const unsigned n_segs = p.seg.n_segs;
     {
+        // counts -> shared memory (coalesced), per-thread sums of contiguous chunks, block-wide scan of the 128 sums,
+        // then every thread turns its chunk into exclusive prefixes in place
+        for (unsigned i = threadIdx.x; i < n_segs; i += kLaneThreads) sh.prefix[i] = p.seg_count[i];
+        __syncthreads();
         const unsigned per = (n_segs + kLaneThreads - 1) / kLaneThreads, first = threadIdx.x * per;
+        const unsigned last = first + per < n_segs ? first + per : n_segs;
         unsigned sum = 0;
-        for (unsigned i = first; i < first + per && i < n_segs; ++i) sum += p.seg_count[i];
-        sh.prefix[kMaxWorklistSegments - kLaneThreads + threadIdx.x] = sum;   // parked at the far end, consumed below
-        __syncthreads();
-        unsigned base = 0;
-        for (unsigned t = 0; t < threadIdx.x; ++t) base += sh.prefix[kMaxWorklistSegments - kLaneThreads + t];
-        __syncthreads();
-        for (unsigned i = first; i < first + per && i < n_segs; ++i) {
-            sh.prefix[i] = base;
-            base += p.seg_count[i];
+        for (unsigned i = first; i < last; ++i) sum += sh.prefix[i];
+        unsigned incl = sum;                              // inclusive scan over the CTA's 128 threads
+        const int ln_ = threadIdx.x & 31, wp_ = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (ln_ >= d) incl += v;
         }
-        if (first + per >= n_segs && first <= n_segs) sh.prefix[n_segs] = base;   // exactly one thread ends at n_segs
+        __shared__ unsigned warp_tot[kLaneWarps];
+        if (ln_ == 31) warp_tot[wp_] = incl;
+        __syncthreads();
+        unsigned base = incl - sum;
+        for (int w = 0; w < wp_; ++w) base += warp_tot[w];
+        for (unsigned i = first; i < last; ++i) {
+            const unsigned c = sh.prefix[i];
+            sh.prefix[i] = base;
+            base += c;
+        }
+        if (threadIdx.x == kLaneThreads - 1) sh.prefix[n_segs] = base;   // the last thread's running sum is the total
         __syncthreads();
     }
     const unsigned count = sh.prefix[n_segs];
