@@ -750,7 +750,10 @@ __global__ void k_block_dequantize_f64(int n, const double *R, int adaptive, dou
 static unsigned replay_grid(const ReplayParams &p)
 {
     // worklist mode: the count lives on the device; a fixed grid (4 CTAs per SM) strides over it
-    if (p.worklist != nullptr) return 148 * 4;
+    if (p.worklist != nullptr) {                         // small planes: no point in 592 CTAs that only set up and leave
+        const unsigned ctas = (p.nblocks + 2047) / 2048;
+        return ctas < 16u ? 16u : (ctas > 148u * 4u ? 148u * 4u : ctas);
+    }
     const unsigned ctas = (p.nblocks + kReplayThreads / 8 - 1) / (kReplayThreads / 8);
     return ctas < 148u * 8u ? (ctas ? ctas : 1u) : 148u * 8u;
 }
@@ -764,8 +767,11 @@ template <typename K> static cudaError_t launch_replay(K kernel, const ReplayPar
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s)
 {
     if (!p.px_is_f32 && p.worklist != nullptr && p.seg_count != nullptr) {      // uint8 planes on the fast path: one lane per flagged block
-        if (p.layout == LAYOUT_ZIGZAG) k_replay_fwd_lane<LAYOUT_ZIGZAG><<<148 * 4, kLaneThreads, 0, s>>>(p);
-        else k_replay_fwd_lane<LAYOUT_NATURAL><<<148 * 4, kLaneThreads, 0, s>>>(p);
+        // one CTA per ~1024 blocks of the plane (a tenth of them flagged would keep its four warps busy), at most 4 per SM
+        unsigned grid = (p.nblocks + 1023) / 1024;
+        grid = grid < 16u ? 16u : (grid > 148u * 4u ? 148u * 4u : grid);
+        if (p.layout == LAYOUT_ZIGZAG) k_replay_fwd_lane<LAYOUT_ZIGZAG><<<grid, kLaneThreads, 0, s>>>(p);
+        else k_replay_fwd_lane<LAYOUT_NATURAL><<<grid, kLaneThreads, 0, s>>>(p);
         return cudaGetLastError();
     }
     if (p.px_is_f32)
