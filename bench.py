@@ -14,8 +14,7 @@ power cap within a 100-step region: 128 frames 1 692, 256 frames 1 698 Gpixel/s 
 `e2e` is the same metric through the host-plane calls with PINNED HOST buffers, the H2D and D2H
 copies inside the timed region.  `roofline` is for K1 (the dominant kernel): 192 algorithmic bytes
 per 8x8 block (64 B of pixels in, 128 B of records out) over the K1 phase's own
-CUDA-event time (the library cuts a plane of more than ~12 M blocks into several K1 + K3 passes; their
-K1 times are summed and the bytes are the whole plane's), against the measured copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` times
+CUDA-event time, against the measured copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` times
 the reference's own C code (oracle/_ref, else the oracle port) on this box's host cores.
 
 Multi-GPU: every rank owns its own batch (weak scaling), no data-path collective; torch.distributed
@@ -358,7 +357,7 @@ def main():
 
     # ---- roofline of the dominant kernel (K1) -----------------------------------------------------
     peak, peak_src = measured_peak()
-    k1_ms = prof["fwd_ms"] / max(args.steps, 1)        # K1 time per step (planes beyond 12 M blocks take several launches)
+    k1_ms = prof["fwd_ms"] / max(args.steps, 1)        # K1 time per step
     k2_ms = prof["inv_ms"] / max(args.steps, 1)
     alg_bytes = 192.0 * nblocks
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9

@@ -91,8 +91,7 @@ dct_cuda_plan *dct_cuda_plan_create(const DCTContext *dct, const QuantContext *q
 int dct_cuda_plan_refresh(dct_cuda_plan *plan);
 void dct_cuda_plan_destroy(dct_cuda_plan *plan);
 int dct_cuda_plan_device(const dct_cuda_plan *plan);
-/* Kernels launched for this plan so far (fused kernels, replays, record conversions).  Planes beyond ~12 M blocks
- * are cut into several launches of the forward kernel, so this is not simply 2 per call. */
+/* Kernels launched for this plan so far (fused kernels, replays, record conversions). */
 uint64_t dct_cuda_plan_kernel_launches(const dct_cuda_plan *plan);
 
 /* ---- device-resident planes: all data pointers are device pointers on the plan's GPU; the work
