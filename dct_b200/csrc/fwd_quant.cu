@@ -337,17 +337,10 @@ static int sm_count()
 template <typename K>
 static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
 {
-    // function attributes are per device and sticky: set them once per (instantiation, device), not per launch
-    static bool configured[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     static int per_sm = 0;   // resident CTAs per SM for this instantiation (3 by design: registers and shared memory)
     if (per_sm == 0) {
         int n = 0;
@@ -370,7 +363,12 @@ static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t 
     const unsigned tiles_per_warp = (ntiles + n_segs - 1) / n_segs;
     q.seg_cap = p.wl_cap / n_segs;
     q.side_seg_cap = p.side ? p.side_cap / n_segs : 0;
-    if (n_segs > kMaxWorklistSegments - 128 || q.seg_cap < tiles_per_warp * 32 || p.seg_count == nullptr) return cudaErrorInvalidValue;
+    if (n_segs > kMaxWorklistSegments - 128 || q.seg_cap < tiles_per_warp * 32 || p.seg_count == nullptr) {
+        if (getenv("DCT_CUDA_DEBUG"))
+            fprintf(stderr, "libdct_cuda: K1 worklist segments: n_segs %u seg_cap %u tiles/warp %u wl_cap %u seg_count %p\n", n_segs, q.seg_cap,
+                    tiles_per_warp, p.wl_cap, (void *)p.seg_count);
+        return cudaErrorInvalidValue;
+    }
     if (segments) *segments = WorklistSegments{n_segs, q.seg_cap, q.side_seg_cap};
     kernel<<<grid, kThreads, kSmemBytes, s>>>(q);
     if (launches) ++*launches;
