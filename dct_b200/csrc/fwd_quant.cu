@@ -337,6 +337,9 @@ static int sm_count()
 template <typename K>
 static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
 {
+    // NB: K is the same function-pointer type for every kernel variant, so this template has ONE instance and its
+    // statics are shared by all variants: nothing per-kernel may be cached here (the attributes are set on every launch;
+    // per_sm is the same for all variants: identical launch bounds and shared memory).
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
