@@ -39,7 +39,7 @@ int fail(int code, const char *fmt, ...);
 // plan
 // ------------------------------------------------------------------------------------------
 constexpr int kLanes = 3;                       // depth of the host-plane pipeline
-constexpr size_t kStripPixels = 16u << 20;      // ~16 Mpx per strip
+constexpr size_t kStripPixels = 32u << 20;      // ~32 Mpx per strip (measured: 16 -> 32 Mpx is +4 % on two overlapped plans, -1 % on one)
 
 struct Lane {
     cudaStream_t stream = nullptr;

@@ -640,7 +640,8 @@ static int strip_rows(int W, int H, int n = 8)
 {
     const size_t bw = (size_t)W / n;
     if (bw == 0 || H == 0) return 0;
-    size_t rows = std::max<size_t>(1, kStripPixels / (bw * n * n));         // block rows per strip
+    static const size_t strip_px = getenv("DCT_CUDA_STRIP_MPX") ? (size_t)atol(getenv("DCT_CUDA_STRIP_MPX")) << 20 : kStripPixels;   // tuning aid
+    size_t rows = std::max<size_t>(1, strip_px / (bw * n * n));             // block rows per strip
     const size_t total = (size_t)H / n;
     // at least kLanes strips when the plane is big enough to be worth overlapping
     if (total >= (size_t)kLanes * 4) rows = std::min(rows, (total + kLanes - 1) / kLanes);
