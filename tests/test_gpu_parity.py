@@ -128,6 +128,15 @@ def test_c_host_program_roundtrip():
     assert r.returncode == 0 and "C ROUNDTRIP PASSED" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "c_frames")),
+                    reason="examples/c_frames.c not built (make -C oracle dropin)")
+def test_c_host_program_frames():
+    """examples/c_frames.c: ragged planes, int8 records and RGB frames driven from plain C99."""
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "c_frames")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 mismatches" in r.stdout
+
+
 # ---------------------------------------------------------------------------------------------
 # planes: golden fixtures and oracle comparisons
 # ---------------------------------------------------------------------------------------------
