@@ -147,3 +147,27 @@ def test_band_tables_are_current():
     m.emit(tmp)
     assert open(tmp).read() == open(os.path.join(ROOT, "dct_b200", "csrc", "band_tables.h")).read()
     m.check(nblocks=2000)
+
+
+def test_frame420_geometry_is_pure_host_arithmetic():
+    """dct_cuda_frame420_geometry needs no GPU: plane sizes rounded up to whole 8x8 blocks (include/dct_cuda.h)."""
+    from dct_b200 import api
+    for w, h, want in ((3840, 2160, (3840, 2160, 1920, 1080)), (1919, 1081, (1920, 1088, 960, 544)),
+                       (1, 1, (8, 8, 8, 8)), (17, 8, (24, 8, 16, 8)), (7680, 4320, (7680, 4320, 3840, 2160))):
+        g = api.frame420_geometry(w, h)
+        assert (g.width, g.height) == (w, h)
+        assert (g.y_width, g.y_height, g.c_width, g.c_height) == want
+    assert api._peer_share(None, 8, 1) == 0.0          # no plan, no share
+
+
+def test_no_cuda_device_means_errors_not_fallbacks():
+    """Without a GPU every plan-level entry point reports DCT_CUDA_ENODEV / EINVAL; nothing computes on the CPU."""
+    from dct_b200 import api
+    if api.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    d, q = api.dct_init(8), api.quant_init(8, 50, 0)
+    try:
+        with pytest.raises(api.DctCudaError, match="no CUDA device"):
+            api.Plan(d, q, 0)
+    finally:
+        api.dct_free(d), api.quant_free(q)
