@@ -56,11 +56,6 @@ __device__ __forceinline__ uint32_t pack_b3(uint32_t a, uint32_t b, uint32_t c, 
 {
     return __byte_perm(__byte_perm(a, b, 0x0073), __byte_perm(c, d, 0x0073), 0x5410);
 }
-__device__ __forceinline__ uint32_t pack_b0(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
-}
-
 // channel c of pixel p (0..15) of a 48-byte group held in 12 words
 template <int P, int C> __device__ __forceinline__ uint32_t channel(const uint32_t (&w)[12])
 {
@@ -170,29 +165,46 @@ __global__ void __launch_bounds__(kTX * kTY) k_ycbcr420_to_rgb(PlanarParams p)
         const uint2 crv = __ldg(reinterpret_cast<const uint2 *>(p.cr + co));
         const uint32_t yaw[4] = {ya.x, ya.y, ya.z, ya.w}, ybw[4] = {yb.x, yb.y, yb.z, yb.w};
         const uint32_t cbw[2] = {cbv.x, cbv.y}, crw[2] = {crv.x, crv.y};
-        uint32_t oa[48], ob[48];   // one byte value per entry, packed below
-        ChromaTerms t[8];
-        static_for<0, 8>([&](auto C) {
-            constexpr int c = decltype(C)::value;
-            t[c] = chroma_terms((int)byte_of(cbw[c >> 2], c & 3), (int)byte_of(crw[c >> 2], c & 3));
-        });
-        static_for<0, 16>([&](auto P) {
-            constexpr int px = decltype(P)::value, c = px >> 1;
-            const int la = (int)byte_of(yaw[px >> 2], px & 3), lb = (int)byte_of(ybw[px >> 2], px & 3);
-            oa[3 * px] = clamp255(la + t[c].r), oa[3 * px + 1] = clamp255(la + t[c].g), oa[3 * px + 2] = clamp255(la + t[c].b);
-            ob[3 * px] = clamp255(lb + t[c].r), ob[3 * px + 1] = clamp255(lb + t[c].g), ob[3 * px + 2] = clamp255(lb + t[c].b);
+        // Packed int16 arithmetic: the two pixels of a 2x2 cell's row share their chroma terms, so one VIADD.16x2 adds
+        // the term to both luma samples and one VIMNMX.S16x2.RELU clamps both to [0, 255] (three scalar operations per
+        // component before).  Per cell and row: r2 = (R0, R1), g2, b2 as int16 pairs -> the six bytes R0 G0 B0 R1 G1 B1.
+        uint32_t wa[12], wb[12];                   // the 48 output bytes of each row
+        static_for<0, 4>([&](auto Q4) {
+            constexpr int qd = decltype(Q4)::value;            // four pixels = two cells = three output words
+            uint32_t rga[2], ba[2], rgb_[2], bb[2];            // per cell: (R0 G0 R1 G1) and (B0 . B1 .) bytes, rows a and b
+            static_for<0, 2>([&](auto H2) {
+                constexpr int h = decltype(H2)::value, c = 2 * qd + h;                 // chroma sample / cell index
+                const ChromaTerms t = chroma_terms((int)byte_of(cbw[c >> 2], c & 3), (int)byte_of(crw[c >> 2], c & 3));
+                const uint32_t tr = __byte_perm((uint32_t)t.r, 0u, 0x1010), tg = __byte_perm((uint32_t)t.g, 0u, 0x1010),
+                               tb = __byte_perm((uint32_t)t.b, 0u, 0x1010);           // (term, term) as int16 pairs
+                // luma pair of this cell: bytes (2c, 2c+1) of the row -> zero-extended int16 pair
+                constexpr int sel = ((2 * c) & 3) == 0 ? 0x4140 : 0x4342;
+                const uint32_t la = __byte_perm(yaw[(2 * c) >> 2], 0u, sel), lb = __byte_perm(ybw[(2 * c) >> 2], 0u, sel);
+                auto add_clamp = [](uint32_t l2, uint32_t t2) {
+                    uint32_t r;
+                    asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(l2), "r"(t2));
+                    asm("min.s16x2.relu %0, %0, %1;" : "+r"(r) : "r"(0x00ff00ffu));
+                    return r;
+                };
+                const uint32_t ra2 = add_clamp(la, tr), ga2 = add_clamp(la, tg), ba2 = add_clamp(la, tb);
+                const uint32_t rb2 = add_clamp(lb, tr), gb2 = add_clamp(lb, tg), bb2 = add_clamp(lb, tb);
+                rga[h] = __byte_perm(ra2, ga2, 0x6240);        // R0 G0 R1 G1
+                rgb_[h] = __byte_perm(rb2, gb2, 0x6240);
+                ba[h] = ba2, bb[h] = bb2;                      // B0 at byte 0, B1 at byte 2
+            });
+            // bytes: R0 G0 B0 R1 | G1 B1 R0' G0' | B0' R1' G1' B1'
+            wa[3 * qd] = __byte_perm(rga[0], ba[0], 0x2410);
+            wa[3 * qd + 1] = __byte_perm(__byte_perm(rga[0], ba[0], 0x0063), rga[1], 0x5410);
+            wa[3 * qd + 2] = __byte_perm(rga[1], ba[1], 0x6324);
+            wb[3 * qd] = __byte_perm(rgb_[0], bb[0], 0x2410);
+            wb[3 * qd + 1] = __byte_perm(__byte_perm(rgb_[0], bb[0], 0x0063), rgb_[1], 0x5410);
+            wb[3 * qd + 2] = __byte_perm(rgb_[1], bb[1], 0x6324);
         });
         uint4 ua[3], ub[3];
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
-            ua[v].x = pack_b0(oa[16 * v], oa[16 * v + 1], oa[16 * v + 2], oa[16 * v + 3]);
-            ua[v].y = pack_b0(oa[16 * v + 4], oa[16 * v + 5], oa[16 * v + 6], oa[16 * v + 7]);
-            ua[v].z = pack_b0(oa[16 * v + 8], oa[16 * v + 9], oa[16 * v + 10], oa[16 * v + 11]);
-            ua[v].w = pack_b0(oa[16 * v + 12], oa[16 * v + 13], oa[16 * v + 14], oa[16 * v + 15]);
-            ub[v].x = pack_b0(ob[16 * v], ob[16 * v + 1], ob[16 * v + 2], ob[16 * v + 3]);
-            ub[v].y = pack_b0(ob[16 * v + 4], ob[16 * v + 5], ob[16 * v + 6], ob[16 * v + 7]);
-            ub[v].z = pack_b0(ob[16 * v + 8], ob[16 * v + 9], ob[16 * v + 10], ob[16 * v + 11]);
-            ub[v].w = pack_b0(ob[16 * v + 12], ob[16 * v + 13], ob[16 * v + 14], ob[16 * v + 15]);
+            ua[v] = make_uint4(wa[4 * v], wa[4 * v + 1], wa[4 * v + 2], wa[4 * v + 3]);
+            ub[v] = make_uint4(wb[4 * v], wb[4 * v + 1], wb[4 * v + 2], wb[4 * v + 3]);
         }
         // A thread's 48 bytes are 48 bytes apart from its neighbour's: written directly, every STG.128 of the
         // warp would touch 32 half-filled sectors.  When the whole warp is on this path the two rows go through
