@@ -11,8 +11,12 @@
 // 256-pixel x 8-row tile with 8 STG.64 per lane (256 contiguous bytes per warp instruction).
 // Both butterfly passes and the pixel residuals run on packed fp32 instructions (FADD2 / FFMA2).
 // The fp32 error bound is dynamic here (inputs are arbitrary int16): 2^-24 * sum gain_k |v_k|.
+#include <cstdio>
+#include <cstdlib>
+
 #include "fast_core.cuh"
 #include "kernels.cuh"
+#include "tma.cuh"
 
 namespace dctb {
 
@@ -38,42 +42,11 @@ __device__ __forceinline__ void stg_stream_u2(void *p, uint32_t a, uint32_t b)
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
 
+// The arithmetic of one block, shared by the one-shot and the bulk-tensor kernels: w[m] = packed int16 pair m of the
+// record in storage order; writes the block's 64 pixels (if valid); returns "replay this block in fp64".
 template <int LAYOUT, bool ADAPTIVE>
-__global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8(const __grid_constant__ InvParams p)
+__device__ __forceinline__ bool inv_block(const InvParams &p, const uint32_t (&w)[32], bool valid, uint32_t b, uint8_t *dst)
 {
-    __shared__ uint4 stage[kWarps * kStageWordsPerWarp / 4];
-
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t warp_base = blockIdx.x * kThreads + warp * 32;
-    const uint32_t b = warp_base + lane;
-    const bool valid = b < p.nblocks;
-
-    // 4 KB of records: coalesced 16-byte chunks -> padded stage -> one record per lane
-    uint32_t *wstage = reinterpret_cast<uint32_t *>(stage) + warp * kStageWordsPerWarp;
-    const uint4 *srcv = reinterpret_cast<const uint4 *>(p.coef) + (size_t)warp_base * 8;
-    uint4 chunk[8];
-    const uint32_t full = warp_base < p.nblocks ? p.nblocks - warp_base : 0;   // records in this tile
-    if (full >= 32) {                                   // warp-uniform: every tile but possibly the last
-#pragma unroll
-        for (int j = 0; j < 8; ++j) chunk[j] = ldg_stream_u4(srcv + j * 32 + lane);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            chunk[j] = (j * 4 + (lane >> 3) < full) ? ldg_stream_u4(srcv + j * 32 + lane) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t c = j * 32 + lane;
-        *reinterpret_cast<uint4 *>(wstage + (c >> 3) * kStageWordsPerBlock + 4 * (c & 7)) = chunk[j];
-    }
-    __syncwarp();
-    uint32_t w[32];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint4 t = *reinterpret_cast<const uint4 *>(wstage + lane * kStageWordsPerBlock + 4 * j);
-        w[4 * j] = t.x, w[4 * j + 1] = t.y, w[4 * j + 2] = t.z, w[4 * j + 3] = t.w;
-    }
-
     float s = 1.0f;
     if constexpr (ADAPTIVE) {
         // multiplier 1/((1/Q)*(1/(2-nv))) = Q*(2-nv) up to fp64 rounding; exact form in K3
@@ -120,10 +93,6 @@ __global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8(const __grid_co
         else idct8_dequant<float2, 1>(cpv[c], p.ma[c], p.mb[c]);
     }
 
-    const uint32_t bb = valid ? b : p.nblocks - 1;
-    const uint32_t by = bb / p.bw, bx = bb - by * p.bw;
-    uint8_t *dst = p.px + (long long)by * 8 * p.pitch + (long long)bx * 8;
-
     // Row pass on row pairs (2a, 2a+1), then per pixel: t = x + (1.5*2^23 + 128): the low 16 mantissa bits
     // of t are round(x) + 128 as an int16 (valid for |x| < 2^15 - 128, guaranteed below by the bound test);
     // residual e = x - round(x) is exact.  Clamp to [0, 255] on packed int16 pairs (VIMNMX.S16x2.RELU),
@@ -167,6 +136,49 @@ __global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8(const __grid_co
     // keeps |x| far below 2^15; larger inputs go to the fp64 path
     const bool flag = (emax >= thr) | !(bound < 1.4e5f);
 
+    return flag;
+}
+
+template <int LAYOUT, bool ADAPTIVE>
+__global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8(const __grid_constant__ InvParams p)
+{
+    __shared__ uint4 stage[kWarps * kStageWordsPerWarp / 4];
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warp_base = blockIdx.x * kThreads + warp * 32;
+    const uint32_t b = warp_base + lane;
+    const bool valid = b < p.nblocks;
+
+    // 4 KB of records: coalesced 16-byte chunks -> padded stage -> one record per lane
+    uint32_t *wstage = reinterpret_cast<uint32_t *>(stage) + warp * kStageWordsPerWarp;
+    const uint4 *srcv = reinterpret_cast<const uint4 *>(p.coef) + (size_t)warp_base * 8;
+    uint4 chunk[8];
+    const uint32_t full = warp_base < p.nblocks ? p.nblocks - warp_base : 0;   // records in this tile
+    if (full >= 32) {                                   // warp-uniform: every tile but possibly the last
+#pragma unroll
+        for (int j = 0; j < 8; ++j) chunk[j] = ldg_stream_u4(srcv + j * 32 + lane);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            chunk[j] = (j * 4 + (lane >> 3) < full) ? ldg_stream_u4(srcv + j * 32 + lane) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t c = j * 32 + lane;
+        *reinterpret_cast<uint4 *>(wstage + (c >> 3) * kStageWordsPerBlock + 4 * (c & 7)) = chunk[j];
+    }
+    __syncwarp();
+    uint32_t w[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint4 t = *reinterpret_cast<const uint4 *>(wstage + lane * kStageWordsPerBlock + 4 * j);
+        w[4 * j] = t.x, w[4 * j + 1] = t.y, w[4 * j + 2] = t.z, w[4 * j + 3] = t.w;
+    }
+
+    const uint32_t bb = valid ? b : p.nblocks - 1;
+    const uint32_t by = bb / p.bw, bx = bb - by * p.bw;
+    const bool flag = inv_block<LAYOUT, ADAPTIVE>(p, w, valid, b, p.px + (long long)by * 8 * p.pitch + (long long)bx * 8);
+
     const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
     if (ballot != 0) {
         const int leader = __ffs(ballot) - 1;
@@ -180,6 +192,101 @@ __global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8(const __grid_co
     }
 }
 
+
+
+// ------------------------------------------------------------------------------------------
+// K2 with bulk-tensor (TMA) record tiles -- the default whenever the plane allows it (16-byte aligned records,
+// block rows of at least 32 blocks).  Same arithmetic as k_dequant_idct_u8 above (inv_block); what changes:
+//   * persistent grid, every warp runs its own two-stage pipeline: lane 0 fetches the 4 KB of the next tile's 32 records
+//     with ONE cp.async.bulk.tensor.2d (128-byte swizzle: a lane then reads its own record with 8 conflict-free LDS.128)
+//     while the warp transforms the current tile; no LDG / STS re-staging pass, no address arithmetic per chunk;
+//   * a tile is 32 blocks of ONE block row, so the pixel address of a lane is a warp-uniform base + 8 * lane;
+//   * flagged blocks go to the warp's own worklist segment (as in K1): no global atomic, which matters when a
+//     high-quality table makes the dynamic band flag every other tile.
+// ------------------------------------------------------------------------------------------
+struct alignas(64) InvTmaParams {
+    CUtensorMap map_rec;       // records, box 128 B x 32, 128-byte swizzle
+    InvParams f;
+    uint32_t tpr;              // tiles per block row = ceil(bw / 32)
+    uint32_t nby;              // block rows
+    uint32_t step_ty, step_tx; // divmod(warps in the grid, tpr)
+    uint32_t *seg_count;       // one entry per warp of the grid
+    uint32_t seg_cap;          // worklist entries per segment
+};
+
+constexpr int kInStages = 2;
+constexpr int kTmaInBytes = 4096;
+constexpr int kTmaSmemBytes = 1024 /* alignment slack */ + kWarps * kInStages * kTmaInBytes + kWarps * 32;
+
+template <int LAYOUT, bool ADAPTIVE>
+__global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8_tma(const __grid_constant__ InvTmaParams P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const InvParams &p = P.f;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // tells the compiler it is warp-uniform
+    uint8_t *sm = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+    uint8_t *in_p = sm + warp * (kInStages * kTmaInBytes);
+    uint32_t *ctl_p = reinterpret_cast<uint32_t *>(sm + kWarps * kInStages * kTmaInBytes + warp * 32);
+    const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in_p);
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(ctl_p);           // two 8-byte mbarriers
+
+    if (lane == 0) {
+        tma::mbar_init(bar_s, 1);
+        tma::mbar_init(bar_s + 8, 1);
+        tma::fence_barrier_init();
+    }
+    __syncwarp();
+
+    uint32_t ty, tx;            // block row and tile-in-row of the next tile to fetch
+    {
+        const uint32_t t = blockIdx.x * kWarps + warp;
+        ty = t / P.tpr;
+        tx = t - ty * P.tpr;
+    }
+    auto issue = [&](uint32_t stage) {
+        if (lane == 0) {
+            tma::mbar_expect_tx(bar_s + stage * 8, kTmaInBytes);
+            tma::load_2d(in_s + stage * kTmaInBytes, &P.map_rec, 0, (int)(ty * p.bw + tx * 32), bar_s + stage * 8);
+        }
+    };
+    if (ty < P.nby) issue(0);
+    const uint32_t swz = (lane & 7) << 4;
+    uint32_t wl_n = 0;          // entries this warp has appended to its worklist segment
+    const uint32_t gwarp = blockIdx.x * kWarps + warp;
+
+    for (uint32_t it = 0; ty < P.nby; ++it) {
+        const uint32_t stage = it & 1;
+        const uint32_t bx0 = tx * 32;
+        const uint32_t warp_base = ty * p.bw + bx0;
+        const uint32_t nvalid = min(32u, p.bw - bx0);
+        uint8_t *dst = p.px + (long long)ty * 8 * p.pitch + (long long)(bx0 + lane) * 8;
+        tx += P.step_tx;
+        ty += P.step_ty;
+        if (tx >= P.tpr) tx -= P.tpr, ++ty;
+        if (ty < P.nby) issue(stage ^ 1);
+        tma::mbar_wait(bar_s + stage * 8, (it >> 1) & 1);
+
+        const uint32_t b = warp_base + lane;
+        const bool valid = lane < nvalid;
+        const uint8_t *rec = in_p + stage * kTmaInBytes + lane * 128;
+        uint32_t w[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 t = *reinterpret_cast<const uint4 *>(rec + ((j << 4) ^ swz));
+            w[4 * j] = t.x, w[4 * j + 1] = t.y, w[4 * j + 2] = t.z, w[4 * j + 3] = t.w;
+        }
+        __syncwarp();           // every lane has its record: the fetch after next may overwrite this stage
+
+        const bool flag = inv_block<LAYOUT, ADAPTIVE>(p, w, valid, b, dst);
+        const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
+        if (ballot != 0) {
+            if (flag && valid) p.worklist[(size_t)gwarp * P.seg_cap + wl_n + __popc(ballot & ((1u << lane) - 1u))] = b;
+            wl_n += __popc(ballot);
+        }
+    }
+    if (lane == 0) P.seg_count[gwarp] = wl_n;     // <= 32 per tile visited, < seg_cap by construction
+}
 
 // ------------------------------------------------------------------------------------------
 // fp64 variant: same mapping, the butterfly in double precision.  Used for ADAPTIVE plans, whose
@@ -294,9 +401,69 @@ cudaError_t launch_dequant_idct_u8_f64(const InvParams &p, const ExactTables *d_
     return cudaGetLastError();
 }
 
-cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s)
+static int sm_count_k2()
 {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    return n;
+}
+
+template <typename K>
+static cudaError_t launch_persistent_tma(K kernel, const InvParams &p, cudaStream_t s, WorklistSegments *segments)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    static int per_sm = 0;   // same for every variant: identical launch bounds and shared memory
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, kTmaSmemBytes) != cudaSuccess || n < 1) n = 1;
+        per_sm = n;
+        if (getenv("DCT_CUDA_DEBUG")) fprintf(stderr, "libdct_cuda: K2 (bulk tensor): %d CTAs/SM, %d B smem\n", n, kTmaSmemBytes);
+    }
+    InvTmaParams q;
+    q.f = p;
+    q.nby = p.nblocks / p.bw;
+    q.tpr = (p.bw + 31) / 32;
+    const unsigned ntiles = q.nby * q.tpr;
+    const unsigned resident = (unsigned)sm_count_k2() * (unsigned)per_sm;
+    const unsigned want = (ntiles + kWarps - 1) / kWarps;
+    const unsigned grid = want < resident ? want : resident;
+    const unsigned n_segs = grid * kWarps;
+    q.step_ty = n_segs / q.tpr;
+    q.step_tx = n_segs - q.step_ty * q.tpr;
+    const unsigned tiles_per_warp = (ntiles + n_segs - 1) / n_segs;
+    q.seg_cap = p.wl_cap / n_segs;
+    q.seg_count = p.seg_count;
+    if (n_segs > kMaxWorklistSegments - 128 || q.seg_cap < tiles_per_warp * 32 || p.seg_count == nullptr) return cudaErrorInvalidValue;
+    if ((e = make_record_map(&q.map_rec, p.coef, p.nblocks, 32)) != cudaSuccess) return e;
+    if (segments) *segments = WorklistSegments{n_segs, q.seg_cap, 0};
+    kernel<<<grid, kThreads, kTmaSmemBytes, s>>>(q);
+    return cudaGetLastError();
+}
+
+static bool tma_eligible(const InvParams &p)
+{
+    static const bool disabled = getenv("DCT_CUDA_NO_TMA") != nullptr;   // measurement aid: force the one-shot kernels
+    if (disabled || p.no_tma || !tma_available() || p.seg_count == nullptr) return false;
+    if (p.bw < 32 || ((uintptr_t)p.coef % 16)) return false;
+    const unsigned long long padded = (unsigned long long)(p.nblocks / p.bw) * ((p.bw + 31) / 32) * 32;
+    return padded + (unsigned long long)kMaxWorklistSegments * 64 <= p.wl_cap;
+}
+
+cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments)
+{
+    if (segments) *segments = WorklistSegments{0, 0, 0};
     if (p.nblocks == 0) return cudaSuccess;
+    if (tma_eligible(p)) {
+        if (layout == LAYOUT_ZIGZAG)
+            return adaptive ? launch_persistent_tma(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, true>, p, s, segments)
+                            : launch_persistent_tma(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, false>, p, s, segments);
+        return adaptive ? launch_persistent_tma(k_dequant_idct_u8_tma<LAYOUT_NATURAL, true>, p, s, segments)
+                        : launch_persistent_tma(k_dequant_idct_u8_tma<LAYOUT_NATURAL, false>, p, s, segments);
+    }
     const unsigned grid = (p.nblocks + kThreads - 1) / kThreads;
     if (layout == LAYOUT_ZIGZAG) {
         if (adaptive) k_dequant_idct_u8<LAYOUT_ZIGZAG, true><<<grid, kThreads, 0, s>>>(p);

@@ -24,6 +24,7 @@
 
 #include "fast_core.cuh"
 #include "kernels.cuh"
+#include "tma.cuh"
 
 namespace dctb {
 
@@ -52,6 +53,76 @@ __device__ __forceinline__ void stg_stream_u4(void *p, const uint4 &v)
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
                  "r"(v.z), "r"(v.w)
                  : "memory");
+}
+
+// The arithmetic of one block, shared by the cp.async and the bulk-tensor kernels: raw[i] = the 8 bytes of pixel
+// row i; w[m] = the packed int16 pair m of the record in storage order; returns "replay this block in fp64".
+template <int LAYOUT, bool ADAPTIVE, bool UNIFORM>
+__device__ __forceinline__ bool fwd_block(const FwdParams &p, const uint2 (&raw)[8], uint32_t (&w)[32], bool valid, uint32_t b)
+{
+    float inv_s = 1.0f;
+    if constexpr (ADAPTIVE) {
+        // Sum and sum of squares of the centred samples, as exact integers: packed byte dot products.
+        // 4096 * variance = 64 * sum(x^2) - sum(x)^2 is exact, so the side array equals
+        // calculate_block_variance (src/quantization.c:153-169) bit for bit.
+        int isum = 0, isq = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) row_moments(raw[i], isum, isq);
+        const int num = 64 * isq - isum * isum;   // 4096 * variance, exact (< 2^27)
+        if (p.var_out != nullptr && valid) p.var_out[b] = (double)num * (1.0 / 4096.0);
+        // s = 2 - clamp(var/1000, 0.1, 1)  (src/quantization.c:186-190), fp32 here, exact in K3
+        inv_s = adaptive_inv_scale(num);
+    }
+
+    // Rows (X * D^T), then columns (D * temp): same order as src/dct.c:57-74.  Both passes run on packed
+    // pairs (FADD2 / FFMA2: two fp32 lanes per instruction, half the issue slots).  The row pass takes rows
+    // a and 7-a in its two lanes -- exactly the pairs the first butterfly stage of the column pass adds and
+    // subtracts, so that stage is 64 scalar FADDs on the two halves of a register pair, whose results are
+    // written straight into (column 2b, column 2b+1) pairs: the 2x2 re-pairing costs no instruction.
+    float2 rp[4][8];                         // rp[a][k] = (T[a][k], T[7-a][k])
+#pragma unroll
+    for (int a = 0; a < 4; ++a) fdct8_rowpair_from_bytes(rp[a], raw[a], raw[7 - a]);
+    float2 cp[4][8];                         // cp[b][u] = scaled coefficients (u, 2b) and (u, 2b+1)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        float2 s[4], d[4];                   // s[a] = T[a] + T[7-a], d[a] = T[a] - T[7-a] for columns 2b, 2b+1
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            s[a] = make_float2(__fadd_rn(rp[a][2 * b].x, rp[a][2 * b].y), __fadd_rn(rp[a][2 * b + 1].x, rp[a][2 * b + 1].y));
+            d[a] = make_float2(__fsub_rn(rp[a][2 * b].x, rp[a][2 * b].y), __fsub_rn(rp[a][2 * b + 1].x, rp[a][2 * b + 1].y));
+        }
+        fdct8_tail<float2, 1>(cp[b], s[0], s[1], s[2], s[3], d[0], d[1], d[2], d[3]);
+    }
+
+    // Quantise in natural pairs (k, k+1) = cp[(k%8)/2][k/8]: t = c*r + 1.5*2^23 holds round(c*r) in its low
+    // mantissa bits; residual e = c*r - round(c*r) (one rounding); |e| >= 0.5 - band  => replay.
+    // t overwrites cp; the layout (natural / zigzag) is applied when the int16 halves are packed.
+    bool flag = false;
+    float emax = 0.0f;
+    static_for<0, 32>([&](auto M) {
+        constexpr int m = decltype(M)::value;      // natural pair: coefficients 2m, 2m+1
+        constexpr int u = m >> 2, b = m & 3;
+        float2 r2 = reinterpret_cast<const float2 *>(p.r)[m];
+        if constexpr (ADAPTIVE) {
+            if (m == 0) r2.y = __fmul_rn(r2.y, inv_s);       // DC keeps the unscaled table entry
+            else r2 = Ops<float2>::mul(r2, make_float2(inv_s, inv_s));
+        }
+        float2 t2, e2;
+        quant_residual2(cp[b][u], r2, t2, e2);
+        if constexpr (UNIFORM) emax = fmaxf(fmaxf(emax, fabsf(e2.x)), fabsf(e2.y));   // FMNMX3
+        else flag |= (fabsf(e2.x) >= p.thr[2 * m]) | (fabsf(e2.y) >= p.thr[2 * m + 1]);
+        cp[b][u] = t2;
+    });
+    static_for<0, 32>([&](auto M) {
+        constexpr int m = decltype(M)::value;      // storage pair
+        constexpr int k0 = storage_to_natural<LAYOUT>(2 * m), k1 = storage_to_natural<LAYOUT>(2 * m + 1);
+        const float2 a2 = cp[(k0 & 7) >> 1][k0 >> 3], b2 = cp[(k1 & 7) >> 1][k1 >> 3];
+        w[m] = __byte_perm(__float_as_uint((k0 & 1) ? a2.y : a2.x), __float_as_uint((k1 & 1) ? b2.y : b2.x), 0x5410);
+    });
+
+    if constexpr (UNIFORM) flag = emax >= p.thr_min;
+
+    return flag;
 }
 
 // UNIFORM: one band for all 64 coefficients (the widest), tested with 3-input max -- half the
@@ -115,68 +186,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
     for (int i = 0; i < 8; ++i)
         raw[i] = *reinterpret_cast<const uint2 *>(wsm + stage * kInWordsPerStage + i * 64 + lane * 2);
 
-    float inv_s = 1.0f;
-    if constexpr (ADAPTIVE) {
-        // Sum and sum of squares of the centred samples, as exact integers: packed byte dot products.
-        // 4096 * variance = 64 * sum(x^2) - sum(x)^2 is exact, so the side array equals
-        // calculate_block_variance (src/quantization.c:153-169) bit for bit.
-        int isum = 0, isq = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) row_moments(raw[i], isum, isq);
-        const int num = 64 * isq - isum * isum;   // 4096 * variance, exact (< 2^27)
-        if (p.var_out != nullptr && valid) p.var_out[b] = (double)num * (1.0 / 4096.0);
-        // s = 2 - clamp(var/1000, 0.1, 1)  (src/quantization.c:186-190), fp32 here, exact in K3
-        inv_s = adaptive_inv_scale(num);
-    }
-
-    // Rows (X * D^T), then columns (D * temp): same order as src/dct.c:57-74.  Both passes run on packed
-    // pairs (FADD2 / FFMA2: two fp32 lanes per instruction, half the issue slots).  The row pass takes rows
-    // a and 7-a in its two lanes -- exactly the pairs the first butterfly stage of the column pass adds and
-    // subtracts, so that stage is 64 scalar FADDs on the two halves of a register pair, whose results are
-    // written straight into (column 2b, column 2b+1) pairs: the 2x2 re-pairing costs no instruction.
-    float2 rp[4][8];                         // rp[a][k] = (T[a][k], T[7-a][k])
-#pragma unroll
-    for (int a = 0; a < 4; ++a) fdct8_rowpair_from_bytes(rp[a], raw[a], raw[7 - a]);
-    float2 cp[4][8];                         // cp[b][u] = scaled coefficients (u, 2b) and (u, 2b+1)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        float2 s[4], d[4];                   // s[a] = T[a] + T[7-a], d[a] = T[a] - T[7-a] for columns 2b, 2b+1
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            s[a] = make_float2(__fadd_rn(rp[a][2 * b].x, rp[a][2 * b].y), __fadd_rn(rp[a][2 * b + 1].x, rp[a][2 * b + 1].y));
-            d[a] = make_float2(__fsub_rn(rp[a][2 * b].x, rp[a][2 * b].y), __fsub_rn(rp[a][2 * b + 1].x, rp[a][2 * b + 1].y));
-        }
-        fdct8_tail<float2, 1>(cp[b], s[0], s[1], s[2], s[3], d[0], d[1], d[2], d[3]);
-    }
-
-    // Quantise in natural pairs (k, k+1) = cp[(k%8)/2][k/8]: t = c*r + 1.5*2^23 holds round(c*r) in its low
-    // mantissa bits; residual e = c*r - round(c*r) (one rounding); |e| >= 0.5 - band  => replay.
-    // t overwrites cp; the layout (natural / zigzag) is applied when the int16 halves are packed.
-    bool flag = false;
-    float emax = 0.0f;
-    static_for<0, 32>([&](auto M) {
-        constexpr int m = decltype(M)::value;      // natural pair: coefficients 2m, 2m+1
-        constexpr int u = m >> 2, b = m & 3;
-        float2 r2 = reinterpret_cast<const float2 *>(p.r)[m];
-        if constexpr (ADAPTIVE) {
-            if (m == 0) r2.y = __fmul_rn(r2.y, inv_s);       // DC keeps the unscaled table entry
-            else r2 = Ops<float2>::mul(r2, make_float2(inv_s, inv_s));
-        }
-        float2 t2, e2;
-        quant_residual2(cp[b][u], r2, t2, e2);
-        if constexpr (UNIFORM) emax = fmaxf(fmaxf(emax, fabsf(e2.x)), fabsf(e2.y));   // FMNMX3
-        else flag |= (fabsf(e2.x) >= p.thr[2 * m]) | (fabsf(e2.y) >= p.thr[2 * m + 1]);
-        cp[b][u] = t2;
-    });
     uint32_t w[32];
-    static_for<0, 32>([&](auto M) {
-        constexpr int m = decltype(M)::value;      // storage pair
-        constexpr int k0 = storage_to_natural<LAYOUT>(2 * m), k1 = storage_to_natural<LAYOUT>(2 * m + 1);
-        const float2 a2 = cp[(k0 & 7) >> 1][k0 >> 3], b2 = cp[(k1 & 7) >> 1][k1 >> 3];
-        w[m] = __byte_perm(__float_as_uint((k0 & 1) ? a2.y : a2.x), __float_as_uint((k1 & 1) ? b2.y : b2.x), 0x5410);
-    });
-
-    if constexpr (UNIFORM) flag = emax >= p.thr_min;
+    const bool flag = fwd_block<LAYOUT, ADAPTIVE, UNIFORM>(p, raw, w, valid, b);
 
     const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
 
@@ -229,6 +240,138 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8(const __grid_const
 
 #undef ntiles
 #undef tile_stride
+
+// ------------------------------------------------------------------------------------------
+// K1 with bulk-tensor (TMA) tile movement -- the default whenever the plane allows it (16-byte aligned base,
+// pitch a multiple of 16, at least 256 pixels wide).  Same mapping and arithmetic as k_fwd_quant_u8 above;
+// what changes is how the tiles move:
+//   in   one cp.async.bulk.tensor.2d per tile, issued by lane 0: a 256-byte x 8-row box of the pixel plane lands in
+//        the warp's input stage and signals the stage's mbarrier (two stages: tile t+1 is in flight while tile t is
+//        transformed).  Columns past the plane's width arrive as zeros, so a block row whose width is not a multiple
+//        of 256 simply ends with a partial tile: tiles never straddle block rows here (tile = 32 blocks of ONE block row).
+//   out  each lane writes its 128-byte record into a 128B-swizzled 4 KB stage (8 conflict-free STS.128), lane 0 hands
+//        the stage to the copy engine (cp.async.bulk.tensor.2d shared -> global); the store drains while the warp is
+//        already transforming the next tile.  Partial tiles use a second tensor map whose box holds bw % 32 records.
+// Against the cp.async kernel this removes 8 LDGSTS, 8 LDS.128 and 8 STG.128 per lane and the address arithmetic
+// that went with them.
+// ------------------------------------------------------------------------------------------
+struct alignas(64) FwdTmaParams {
+    CUtensorMap map_px;        // uint8 plane, box 256 x 8
+    CUtensorMap map_rec;       // records, box 128 B x 32, 128-byte swizzle
+    CUtensorMap map_rec_tail;  // records, box 128 B x (bw % 32)
+    FwdParams f;
+    uint32_t tpr;              // tiles per block row = ceil(bw / 32)
+    uint32_t nby;              // block rows
+    uint32_t step_ty, step_tx; // divmod(warps in the grid, tpr): how a warp's tile coordinates advance
+};
+
+constexpr int kTmaOutBytes = 4096;                                  // per warp: 32 records
+constexpr int kTmaInBytes = 2048;                                   // per warp and stage: 8 rows x 256 B
+constexpr int kTmaSmemBytes = 1024 /* alignment slack */ + kWarps * (kTmaOutBytes + kInStages * kTmaInBytes) + kWarps * 32;
+
+template <int LAYOUT, bool ADAPTIVE, bool UNIFORM>
+__global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8_tma(const __grid_constant__ FwdTmaParams P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const FwdParams &p = P.f;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // tells the compiler it is warp-uniform
+    // carve: [8 x 4 KB record stages, 1024-aligned for the swizzle][8 x 2 x 2 KB pixel stages][8 x (2 mbarriers + count)]
+    uint8_t *sm = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+    uint8_t *out_p = sm + warp * kTmaOutBytes;
+    uint8_t *in_p = sm + kWarps * kTmaOutBytes + warp * (kInStages * kTmaInBytes);
+    uint32_t *ctl_p = reinterpret_cast<uint32_t *>(sm + kWarps * (kTmaOutBytes + kInStages * kTmaInBytes) + warp * 32);
+    const uint32_t out_s = (uint32_t)__cvta_generic_to_shared(out_p), in_s = (uint32_t)__cvta_generic_to_shared(in_p);
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(ctl_p);           // two 8-byte mbarriers, then the count
+
+    if (lane == 0) {
+        tma::mbar_init(bar_s, 1);
+        tma::mbar_init(bar_s + 8, 1);
+        ctl_p[4] = 0;                        // entries this warp has appended to its worklist segment
+        tma::fence_barrier_init();
+    }
+    __syncwarp();
+
+    // (ty, tx): block row and tile-in-row of the next tile to fetch
+    uint32_t ty, tx;
+    {
+        const uint32_t t = blockIdx.x * kWarps + warp;
+        ty = t / P.tpr;
+        tx = t - ty * P.tpr;
+    }
+    auto issue = [&](uint32_t stage) {
+        if (lane == 0) {
+            tma::mbar_expect_tx(bar_s + stage * 8, kTmaInBytes);
+            tma::load_2d(in_s + stage * kTmaInBytes, &P.map_px, (int)(tx * 256), (int)(ty * 8), bar_s + stage * 8);
+        }
+    };
+    if (ty < P.nby) issue(0);
+    // my chunk j goes to 16-byte slot j ^ (lane & 7) of my 128-byte row
+    uint8_t *const my_out = out_p + lane * 128;
+    const uint32_t swz = (lane & 7) << 4;
+
+    for (uint32_t it = 0; ty < P.nby; ++it) {
+        const uint32_t stage = it & 1;
+        const uint32_t bx0 = tx * 32;
+        const uint32_t warp_base = ty * p.bw + bx0;               // first record of this tile
+        const uint32_t nvalid = min(32u, p.bw - bx0);
+        // advance to the next tile and fetch it
+        tx += P.step_tx;
+        ty += P.step_ty;
+        if (tx >= P.tpr) tx -= P.tpr, ++ty;
+        if (ty < P.nby) issue(stage ^ 1);
+        tma::mbar_wait(bar_s + stage * 8, (it >> 1) & 1);
+
+        const uint32_t b = warp_base + lane;
+        const bool valid = lane < nvalid;
+        const uint8_t *in_stage = in_p + stage * kTmaInBytes;
+        uint2 raw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) raw[i] = *reinterpret_cast<const uint2 *>(in_stage + i * 256 + lane * 8);
+
+        uint32_t w[32];
+        const bool flag = fwd_block<LAYOUT, ADAPTIVE, UNIFORM>(p, raw, w, valid, b);
+        const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
+
+        // the previous tile's store must have finished reading the stage before it is rewritten
+        if (lane == 0) tma::store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4 *>(my_out + ((j << 4) ^ swz)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        tma::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tma::store_2d(nvalid == 32 ? &P.map_rec : &P.map_rec_tail, 0, (int)warp_base, out_s);
+            tma::store_commit();
+        }
+
+        if (ballot != 0) {
+            // The warp appends to its own segment of the worklist (no global atomic); lane 8 writes the entry,
+            // lanes 0-7 copy one pixel row each from the input stage to the 64 bytes that go with it (read by K3).
+            const uint32_t gwarp = blockIdx.x * kWarps + warp;
+            uint32_t wl_n = ctl_p[4];
+            __syncwarp();
+            if (lane == 0) ctl_p[4] = wl_n + __popc(ballot);
+            for (unsigned todo = ballot; todo != 0; todo &= todo - 1, ++wl_n) {
+                const unsigned f = __ffs(todo) - 1;
+                if (lane < 8) {
+                    if (wl_n < p.side_seg_cap)
+                        reinterpret_cast<uint2 *>(p.side + ((size_t)gwarp * p.side_seg_cap + wl_n) * 64)[lane] =
+                            *reinterpret_cast<const uint2 *>(in_stage + lane * 256 + f * 8);
+                } else if (lane == 8) {
+                    p.worklist[(size_t)gwarp * p.seg_cap + wl_n] = warp_base + f;
+                }
+            }
+        }
+        __syncwarp();   // every lane is done with this input stage: the fetch after next may overwrite it
+    }
+    if (lane == 0) {
+        p.seg_count[blockIdx.x * kWarps + warp] = ctl_p[4];
+        tma::store_wait_read();               // shared memory must outlive the last store's reads
+    }
+}
+
 
 // ------------------------------------------------------------------------------------------
 // K1 from FLOAT pixel tiles (north_star: "8-bit or float pixel tiles"): block = (double)p - 128.0
@@ -378,9 +521,64 @@ static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t 
     return cudaGetLastError();
 }
 
+// bulk-tensor kernel: persistent grid like the cp.async one, tiles = 32 blocks of one block row
+template <typename K>
+static cudaError_t launch_persistent_tma(K kernel, const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    static int per_sm = 0;   // same for every variant: identical launch bounds and shared memory
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, kTmaSmemBytes) != cudaSuccess || n < 1) n = 1;
+        per_sm = n;
+        if (getenv("DCT_CUDA_DEBUG")) fprintf(stderr, "libdct_cuda: K1 (bulk tensor): %d CTAs/SM, %d B smem\n", n, kTmaSmemBytes);
+    }
+    FwdTmaParams q;
+    q.f = p;
+    q.nby = p.nblocks / p.bw;
+    q.tpr = (p.bw + 31) / 32;
+    const unsigned ntiles = q.nby * q.tpr;
+    const unsigned resident = (unsigned)sm_count() * (unsigned)per_sm;
+    const unsigned want = (ntiles + kWarps - 1) / kWarps;
+    const unsigned grid = want < resident ? want : resident;
+    const unsigned n_segs = grid * kWarps;
+    q.step_ty = n_segs / q.tpr;
+    q.step_tx = n_segs - q.step_ty * q.tpr;
+    const unsigned tiles_per_warp = (ntiles + n_segs - 1) / n_segs;
+    q.f.seg_cap = p.wl_cap / n_segs;
+    q.f.side_seg_cap = p.side ? p.side_cap / n_segs : 0;
+    if (n_segs > kMaxWorklistSegments - 128 || q.f.seg_cap < tiles_per_warp * 32 || p.seg_count == nullptr) return cudaErrorInvalidValue;
+    const int W = (int)p.bw * 8, H = (int)q.nby * 8;
+    if ((e = make_pixel_map(&q.map_px, p.px, p.pitch, W, H)) != cudaSuccess) return e;
+    if ((e = make_record_map(&q.map_rec, p.coef, p.nblocks, 32)) != cudaSuccess) return e;
+    const int tail = (int)(p.bw % 32);
+    if ((e = make_record_map(&q.map_rec_tail, p.coef, p.nblocks, tail ? tail : 32)) != cudaSuccess) return e;
+    if (segments) *segments = WorklistSegments{n_segs, q.f.seg_cap, q.f.side_seg_cap};
+    kernel<<<grid, kThreads, kTmaSmemBytes, s>>>(q);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+// the bulk-tensor kernel needs: the driver's tensor-map encoder, a 16-byte aligned plane whose pitch is a multiple
+// of 16, and block rows of at least one whole tile (narrower planes stay on the cp.async kernel, whose tiles wrap)
+static bool tma_eligible(const FwdParams &p)
+{
+    static const bool disabled = getenv("DCT_CUDA_NO_TMA") != nullptr;   // measurement aid: force the cp.async kernels
+    if (disabled || p.no_tma || !tma_available()) return false;
+    if (p.bw < 32 || (p.pitch % 16) || ((uintptr_t)p.px % 16) || ((uintptr_t)p.coef % 16)) return false;
+    const unsigned long long padded = (unsigned long long)(p.nblocks / p.bw) * ((p.bw + 31) / 32) * 32;
+    return padded + (unsigned long long)kMaxWorklistSegments * 64 <= p.wl_cap;
+}
+
 template <int LAYOUT, bool ADAPTIVE>
 static cudaError_t launch_k1(const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
 {
+    if (tma_eligible(p))
+        return p.uniform_band ? launch_persistent_tma(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, true>, p, s, launches, segments)
+                              : launch_persistent_tma(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, false>, p, s, launches, segments);
     return p.uniform_band ? launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, true>, p, s, launches, segments)
                           : launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, false>, p, s, launches, segments);
 }

@@ -62,6 +62,7 @@ struct FwdParams {
     uint32_t *seg_count;       // one entry per warp of the grid
     uint32_t seg_cap;          // worklist entries per segment (>= 32 * tiles per warp)
     uint32_t side_seg_cap;     // side slots per segment (entries beyond it have no pixel copy)
+    int no_tma;                // 1: keep the cp.async kernel (planes mapped from a peer GPU)
 };
 
 // geometry of the segmented worklist a k_fwd_quant_u8 launch produced (consumed by k_replay_fwd_lane)
@@ -96,6 +97,9 @@ struct InvParams {
     float2 ma[4][4];
     PosNeg2 mb[4][4];
     float rg[64];          // natural index: rs * gain, rounded up (bound on the raw quantised values)
+    // bulk-tensor kernel only: every warp of the persistent grid appends to its OWN worklist segment (see FwdParams)
+    uint32_t *seg_count;   // one entry per warp of the grid, or null (keeps the one-shot kernel and its atomic append)
+    int no_tma;            // 1: keep the one-shot kernel (planes mapped from a peer GPU)
 };
 
 // K3: exact fp64 replay of the blocks on the worklist (or of every block when wl == null).
@@ -127,7 +131,8 @@ cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cu
                                 WorklistSegments *segments = nullptr);
 constexpr uint32_t kMaxWorklistSegments = 4096;   // warps of the largest persistent grid this library launches
 cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s);
-cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s);
+// `segments`: geometry of the segmented worklist the launch produced (n_segs == 0: flat worklist counted in ctr->wl_count)
+cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments = nullptr);
 cudaError_t launch_dequant_idct_u8_f64(const InvParams &p, const ExactTables *d_tab, int layout, cudaStream_t s);
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s);
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s);

@@ -95,6 +95,7 @@ struct dct_cuda_plan {
     size_t frame_cap = 0;
     cudaEvent_t ev_peer = nullptr;              // *_peer calls: "input ready" (owner) / "shard done" (peers)
     uint64_t launches = 0;                      // kernels launched for this plan (dct_cuda_plan_kernel_launches)
+    bool no_tma = false;                        // set around the peer calls: planes mapped from another GPU keep the cp.async / LDG kernels
     bool fits_i8 = false;                       // every quantised value of a uint8 plane fits int8 (narrow.cu)
     std::mutex mu;                              // serialises the entry points on one plan (lanes and buffers are state)
 };

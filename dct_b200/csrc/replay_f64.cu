@@ -274,6 +274,54 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
     }
 }
 
+// ---- segmented worklists (K1 / K2 bulk-tensor kernels): one segment per warp of the producer's grid ------------------
+// Exclusive prefix sums of the segments' counts into prefix[0 .. n_segs]; every thread of a kLaneThreads-wide CTA calls it.
+constexpr int kLaneThreads = 128;
+constexpr int kLaneWarps = kLaneThreads / 32;
+
+__device__ __forceinline__ void build_segment_prefix(unsigned *prefix, const uint32_t *seg_count, unsigned n_segs)
+{
+    // counts -> shared memory (coalesced), per-thread sums of contiguous chunks, block-wide scan of the 128 sums,
+    // then every thread turns its chunk into exclusive prefixes in place
+    for (unsigned i = threadIdx.x; i < n_segs; i += kLaneThreads) prefix[i] = seg_count[i];
+    __syncthreads();
+    const unsigned per = (n_segs + kLaneThreads - 1) / kLaneThreads, first = threadIdx.x * per;
+    const unsigned last = first + per < n_segs ? first + per : n_segs;
+    unsigned sum = 0;
+    for (unsigned i = first; i < last; ++i) sum += prefix[i];
+    unsigned incl = sum;                              // inclusive scan over the CTA's 128 threads
+    const int ln_ = threadIdx.x & 31, wp_ = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (ln_ >= d) incl += v;
+    }
+    __shared__ unsigned warp_tot[kLaneWarps];
+    if (ln_ == 31) warp_tot[wp_] = incl;
+    __syncthreads();
+    unsigned base = incl - sum;
+    for (int w = 0; w < wp_; ++w) base += warp_tot[w];
+    for (unsigned i = first; i < last; ++i) {
+        const unsigned c = prefix[i];
+        prefix[i] = base;
+        base += c;
+    }
+    if (threadIdx.x == kLaneThreads - 1) prefix[n_segs] = base;   // the last thread's running sum is the total
+    __syncthreads();
+}
+
+// binary search: the segment with prefix[seg] <= entry < prefix[seg + 1], and the entry's index inside it
+__device__ __forceinline__ void find_segment(const unsigned *prefix, unsigned n_segs, unsigned entry, unsigned &seg, unsigned &local)
+{
+    unsigned lo = 0, hi = n_segs;
+    while (hi - lo > 1) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (prefix[mid] <= entry) lo = mid;
+        else hi = mid;
+    }
+    seg = lo, local = entry - prefix[lo];
+}
+
 // ------------------------------------------------------------------------------------------
 // K3 forward, common case (uint8 pixels, worklist mode; adaptive tables included): ONE LANE PER FLAGGED BLOCK.
 // The 8-lanes-per-block kernel above spends ~125 warp instructions per block, most of them on the
@@ -284,8 +332,6 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
 // value on its own: the reference's 64 + 8 non-contracted fp64 multiply-adds in its own order
 // (src/dct.c:57-74), true division, half-away rounding (src/quantization.c:122-126).
 // ------------------------------------------------------------------------------------------
-constexpr int kLaneThreads = 128;
-constexpr int kLaneWarps = kLaneThreads / 32;
 constexpr int kPairsPerRound = 4;                  // pairs one lane may append per round
 
 struct LaneShared {
@@ -311,35 +357,7 @@ __global__ void __launch_bounds__(kLaneThreads, 4) k_replay_fwd_lane(const Repla
     // K1 left one worklist segment per warp of its grid and the segments' counts; entry e of the concatenation lives
     // in the segment s with prefix[s] <= e < prefix[s + 1].  Every CTA builds the prefix sums for itself.
     const unsigned n_segs = p.seg.n_segs;
-    {
-        // counts -> shared memory (coalesced), per-thread sums of contiguous chunks, block-wide scan of the 128 sums,
-        // then every thread turns its chunk into exclusive prefixes in place
-        for (unsigned i = threadIdx.x; i < n_segs; i += kLaneThreads) sh.prefix[i] = p.seg_count[i];
-        __syncthreads();
-        const unsigned per = (n_segs + kLaneThreads - 1) / kLaneThreads, first = threadIdx.x * per;
-        const unsigned last = first + per < n_segs ? first + per : n_segs;
-        unsigned sum = 0;
-        for (unsigned i = first; i < last; ++i) sum += sh.prefix[i];
-        unsigned incl = sum;                              // inclusive scan over the CTA's 128 threads
-        const int ln_ = threadIdx.x & 31, wp_ = threadIdx.x >> 5;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (ln_ >= d) incl += v;
-        }
-        __shared__ unsigned warp_tot[kLaneWarps];
-        if (ln_ == 31) warp_tot[wp_] = incl;
-        __syncthreads();
-        unsigned base = incl - sum;
-        for (int w = 0; w < wp_; ++w) base += warp_tot[w];
-        for (unsigned i = first; i < last; ++i) {
-            const unsigned c = sh.prefix[i];
-            sh.prefix[i] = base;
-            base += c;
-        }
-        if (threadIdx.x == kLaneThreads - 1) sh.prefix[n_segs] = base;   // the last thread's running sum is the total
-        __syncthreads();
-    }
+    build_segment_prefix(sh.prefix, p.seg_count, n_segs);
     const unsigned count = sh.prefix[n_segs];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned tiles = (count + 31) / 32, warps_per_grid = gridDim.x * kLaneWarps;
@@ -349,15 +367,7 @@ __global__ void __launch_bounds__(kLaneThreads, 4) k_replay_fwd_lane(const Repla
         const unsigned entry = tile * 32 + lane;
         const bool active = entry < count;
         unsigned seg = 0, local = 0;
-        if (active) {                                     // binary search: largest seg with prefix[seg] <= entry
-            unsigned lo = 0, hi = n_segs;
-            while (hi - lo > 1) {
-                const unsigned mid = (lo + hi) >> 1;
-                if (sh.prefix[mid] <= entry) lo = mid;
-                else hi = mid;
-            }
-            seg = lo, local = entry - sh.prefix[lo];
-        }
+        if (active) find_segment(sh.prefix, n_segs, entry, seg, local);
         const unsigned slot = local < p.seg.side_seg_cap ? seg * p.seg.side_seg_cap + local : 0xffffffffu;   // side slot
         const unsigned b = active ? p.worklist[(size_t)seg * p.seg.seg_cap + local] : 0;
         const unsigned by = b / p.bw, bx = b - by * p.bw;
@@ -693,6 +703,149 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K3 inverse, worklist mode: ONE LANE PER FLAGGED BLOCK (the decoder's counterpart of k_replay_fwd_lane).
+// The reference path being reproduced: dequantize (src/quantization.c:133-151) and dct_inverse (src/dct.c:80-105).
+// A lane redoes its whole block with the butterfly in fp64: its error (~1e-13 of the bound) is five orders of magnitude
+// below the fp32 band that flagged the block, so every pixel farther than band64 (~2e-9) from a .5 boundary is
+// settled right there -- with a wide dynamic fp32 band (high-quality tables) that is all of them.  What is left, a
+// value within 2e-9 of a boundary, is replayed by the same lane in the reference's own operation order: 64 + 8
+// non-contracted multiply-adds on the reference's dequantised values, ascending index, then the pixel rule.
+// The block's 64 pixels are rewritten as whole rows (the unflagged ones with the values K2 already wrote).
+// Against the 8-lanes-per-block kernel: no shared-memory transposes, no shuffles, no fp32 re-flagging pass.
+// ------------------------------------------------------------------------------------------
+constexpr double kMagic52_128r = 6755399441055744.0 + 128.0;   // 1.5 * 2^52 + 128
+
+struct LaneInvShared {
+    ExactTables tab;
+    unsigned prefix[kMaxWorklistSegments + 1];
+};
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kLaneThreads, 2) k_replay_inv_lane(const ReplayParams p)
+{
+    __shared__ LaneInvShared sh;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.tab);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(ExactTables) / 4); i += kLaneThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    const ExactTables &tab = sh.tab;
+    // segmented worklist (bulk-tensor K2: one segment per warp of its grid) or a flat one counted in ctr->wl_count
+    const bool segmented = p.seg_count != nullptr && p.seg.n_segs != 0;
+    const unsigned n_segs = p.seg.n_segs;
+    unsigned count;
+    if (segmented) {
+        build_segment_prefix(sh.prefix, p.seg_count, n_segs);
+        count = sh.prefix[n_segs];
+    } else {
+        count = p.ctr->wl_count;
+        if (count > p.wl_cap) count = p.wl_cap;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned warps_per_grid = gridDim.x * kLaneWarps;
+    unsigned ties = 0;
+
+    for (unsigned entry = (blockIdx.x * kLaneWarps + warp) * 32 + lane; entry < count; entry += warps_per_grid * 32) {
+        unsigned b;
+        if (segmented) {
+            unsigned seg, local;
+            find_segment(sh.prefix, n_segs, entry, seg, local);
+            b = p.worklist[(size_t)seg * p.seg.seg_cap + local];
+        } else {
+            b = p.worklist[entry];
+        }
+        const unsigned by = b / p.bw, bx = b - by * p.bw;
+        uint8_t *dst = p.px_out + (long long)by * 8 * p.pitch + (long long)bx * 8;
+        const int16_t *rec = p.coef_in + (size_t)b * 64;
+
+        double two_minus_nv = 1.0, inv_two_minus_nv = 1.0;
+        if (p.adaptive) {
+            const double var = p.var_in ? p.var_in[b] : 0.0;
+            two_minus_nv = __dsub_rn(2.0, norm_variance(var));
+            inv_two_minus_nv = __ddiv_rn(1.0, two_minus_nv);   // src/quantization.c:193
+        }
+
+        // the block in fp64: q * multiplier * (2-nv) instead of the reference's reciprocal chain (a few ulps apart,
+        // inside the 8 * 2^-53 relative input error the bound allows for), columns then rows as src/dct.c:85-102
+        double v[64];
+        double bound64 = 0.0;
+        static_for<0, 8>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            const uint4 t = reinterpret_cast<const uint4 *>(rec)[j];
+            const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+            static_for<0, 8>([&](auto Hh) {
+                constexpr int h = decltype(Hh)::value;
+                constexpr int k = storage_to_natural<LAYOUT>(8 * j + h);
+                const int q = (int)(int16_t)(h & 1 ? (w4[h >> 1] >> 16) : (w4[h >> 1] & 0xFFFFu));
+                double x = (double)q * tab.mp64[k];
+                if (k != 0) x *= two_minus_nv;
+                v[k] = x;
+                bound64 = fma(fabs(x), (double)tab.gain32[k], bound64);
+            });
+        });
+#pragma unroll
+        for (int j = 0; j < 8; ++j) idct8<double, 8>(&v[j]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) idct8<double, 1>(&v[8 * i]);
+
+        // 1e-9: the tie-accounting margin; 8 * 2^-53 * bound: fp64 butterfly + the reference's own rounding
+        const double thr = 0.5 - (2e-9 + bound64 * 8.9e-16);
+        const bool sane = bound64 < 1e12;
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double x = v[8 * i + j];
+                const double t = x + kMagic52_128r;           // low mantissa bits: round-to-nearest(x) + 128
+                const double e = x - (t - kMagic52_128r);
+                int px = __double2loint(t);
+                if (!(fabs(e) < thr) || !sane) {
+                    // exact replay of pixel (i, j): temp[i][k] = sum_m D[m][i] * in[m][k] (src/dct.c:85-92),
+                    // out = sum_k temp[i][k] * D[k][j] (:95-102); in = the reference's dequantised values
+                    double out = 0.0;
+                    for (int k = 0; k < 8; ++k) {
+                        double temp = 0.0;
+                        for (int m = 0; m < 8; ++m) {
+                            const int nat = 8 * m + k;
+                            const int q = rec[LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[nat] : nat];
+                            temp = __dadd_rn(temp, __dmul_rn(tab.D[m * 8 + i], exact_dequant(tab, p.adaptive, inv_two_minus_nv, nat, q)));
+                        }
+                        out = __dadd_rn(out, __dmul_rn(temp, tab.D[k * 8 + j]));
+                    }
+                    const double val = __dadd_rn(out, 128.0);
+                    const double rr = round_half_away(val);
+                    ties += near_half(val);
+                    px = rr < 0.0 ? 0 : (rr > 255.0 ? 255 : (int)rr);
+                }
+                px = px < 0 ? 0 : (px > 255 ? 255 : px);
+                if (j < 4) lo |= (uint32_t)px << (8 * j);
+                else hi |= (uint32_t)px << (8 * (j - 4));
+            }
+            *reinterpret_cast<uint2 *>(dst + i * p.pitch) = make_uint2(lo, hi);
+        }
+    }
+
+    ties = __reduce_add_sync(0xffffffffu, ties);
+    if (lane == 0 && ties) atomicAdd(&p.ctr->near_ties, (unsigned long long)ties);
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
+    if (!segmented) {
+        // the last CTA to finish empties the flat worklist for the next K2 on this lane (saves a memset launch);
+        // every CTA has read wl_count long before it gets here
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&p.ctr->done_ctas, 1u) == gridDim.x - 1) {
+                p.ctr->wl_count = 0;
+                p.ctr->done_ctas = 0;
+            }
+        }
+    }
+}
+
 // ---- generic n x n single-block kernels (n <= 32): the per-block drop-in API -------------
 
 __global__ void k_block_dct_f64(int n, const double *D, const double *in, double *out, int inverse)
@@ -783,6 +936,14 @@ cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s)
 
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s)
 {
+    if (p.worklist != nullptr) {                         // the fused kernel ran: one lane per flagged block
+        // one CTA per ~1024 blocks of the plane (a tenth of them flagged would keep its four warps busy), at most 4 per SM
+        unsigned grid = (p.nblocks + 1023) / 1024;
+        grid = grid < 16u ? 16u : (grid > 148u * 4u ? 148u * 4u : grid);
+        if (p.layout == LAYOUT_ZIGZAG) k_replay_inv_lane<LAYOUT_ZIGZAG><<<grid, kLaneThreads, 0, s>>>(p);
+        else k_replay_inv_lane<LAYOUT_NATURAL><<<grid, kLaneThreads, 0, s>>>(p);
+        return cudaGetLastError();
+    }
     return p.layout == LAYOUT_ZIGZAG ? launch_replay(k_replay_inv<LAYOUT_ZIGZAG>, p, s)
                                      : launch_replay(k_replay_inv<LAYOUT_NATURAL>, p, s);
 }

@@ -173,10 +173,14 @@ int queue_generic(dct_cuda_plan *p, Lane &ln, int forward, const uint8_t *px_in,
     return DCT_CUDA_OK;
 }
 
+// worklist entries K1 / K2 may need for a plane of bw x nby blocks: their bulk-tensor kernels cut every block row into
+// tiles of 32 blocks (the last one of a row may be partial) and size a warp's segment for 32 entries per tile it visits
+static size_t worklist_entries(uint32_t bw, uint32_t nby) { return (size_t)nby * ((bw + 31) / 32) * 32; }
+
 int ensure_worklist(Lane &ln, size_t nblocks)
 {
-    // K1 appends to one segment per warp of its grid, each sized for all the blocks that warp visits, so the
-    // worklist holds nblocks entries plus up to 64 of slack per segment
+    // K1 / K2 append to one segment per warp of their grid, each sized for all the blocks that warp visits, so the
+    // worklist holds `nblocks` entries (already rounded up to whole tiles by the caller) plus up to 64 of slack per segment
     const size_t want = nblocks + (size_t)kMaxWorklistSegments * 64;
     if (ln.wl_cap >= want) return DCT_CUDA_OK;
     if (ln.d_wl) {
@@ -239,7 +243,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
     if (elem == 4 && p->adaptive)
         return fail(DCT_CUDA_EINVAL, "float pixel tiles are supported for non-adaptive plans only");
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
-    int rc = ensure_worklist(ln, nblocks);
+    int rc = ensure_worklist(ln, worklist_entries(bw, (uint32_t)(H / 8)));
     if (rc) return rc;
     // wl_count is zero here: plan creation zeroes it and K3's last CTA re-zeroes it after every replay
     if (p->skip_replay) CU_TRY(cudaMemsetAsync(&ln.d_ctr->wl_count, 0, sizeof(unsigned), s));
@@ -279,6 +283,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
         fp.side = use_side ? ln.d_side : nullptr;
         fp.side_cap = use_side ? ln.side_cap : 0;
         fp.seg_count = ln.d_seg_count;
+        fp.no_tma = p->no_tma ? 1 : 0;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (p->profile) {
             CU_TRY(cudaEventCreate(&e0));
@@ -318,7 +323,7 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
         return fail(DCT_CUDA_EINVAL, "pixels must be 8-byte and coefficients 16-byte aligned");
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     if (p->adaptive && !d_var) return fail(DCT_CUDA_EINVAL, "adaptive plan needs the per-block variance array");
-    int rc = ensure_worklist(ln, nblocks);
+    int rc = ensure_worklist(ln, worklist_entries(bw, (uint32_t)(H / 8)));
     if (rc) return rc;
     // wl_count is zero here: plan creation zeroes it and K3's last CTA re-zeroes it after every replay
     if (p->skip_replay) CU_TRY(cudaMemsetAsync(&ln.d_ctr->wl_count, 0, sizeof(unsigned), s));
@@ -350,6 +355,8 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
         memcpy(ip.gain, p->gain, sizeof ip.gain);
         memcpy(ip.rg, p->rg, sizeof ip.rg);
         ip.band_floor = p->band_floor;
+        ip.seg_count = ln.d_seg_count;
+        ip.no_tma = p->no_tma ? 1 : 0;
         {   // multipliers of the folded first stage, in the kernel's pair order
             static const int colA[4] = {0, 2, 5, 1}, colB[4] = {4, 6, 3, 7};
             for (int c = 0; c < 4; ++c)
@@ -367,8 +374,12 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
             CU_TRY(cudaEventRecord(e0, s));
         }
         // adaptive plans decode full-scale values: the fp64 butterfly keeps the replay list short
-        if (p->adaptive && !p->force_fp32_inverse) CU_TRY(launch_dequant_idct_u8_f64(ip, p->d_tab, layout, s));
-        else CU_TRY(launch_dequant_idct_u8(ip, layout, p->adaptive, s));
+        if (p->adaptive && !p->force_fp32_inverse) {
+            CU_TRY(launch_dequant_idct_u8_f64(ip, p->d_tab, layout, s));
+        } else {
+            CU_TRY(launch_dequant_idct_u8(ip, layout, p->adaptive, s, &rp.seg));
+            if (rp.seg.n_segs) rp.seg_count = ln.d_seg_count;     // segmented worklist (bulk-tensor kernel)
+        }
         ++p->launches;
         if (p->profile) {
             CU_TRY(cudaEventRecord(e1, s));
@@ -388,7 +399,7 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
 // pixel (int16 and int8 form), one variance per block
 int ensure_strip_buffers(dct_cuda_plan *p, Lane &ln, size_t pixels, int elem)
 {
-    const size_t need = pixels * (size_t)elem;
+    const size_t need = (pixels * (size_t)elem + 255) & ~(size_t)255;   // whole 256-byte units: the int8 records behind the int16 ones stay aligned
     if (ln.cap_blocks >= need) return DCT_CUDA_OK;
     CU_TRY(cudaStreamSynchronize(ln.stream));
     if (ln.d_px) cudaFree(ln.d_px);
@@ -658,6 +669,8 @@ static int fwd_host_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int
         return fail(DCT_CUDA_EINVAL, "int8 records need every table entry >= %.3f (dct_cuda_plan_records_fit_i8)",
                     p->n * 128.0 / 127.5);
     const int n = p->n, nn = n * n;
+    if (rec8 && (nn % 16))
+        return fail(DCT_CUDA_EINVAL, "int8 records need a block size whose square is a multiple of 16 (got %d)", n);
     int rc = ragged ? check_ragged(px, coef, pitch / elem, W, H, n) : check_plane(px, coef, pitch / elem, W, H, false, n);
     if (rc) return rc;
     if (elem == 4 && p->adaptive) return fail(DCT_CUDA_EINVAL, "float pixel tiles are supported for non-adaptive plans only");
@@ -667,17 +680,21 @@ static int fwd_host_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int
     const int Wp = (W + n - 1) / n * n, Hp = (H + n - 1) / n * n;   // == W, H unless ragged
     const int bw = Wp / n, total_rows = Hp / n, rows = strip_rows(Wp, Hp, n);
     if (rows > 0) {
+        // rows of the device strip start on 16-byte boundaries (the bulk-tensor kernels need that)
+        const size_t dev_pitch = ((size_t)Wp * elem + 15) & ~(size_t)15;
         for (int l = 0; l < kLanes; ++l)
-            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw * nn, elem))) return rc;
+            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * n * dev_pitch, 1))) return rc;
         int idx = 0;
-        const size_t dev_pitch = (size_t)Wp * elem;
         for (int r0 = 0; r0 < total_rows; r0 += rows, ++idx) {
             Lane &ln = p->lane[idx % kLanes];
             const int nr = std::min(rows, total_rows - r0);
             const int have = std::min(nr * n, H - r0 * n);               // image rows in this strip
             const size_t nb = (size_t)nr * bw, b0 = (size_t)r0 * bw;
-            CU_TRY(cudaMemcpy2DAsync(ln.d_px, dev_pitch, px + (size_t)r0 * n * pitch, pitch, (size_t)W * elem, (size_t)have,
-                                     cudaMemcpyHostToDevice, ln.stream));
+            if (pitch == dev_pitch && (size_t)W * elem == pitch)         // dense rows on both sides: one linear copy
+                CU_TRY(cudaMemcpyAsync(ln.d_px, px + (size_t)r0 * n * pitch, pitch * (size_t)have, cudaMemcpyHostToDevice, ln.stream));
+            else
+                CU_TRY(cudaMemcpy2DAsync(ln.d_px, dev_pitch, px + (size_t)r0 * n * pitch, pitch, (size_t)W * elem, (size_t)have,
+                                         cudaMemcpyHostToDevice, ln.stream));
             if (Wp != W || have != nr * n)
                 CU_TRY(launch_pad_edges(ln.d_px, (long long)dev_pitch, W, have, Wp, nr * n, elem, ln.stream));
             if ((rc = queue_fwd(p, ln, ln.d_px, dev_pitch, Wp, nr * n, ln.d_coef, layout, ln.d_var, ln.stream, elem))) return rc;
@@ -735,6 +752,8 @@ static int inv_host_async(dct_cuda_plan *p, const void *coef, int W, int H, int 
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     const int n = p->n, nn = n * n;
+    if (rec8 && (nn % 16))
+        return fail(DCT_CUDA_EINVAL, "int8 records need a block size whose square is a multiple of 16 (got %d)", n);
     int rc = ragged ? check_ragged(px, coef, pitch, W, H, n) : check_plane(px, coef, pitch, W, H, false, n);
     if (rc) return rc;
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
@@ -744,8 +763,9 @@ static int inv_host_async(dct_cuda_plan *p, const void *coef, int W, int H, int 
     const int Wp = (W + n - 1) / n * n, Hp = (H + n - 1) / n * n;   // == W, H unless ragged
     const int bw = Wp / n, total_rows = Hp / n, rows = strip_rows(Wp, Hp, n);
     if (rows > 0) {
+        const size_t dev_pitch = ((size_t)Wp + 15) & ~(size_t)15;
         for (int l = 0; l < kLanes; ++l)
-            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * bw * nn))) return rc;
+            if ((rc = ensure_strip_buffers(p, p->lane[l], (size_t)rows * n * dev_pitch))) return rc;
         int idx = 0;
         for (int r0 = 0; r0 < total_rows; r0 += rows, ++idx) {
             Lane &ln = p->lane[idx % kLanes];
@@ -762,9 +782,12 @@ static int inv_host_async(dct_cuda_plan *p, const void *coef, int W, int H, int 
             }
             if (p->adaptive)
                 CU_TRY(cudaMemcpyAsync(ln.d_var, var + b0, nb * sizeof(double), cudaMemcpyHostToDevice, ln.stream));
-            if ((rc = queue_inv(p, ln, ln.d_coef, Wp, nr * n, layout, ln.d_var, ln.d_px, (size_t)Wp, ln.stream))) return rc;
-            CU_TRY(cudaMemcpy2DAsync(px + (size_t)r0 * n * pitch, pitch, ln.d_px, (size_t)Wp, (size_t)W, (size_t)have,
-                                     cudaMemcpyDeviceToHost, ln.stream));
+            if ((rc = queue_inv(p, ln, ln.d_coef, Wp, nr * n, layout, ln.d_var, ln.d_px, dev_pitch, ln.stream))) return rc;
+            if (pitch == dev_pitch && (size_t)W == pitch)                // dense rows on both sides: one linear copy
+                CU_TRY(cudaMemcpyAsync(px + (size_t)r0 * n * pitch, ln.d_px, pitch * (size_t)have, cudaMemcpyDeviceToHost, ln.stream));
+            else
+                CU_TRY(cudaMemcpy2DAsync(px + (size_t)r0 * n * pitch, pitch, ln.d_px, dev_pitch, (size_t)W, (size_t)have,
+                                         cudaMemcpyDeviceToHost, ln.stream));
         }
     }
     return DCT_CUDA_OK;

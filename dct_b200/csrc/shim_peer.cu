@@ -71,7 +71,9 @@ template <typename F> int peer_run(dct_cuda_plan *const *plans, int n, const std
         std::lock_guard<std::mutex> plan_lock(p->mu);
         cudaStream_t s = p->lane[0].stream;
         CU_TRY(cudaStreamWaitEvent(s, own->ev_peer, 0));
+        p->no_tma = true;                    // the shard lives in the owner's memory: plain loads / stores through NVLink
         int rc = queue(p, r0, r1, s);
+        p->no_tma = false;
         if (rc) return rc;
         CU_TRY(cudaEventRecord(p->ev_peer, s));
     }
