@@ -321,6 +321,7 @@ def parity_check(cx, plan, px, coef, rec, layout, quality, adaptive, frames):
     plan.stats()
     var = torch.empty(nrows * W // 64, dtype=torch.float64, device=cx.dev) if adaptive else None
     got_c = plan.fwd_quant_dev(strip, layout, None, var)
+    got_c = got_c[0] if isinstance(got_c, tuple) else got_c
     st = plan.stats()
     got_p = plan.dequant_idct_dev(got_c, W, nrows, layout, var)
     torch.cuda.synchronize()

@@ -331,11 +331,18 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
-def _stream_ptr(stream):
+def _stream_ptr(stream, device=None):
+    """The CUDA stream a call is queued on: `stream` if given, else torch's current stream OF `device` (the plan's
+    or the tensor's GPU -- not of whatever device torch currently has selected)."""
     if stream is None:
         import torch
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     return C.c_void_p(getattr(stream, "cuda_stream", stream))
+
+
+def _on_device(tensor, device, what):
+    if tensor is not None and tensor.device.index != device:
+        raise DctCudaError(f"{what} lives on cuda:{tensor.device.index}, the plan on cuda:{device}")
 
 
 class Plan:
@@ -391,8 +398,9 @@ class Plan:
             assert pixels.is_cuda and pixels.dtype == torch.float32 and pixels.dim() == 2 and pixels.stride(1) == 1
             H, W = pixels.shape
             coef = torch.empty(((H // 8) * (W // 8), 64), dtype=torch.int16, device=pixels.device)
+            _on_device(pixels, self.device, "pixels")
             _check(_fwd_f32_dev(self._h, pixels.data_ptr(), pixels.stride(0) * 4, W, H, coef.data_ptr(), layout,
-                                _stream_ptr(None)))
+                                _stream_ptr(None, self.device)))
             return coef
         assert pixels.dtype == np.float32 and pixels.ndim == 2 and pixels.strides[1] == 4
         H, W = pixels.shape
@@ -479,16 +487,18 @@ class Plan:
         var = var_out
         if self.adaptive and var is None:
             var = torch.empty(nb, dtype=torch.float64, device=pixels.device)
+        _on_device(pixels, self.device, "pixels"), _on_device(coef, self.device, "coef_out"), _on_device(var, self.device, "var_out")
         _check(_fwd_dev(self._h, pixels.data_ptr(), pixels.stride(0), W, H, coef.data_ptr(), layout,
-                        var.data_ptr() if var is not None else None, _stream_ptr(stream)))
+                        var.data_ptr() if var is not None else None, _stream_ptr(stream, self.device)))
         return (coef, var) if self.adaptive else coef
 
     def dequant_idct_dev(self, coef, W, H, layout=NATURAL, var=None, pixels_out=None, stream=None):
         import torch
         assert coef.is_cuda and coef.dtype == torch.int16 and coef.is_contiguous()
         px = pixels_out if pixels_out is not None else torch.empty((H, W), dtype=torch.uint8, device=coef.device)
+        _on_device(coef, self.device, "coef"), _on_device(px, self.device, "pixels_out"), _on_device(var, self.device, "var")
         _check(_inv_dev(self._h, coef.data_ptr(), W, H, layout, var.data_ptr() if var is not None else None,
-                        px.data_ptr(), px.stride(0), _stream_ptr(stream)))
+                        px.data_ptr(), px.stride(0), _stream_ptr(stream, self.device)))
         return px
 
     def debug_skip_replay(self, skip=True):
@@ -511,15 +521,16 @@ class Plan:
         nb = coef.numel() // 64
         off = torch.empty(nb + 1, dtype=torch.int32, device=coef.device)
         total = C.c_uint64(0)
-        _check(_rle_count(self._h, coef.data_ptr(), nb, off.data_ptr(), C.byref(total), _stream_ptr(stream)))
+        _on_device(coef, self.device, "coef")
+        _check(_rle_count(self._h, coef.data_ptr(), nb, off.data_ptr(), C.byref(total), _stream_ptr(stream, self.device)))
         sym = torch.empty((int(total.value), 2), dtype=torch.int32, device=coef.device)
         if total.value:
-            _check(_rle_emit(self._h, coef.data_ptr(), nb, layout, off.data_ptr(), sym.data_ptr(), _stream_ptr(stream)))
+            _check(_rle_emit(self._h, coef.data_ptr(), nb, layout, off.data_ptr(), sym.data_ptr(), _stream_ptr(stream, self.device)))
         return off, sym
 
     def stats(self, stream=None):
         st = Stats()
-        _check(_stats_fetch(self._h, C.byref(st), _stream_ptr(stream)))
+        _check(_stats_fetch(self._h, C.byref(st), _stream_ptr(stream, self.device)))
         return st.as_dict()
 
 
@@ -541,7 +552,7 @@ def rgb_to_ycbcr420_dev(rgb, stream=None):
     cb = torch.empty((g.c_height, g.c_width), dtype=torch.uint8, device=rgb.device)
     cr = torch.empty_like(cb)
     _check(_rgb_to_ycc(rgb.device.index or 0, rgb.data_ptr(), rgb.stride(0), C.byref(g), y.data_ptr(), y.stride(0),
-                       cb.data_ptr(), cr.data_ptr(), cb.stride(0), _stream_ptr(stream)))
+                       cb.data_ptr(), cr.data_ptr(), cb.stride(0), _stream_ptr(stream, rgb.device)))
     return y, cb, cr
 
 
@@ -552,7 +563,7 @@ def ycbcr420_to_rgb_dev(y, cb, cr, width, height, rgb_out=None, stream=None):
     assert cb.stride(0) == cr.stride(0)
     rgb = rgb_out if rgb_out is not None else _alloc_rgb(height, width, y.device)
     _check(_ycc_to_rgb(y.device.index or 0, y.data_ptr(), y.stride(0), cb.data_ptr(), cr.data_ptr(), cb.stride(0),
-                       C.byref(g), rgb.data_ptr(), rgb.stride(0), _stream_ptr(stream)))
+                       C.byref(g), rgb.data_ptr(), rgb.stride(0), _stream_ptr(stream, y.device)))
     return rgb
 
 
@@ -567,7 +578,7 @@ def _alloc_rgb(height, width, device):
 def pad_edges_dev(plane, width, height, stream=None):
     """Fill plane[:, width:] and plane[height:, :] (torch cuda uint8 [H_pad, W_pad]) by edge replication, in place."""
     _check(_pad_edges(plane.device.index or 0, plane.data_ptr(), plane.stride(0), int(width), int(height),
-                      plane.shape[1], plane.shape[0], _stream_ptr(stream)))
+                      plane.shape[1], plane.shape[0], _stream_ptr(stream, plane.device)))
     return plane
 
 
@@ -641,7 +652,7 @@ def fwd_quant_peer(plans, pixels, layout=NATURAL, coef_out=None, var_out=None, s
     hs = (C.c_void_p * len(plans))(*[p._h for p in plans])
     with torch.cuda.device(pixels.device):
         _check(_fwd_peer(hs, len(plans), pixels.data_ptr(), pixels.stride(0), W, H, coef.data_ptr(), layout,
-                         var.data_ptr() if var is not None else None, _shares(share, len(plans)), _stream_ptr(stream)))
+                         var.data_ptr() if var is not None else None, _shares(share, len(plans)), _stream_ptr(stream, pixels.device)))
     return (coef, var) if plans[0].adaptive else coef
 
 
@@ -652,7 +663,7 @@ def dequant_idct_peer(plans, coef, W, H, layout=NATURAL, var=None, pixels_out=No
     hs = (C.c_void_p * len(plans))(*[p._h for p in plans])
     with torch.cuda.device(coef.device):
         _check(_inv_peer(hs, len(plans), coef.data_ptr(), W, H, layout, var.data_ptr() if var is not None else None,
-                         px.data_ptr(), px.stride(0), _shares(share, len(plans)), _stream_ptr(stream)))
+                         px.data_ptr(), px.stride(0), _shares(share, len(plans)), _stream_ptr(stream, coef.device)))
     return px
 
 

@@ -12,28 +12,34 @@ namespace dctb {
 constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: x + kMagic rounds x to an integer (RNE)
 constexpr float kMagic128 = 12583040.0f;   // 1.5 * 2^23 + 128
 
-// byte `idx` of w -> 2^23 + byte as a float: (0x4B000000 | byte), one PRMT, no conversion instruction
+// byte `idx` of w -> 2^15 + byte as a float: (0x47000000 | byte << 8), one PRMT, no conversion instruction
+// (the byte lands in mantissa bits 8..15, whose weight at exponent 15 is 1)
 template <int idx> __device__ __forceinline__ float byte_to_magic(uint32_t w)
 {
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + idx));
+    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7504 + (idx << 4)));
 }
 
-// Row transform straight from the magic-biased bytes m_j = 2^23 + p_j.  The level shift and the
-// removal of the bias are folded into the first butterfly stage, every step exact:
-//   d = m_a - m_b                    = p_a - p_b
-//   s = (m_a - (2^24 + 256)) + m_b   = (p_a - 128) + (p_b - 128)      (|m_a - 2^24 - 256| < 2^24: exact)
-// i.e. the same integers the reference forms as (double)px - 128.0 (src/dct.c:115) summed pairwise.
+// bias that the magic-biased bytes leave in output 0 of a row transform, plus the level shift of its 8 samples:
+// 8 * 2^15 + 8 * 128
+constexpr float kRowBias = 263168.0f;
+
+// Row transform straight from the magic-biased bytes m_j = 2^15 + p_j.  Every value of the first two butterfly stages
+// is an integer below 2^19, so those stages are exact whatever the bias; it cancels in every difference and survives
+// only in output 0 = 8 * 2^15 + sum p_j, from which kRowBias takes it out together with the level shift:
+//   x[0] = sum (p_j - 128)                 (src/dct.c:115's (double)px - 128.0, summed)
+//   d = m_a - m_b = p_a - p_b,  s_a + s_b, s_a - s_b: as without the bias
+// One addition per sum instead of two (the bias used to be removed sum by sum).
 __device__ __forceinline__ void fdct8_row_from_bytes(float *x, uint2 raw)
 {
-    constexpr float kBias2 = 16777472.0f;   // 2 * (2^23 + 128)
     const float m0 = byte_to_magic<0>(raw.x), m1 = byte_to_magic<1>(raw.x), m2 = byte_to_magic<2>(raw.x),
                 m3 = byte_to_magic<3>(raw.x), m4 = byte_to_magic<0>(raw.y), m5 = byte_to_magic<1>(raw.y),
                 m6 = byte_to_magic<2>(raw.y), m7 = byte_to_magic<3>(raw.y);
-    const float s07 = __fadd_rn(__fadd_rn(m0, -kBias2), m7), d07 = __fsub_rn(m0, m7);
-    const float s16 = __fadd_rn(__fadd_rn(m1, -kBias2), m6), d16 = __fsub_rn(m1, m6);
-    const float s25 = __fadd_rn(__fadd_rn(m2, -kBias2), m5), d25 = __fsub_rn(m2, m5);
-    const float s34 = __fadd_rn(__fadd_rn(m3, -kBias2), m4), d34 = __fsub_rn(m3, m4);
+    const float s07 = __fadd_rn(m0, m7), d07 = __fsub_rn(m0, m7);
+    const float s16 = __fadd_rn(m1, m6), d16 = __fsub_rn(m1, m6);
+    const float s25 = __fadd_rn(m2, m5), d25 = __fsub_rn(m2, m5);
+    const float s34 = __fadd_rn(m3, m4), d34 = __fsub_rn(m3, m4);
     fdct8_tail<float, 1>(x, s07, s16, s25, s34, d07, d16, d25, d34);
+    x[0] = __fsub_rn(x[0], kRowBias);
 }
 
 // float pixel -> centred sample on the fast path (the reference's (double)p - 128.0 is exact; this rounds once)
@@ -43,16 +49,16 @@ __device__ __forceinline__ float centre_float_pixel(float p) { return __fsub_rn(
 __device__ __forceinline__ void fdct8_rowpair_from_bytes(float2 *x, uint2 a, uint2 b)
 {
     using O = Ops<float2>;
-    const float2 kBias2 = make_float2(-16777472.0f, -16777472.0f);   // -2 * (2^23 + 128)
     const float2 m0 = make_float2(byte_to_magic<0>(a.x), byte_to_magic<0>(b.x)), m1 = make_float2(byte_to_magic<1>(a.x), byte_to_magic<1>(b.x)),
                  m2 = make_float2(byte_to_magic<2>(a.x), byte_to_magic<2>(b.x)), m3 = make_float2(byte_to_magic<3>(a.x), byte_to_magic<3>(b.x)),
                  m4 = make_float2(byte_to_magic<0>(a.y), byte_to_magic<0>(b.y)), m5 = make_float2(byte_to_magic<1>(a.y), byte_to_magic<1>(b.y)),
                  m6 = make_float2(byte_to_magic<2>(a.y), byte_to_magic<2>(b.y)), m7 = make_float2(byte_to_magic<3>(a.y), byte_to_magic<3>(b.y));
-    const float2 s07 = O::add(O::add(m0, kBias2), m7), d07 = O::sub(m0, m7);
-    const float2 s16 = O::add(O::add(m1, kBias2), m6), d16 = O::sub(m1, m6);
-    const float2 s25 = O::add(O::add(m2, kBias2), m5), d25 = O::sub(m2, m5);
-    const float2 s34 = O::add(O::add(m3, kBias2), m4), d34 = O::sub(m3, m4);
+    const float2 s07 = O::add(m0, m7), d07 = O::sub(m0, m7);
+    const float2 s16 = O::add(m1, m6), d16 = O::sub(m1, m6);
+    const float2 s25 = O::add(m2, m5), d25 = O::sub(m2, m5);
+    const float2 s34 = O::add(m3, m4), d34 = O::sub(m3, m4);
     fdct8_tail<float2, 1>(x, s07, s16, s25, s34, d07, d16, d25, d34);
+    x[0] = O::add(x[0], make_float2(-kRowBias, -kRowBias));
 }
 
 // packed quantise-and-residual of two coefficients: bit-identical per lane to quant_residual

@@ -541,7 +541,8 @@ static cudaError_t launch_persistent_tma(K kernel, const FwdParams &p, cudaStrea
     q.nby = p.nblocks / p.bw;
     q.tpr = (p.bw + 31) / 32;
     const unsigned ntiles = q.nby * q.tpr;
-    const unsigned resident = (unsigned)sm_count() * (unsigned)per_sm;
+    static const int cap = getenv("DCT_CUDA_CTAS_PER_SM") ? atoi(getenv("DCT_CUDA_CTAS_PER_SM")) : 0;   // tuning aid
+    const unsigned resident = (unsigned)sm_count() * (unsigned)((cap > 0 && cap < per_sm) ? cap : per_sm);
     const unsigned want = (ntiles + kWarps - 1) / kWarps;
     const unsigned grid = want < resident ? want : resident;
     const unsigned n_segs = grid * kWarps;

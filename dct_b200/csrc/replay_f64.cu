@@ -715,6 +715,30 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
 // The block's 64 pixels are rewritten as whole rows (the unflagged ones with the values K2 already wrote).
 // Against the 8-lanes-per-block kernel: no shared-memory transposes, no shuffles, no fp32 re-flagging pass.
 // ------------------------------------------------------------------------------------------
+// Pixel (i, j) of one block in the reference's own operation order (rare: values within ~2e-9 of a .5 boundary):
+// in = the reference's dequantised values (src/quantization.c:133-151), temp[i][k] = sum_m D[m][i] * in[m][k]
+// (src/dct.c:85-92), out = sum_k temp[i][k] * D[k][j] (:95-102), both sums from 0.0 in ascending order; then the
+// pixel rule.  Returns round(out + 128) unclamped to int range [-1, 256].
+template <int LAYOUT>
+__device__ __noinline__ int exact_inverse_pixel(const ExactTables &tab, const int16_t *rec, int adaptive, double inv_two_minus_nv,
+                                                int i, int j, unsigned &ties)
+{
+    double out = 0.0;
+    for (int k = 0; k < 8; ++k) {
+        double temp = 0.0;
+        for (int m = 0; m < 8; ++m) {
+            const int nat = 8 * m + k;
+            const int q = rec[LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[nat] : nat];
+            temp = __dadd_rn(temp, __dmul_rn(tab.D[m * 8 + i], exact_dequant(tab, adaptive, inv_two_minus_nv, nat, q)));
+        }
+        out = __dadd_rn(out, __dmul_rn(temp, tab.D[k * 8 + j]));
+    }
+    const double val = __dadd_rn(out, 128.0);
+    const double rr = round_half_away(val);
+    ties += near_half(val);
+    return rr < 0.0 ? -1 : (rr > 255.0 ? 256 : (int)rr);
+}
+
 constexpr double kMagic52_128r = 6755399441055744.0 + 128.0;   // 1.5 * 2^52 + 128
 
 struct LaneInvShared {
@@ -794,7 +818,7 @@ __global__ void __launch_bounds__(kLaneThreads, 2) k_replay_inv_lane(const Repla
         // 1e-9: the tie-accounting margin; 8 * 2^-53 * bound: fp64 butterfly + the reference's own rounding
         const double thr = 0.5 - (2e-9 + bound64 * 8.9e-16);
         const bool sane = bound64 < 1e12;
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
             uint32_t lo = 0, hi = 0;
 #pragma unroll
@@ -803,24 +827,8 @@ __global__ void __launch_bounds__(kLaneThreads, 2) k_replay_inv_lane(const Repla
                 const double t = x + kMagic52_128r;           // low mantissa bits: round-to-nearest(x) + 128
                 const double e = x - (t - kMagic52_128r);
                 int px = __double2loint(t);
-                if (!(fabs(e) < thr) || !sane) {
-                    // exact replay of pixel (i, j): temp[i][k] = sum_m D[m][i] * in[m][k] (src/dct.c:85-92),
-                    // out = sum_k temp[i][k] * D[k][j] (:95-102); in = the reference's dequantised values
-                    double out = 0.0;
-                    for (int k = 0; k < 8; ++k) {
-                        double temp = 0.0;
-                        for (int m = 0; m < 8; ++m) {
-                            const int nat = 8 * m + k;
-                            const int q = rec[LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[nat] : nat];
-                            temp = __dadd_rn(temp, __dmul_rn(tab.D[m * 8 + i], exact_dequant(tab, p.adaptive, inv_two_minus_nv, nat, q)));
-                        }
-                        out = __dadd_rn(out, __dmul_rn(temp, tab.D[k * 8 + j]));
-                    }
-                    const double val = __dadd_rn(out, 128.0);
-                    const double rr = round_half_away(val);
-                    ties += near_half(val);
-                    px = rr < 0.0 ? 0 : (rr > 255.0 ? 255 : (int)rr);
-                }
+                if (!(fabs(e) < thr) || !sane)                // within band64 of a .5 boundary: the reference's own arithmetic
+                    px = exact_inverse_pixel<LAYOUT>(tab, rec, p.adaptive, inv_two_minus_nv, i, j, ties);
                 px = px < 0 ? 0 : (px > 255 ? 255 : px);
                 if (j < 4) lo |= (uint32_t)px << (8 * j);
                 else hi |= (uint32_t)px << (8 * (j - 4));
@@ -937,9 +945,9 @@ cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s)
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s)
 {
     if (p.worklist != nullptr) {                         // the fused kernel ran: one lane per flagged block
-        // one CTA per ~1024 blocks of the plane (a tenth of them flagged would keep its four warps busy), at most 4 per SM
+        // one CTA per ~1024 blocks of the plane (a tenth of them flagged would keep its four warps busy), at most 2 per SM
         unsigned grid = (p.nblocks + 1023) / 1024;
-        grid = grid < 16u ? 16u : (grid > 148u * 4u ? 148u * 4u : grid);
+        grid = grid < 16u ? 16u : (grid > 148u * 2u ? 148u * 2u : grid);     // two CTAs per SM are resident (registers)
         if (p.layout == LAYOUT_ZIGZAG) k_replay_inv_lane<LAYOUT_ZIGZAG><<<grid, kLaneThreads, 0, s>>>(p);
         else k_replay_inv_lane<LAYOUT_NATURAL><<<grid, kLaneThreads, 0, s>>>(p);
         return cudaGetLastError();

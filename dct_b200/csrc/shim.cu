@@ -421,8 +421,11 @@ int collect_stats(dct_cuda_plan *p, dct_cuda_stats *out, cudaStream_t user_strea
     for (int l = 0; l < kLanes; ++l) {
         Lane &ln = p->lane[l];
         CU_TRY(cudaStreamSynchronize(ln.stream));
-        CU_TRY(cudaMemcpy(&p->h_ctr[l], ln.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost));
-        CU_TRY(cudaMemset(ln.d_ctr, 0, sizeof(Counters)));
+        CU_TRY(cudaMemcpyAsync(&p->h_ctr[l], ln.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ln.stream));
+        // reset the statistics only (wl_count / done_ctas belong to K3, which re-zeroes them itself), on the lane's own
+        // stream: a memset on the legacy default stream is not ordered against work queued on non-blocking streams
+        CU_TRY(cudaMemsetAsync(&ln.d_ctr->replayed, 0, sizeof(Counters) - offsetof(Counters, replayed), ln.stream));
+        CU_TRY(cudaStreamSynchronize(ln.stream));
         st.blocks += ln.blocks;
         st.replayed_blocks += p->h_ctr[l].replayed;
         st.near_ties += p->h_ctr[l].near_ties;
@@ -661,8 +664,29 @@ static int strip_rows(int W, int H, int n = 8)
 
 // `ragged`: W and H are any positive sizes; the strips are completed to whole blocks on the device by
 // replicating the last column / row (planar.cu), so the records cover ceil(W/n) x ceil(H/n) blocks
+// waits for everything queued on the plan's lanes (after a failure half way through a plane: the strips already
+// queued still read / write the caller's buffers)
+static void drain_lanes(dct_cuda_plan *p)
+{
+    if (!p) return;
+    DeviceGuard g(p->device);
+    for (int l = 0; l < kLanes; ++l)
+        if (p->lane[l].stream) cudaStreamSynchronize(p->lane[l].stream);
+}
+
+static int fwd_host_queue(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H, void *coef, int layout,
+                          double *var, int elem, bool ragged, bool rec8);
+
 static int fwd_host_async(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H, void *coef, int layout,
                           double *var, int elem, bool ragged = false, bool rec8 = false)
+{
+    const int rc = fwd_host_queue(p, px, pitch, W, H, coef, layout, var, elem, ragged, rec8);
+    if (rc) drain_lanes(p);
+    return rc;
+}
+
+static int fwd_host_queue(dct_cuda_plan *p, const uint8_t *px, size_t pitch, int W, int H, void *coef, int layout,
+                          double *var, int elem, bool ragged, bool rec8)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     if (rec8 && !p->fits_i8)
@@ -747,8 +771,19 @@ extern "C" int dct_cuda_fwd_quant_u8(dct_cuda_plan *p, const uint8_t *px, size_t
     return dct_cuda_plan_wait(p, stats);
 }
 
+static int inv_host_queue(dct_cuda_plan *p, const void *coef, int W, int H, int layout, const double *var, uint8_t *px,
+                          size_t pitch, bool ragged, bool rec8);
+
 static int inv_host_async(dct_cuda_plan *p, const void *coef, int W, int H, int layout, const double *var, uint8_t *px,
                           size_t pitch, bool ragged = false, bool rec8 = false)
+{
+    const int rc = inv_host_queue(p, coef, W, H, layout, var, px, pitch, ragged, rec8);
+    if (rc) drain_lanes(p);
+    return rc;
+}
+
+static int inv_host_queue(dct_cuda_plan *p, const void *coef, int W, int H, int layout, const double *var, uint8_t *px,
+                          size_t pitch, bool ragged, bool rec8)
 {
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     const int n = p->n, nn = n * n;
@@ -932,7 +967,7 @@ extern "C" int dct_cuda_rle_count_dev(dct_cuda_plan *p, const int16_t *d_coef, s
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     if (p->n != 8) return fail(DCT_CUDA_EINVAL, "run-length symbols are implemented for 8x8 records only");
     if ((nblocks && !d_coef) || !d_offsets) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
-    if (nblocks > (1u << 26)) return fail(DCT_CUDA_EINVAL, "at most 2^26 records per call (32-bit symbol offsets)");
+    if (nblocks >= (1u << 26)) return fail(DCT_CUDA_EINVAL, "fewer than 2^26 records per call (32-bit symbol offsets: 64 symbols per record)");
     if ((uintptr_t)d_coef % 16) return fail(DCT_CUDA_EINVAL, "coefficients must be 16-byte aligned");
     DeviceGuard g(p->device);
     std::lock_guard<std::mutex> plan_lock(p->mu);
@@ -964,7 +999,7 @@ extern "C" int dct_cuda_rle_emit_dev(dct_cuda_plan *p, const int16_t *d_coef, si
     if (!p) return fail(DCT_CUDA_EINVAL, "NULL plan");
     if (nblocks == 0) return DCT_CUDA_OK;
     if (!d_coef || !d_offsets || !d_symbols) return fail(DCT_CUDA_EINVAL, "NULL data pointer");
-    if (nblocks > (1u << 26)) return fail(DCT_CUDA_EINVAL, "at most 2^26 records per call (32-bit symbol offsets)");
+    if (nblocks >= (1u << 26)) return fail(DCT_CUDA_EINVAL, "fewer than 2^26 records per call (32-bit symbol offsets: 64 symbols per record)");
     if (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG) return fail(DCT_CUDA_EINVAL, "bad layout %d", layout);
     if (((uintptr_t)d_coef % 16) || ((uintptr_t)d_symbols % 8)) return fail(DCT_CUDA_EINVAL, "misaligned buffer");
     if (nblocks == 0) return DCT_CUDA_OK;

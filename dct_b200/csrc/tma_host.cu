@@ -1,6 +1,7 @@
 // tma_host.cu -- tensor maps for the bulk-tensor tile copies of K1 / K2 (see tma.cuh).
 // cuTensorMapEncodeTiled is reached through cudaGetDriverEntryPoint, so libdct_cuda keeps its single
 // link-time dependency (the static CUDA runtime) and still loads on a box without a driver.
+#include <cstdlib>
 #include <mutex>
 
 #include "tma.cuh"
@@ -31,6 +32,14 @@ EncodeTiledFn encode_fn()
 
 }  // namespace
 
+// L2 fetch granularity of the tensor maps (tuning aid: DCT_CUDA_L2PROMO = 0 none, 64, 128, 256; default 256)
+static CUtensorMapL2promotion l2_promotion()
+{
+    static const int v = getenv("DCT_CUDA_L2PROMO") ? atoi(getenv("DCT_CUDA_L2PROMO")) : 256;
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                  : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
 bool tma_available() { return encode_fn() != nullptr; }
 
 cudaError_t make_pixel_map(CUtensorMap *map, const void *base, long long pitch, int W, int H)
@@ -41,7 +50,7 @@ cudaError_t make_pixel_map(CUtensorMap *map, const void *base, long long pitch, 
     const cuuint64_t strides[1] = {(cuuint64_t)pitch};
     const cuuint32_t box[2] = {256, 8}, estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(),
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
@@ -54,7 +63,7 @@ cudaError_t make_record_map(CUtensorMap *map, const void *base, uint32_t nblocks
     const cuuint64_t strides[1] = {128};
     const cuuint32_t box[2] = {128, (cuuint32_t)rows}, estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(),
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }

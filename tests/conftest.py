@@ -18,6 +18,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+    config.addinivalue_line("markers", "multigpu: needs two or more CUDA devices; skipped (not passed) on a smaller box")
 
 
 @pytest.fixture(scope="session")

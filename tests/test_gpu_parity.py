@@ -641,8 +641,20 @@ def test_adaptive_round_trip_reconstructs(api, oracle):
     assert set(np.unique(rec)) <= {126, 127, 128, 129, 130}
 
 
-def test_multi_gpu_entry_point_with_available_devices(api, oracle):
-    n = min(api.device_count(), 8)
+def _need_devices(api, n):
+    if api.device_count() < n:
+        pytest.skip(f"needs {n} CUDA devices, {api.device_count()} visible (run under `gpurun --gpus {n}`)")
+
+
+N_DEVICES = [1, pytest.param(2, marks=pytest.mark.multigpu), pytest.param(4, marks=pytest.mark.multigpu),
+             pytest.param(8, marks=pytest.mark.multigpu)]
+
+
+@pytest.mark.parametrize("n", N_DEVICES)
+def test_multi_gpu_entry_point(api, oracle, n):
+    """dct_cuda_*_multi: block-row ranges of one host plane dealt to one plan per GPU.  n = 1 is the degenerate case;
+    the multigpu cases SKIP (not pass) when the box has fewer devices."""
+    _need_devices(api, n)
     rng = np.random.default_rng(41)
     px = rng.integers(0, 256, size=(1024, 1024), dtype=np.uint8)
     ctxs = [Ctx(api, 50, 1, device=g) for g in range(n)]
@@ -829,11 +841,12 @@ def test_rgb_frames_encode_and_decode_like_the_oracle_pipeline(api, oracle, shap
 # ---------------------------------------------------------------------------------------------
 # NVLink peers working on one GPU's memory
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", N_DEVICES[:3])
 @pytest.mark.parametrize("adaptive,layout", [(0, 0), (1, 1)])
-def test_peer_calls_on_the_available_gpus(api, oracle, torch, adaptive, layout):
-    """Plane and records resident on GPU 0; every other visible GPU works on that memory in place.  With one
-    GPU this is the degenerate case (the owner does everything); run with >= 2 GPUs for the NVLink path."""
-    n = min(api.device_count(), 4)
+def test_peer_calls(api, oracle, torch, adaptive, layout, n):
+    """Plane and records resident on GPU 0; every other GPU works on that memory in place.  n = 1 is the degenerate
+    case (the owner does everything); the NVLink path proper is n >= 2, which SKIPS on a box with fewer devices."""
+    _need_devices(api, n)
     H, W = 1024, 2048
     rng = np.random.default_rng(77 + adaptive)
     px = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
@@ -866,10 +879,11 @@ def test_peer_calls_on_the_available_gpus(api, oracle, torch, adaptive, layout):
             c.__exit__()
 
 
-def test_peer_default_split_for_exact_path_plans(api, oracle, torch):
+@pytest.mark.parametrize("n", N_DEVICES[:3])
+def test_peer_default_split_for_exact_path_plans(api, oracle, torch, n):
     """A table entry below 1.0 puts the plan on the fp64 exact path (arithmetic-bound): the default deals the rows
     out evenly, and the result is the reference's bit for bit all the same."""
-    n = min(api.device_count(), 4)
+    _need_devices(api, n)
     H, W = 256, 512
     px = np.random.default_rng(12).integers(0, 256, size=(H, W), dtype=np.uint8)
     Q = oracle.quant_table(50)
@@ -994,3 +1008,31 @@ def test_int8_records_are_refused_when_a_value_could_overflow(api, oracle):
         Q = oracle.quant_table(60)
         want, _ = oracle.dequant_idct_plane(c8.astype(np.int16), 320, 240, Q, 0, 0, None, nthreads=4)
         assert np.array_equal(cx.plan.dequant_idct_i8(c8, 320, 240), want)
+
+
+@pytest.mark.parametrize("n,ok", [(4, True), (16, True), (3, False), (6, False)])
+def test_int8_records_with_other_block_sizes(api, oracle, n, ok):
+    """The int8 record calls move whole 16-value groups: offered when n*n is a multiple of 16 (n = 4: the custom
+    table of src/quantization.c:78-96 starts at 8 >= 4 * 128 / 127.5), refused with an error otherwise."""
+    rng = np.random.default_rng(500 + n)
+    H, W = n * 9, n * 9                                    # 81 blocks: an odd count, records end off any 16-byte grid for odd n
+    px = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
+    d, q = api.dct_init(n), api.quant_init(n, 50, 0)
+    plan = api.Plan(d, q)
+    try:
+        if not ok:
+            with pytest.raises(api.DctCudaError, match="multiple of 16"):
+                plan.fwd_quant_i8(px)
+            with pytest.raises(api.DctCudaError, match="multiple of 16"):
+                plan.dequant_idct_i8(np.zeros((81, n * n), np.int8), W, H)
+            return
+        Q = oracle.quant_table(50, n)
+        want_c, _, _ = oracle.fwd_quant_plane_n(n, px, Q, 0, 0, nthreads=2)
+        want_p, _ = oracle.dequant_idct_plane_n(n, want_c, W, H, Q, 0, 0, None, nthreads=2)
+        assert plan.records_fit_i8 and np.abs(want_c).max() <= 127
+        c8 = plan.fwd_quant_i8(px)
+        assert c8.shape == (81, n * n) and np.array_equal(c8.astype(np.int16), want_c)
+        assert np.array_equal(plan.dequant_idct_i8(c8, W, H), want_p)
+    finally:
+        plan.close()
+        api.dct_free(d), api.quant_free(q)
