@@ -214,58 +214,71 @@ struct alignas(64) InvTmaParams {
     uint32_t seg_cap;          // worklist entries per segment
 };
 
-constexpr int kInStages = 2;
-constexpr int kTmaInBytes = 4096;
-constexpr int kTmaSmemBytes = 1024 /* alignment slack */ + kWarps * kInStages * kTmaInBytes + kWarps * 32;
+constexpr int kTmaInBytes = 4096;                                   // per warp and stage: 32 records
+constexpr int kTmaCtlBytes = 64;                                    // per warp: up to 8 mbarriers
 
-template <int LAYOUT, bool ADAPTIVE>
-__global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8_tma(const __grid_constant__ InvTmaParams P)
+// geometry of one kernel variant: warps per CTA, CTAs per SM the register budget is cut for, record stages per warp
+template <int WARPS, int MIN_CTAS, int STAGES> struct TmaCfg {
+    static constexpr int kWarpsT = WARPS, kMinCtas = MIN_CTAS, kStages = STAGES, kThreadsT = 32 * WARPS;
+    static constexpr int kSmem = 1024 /* alignment slack */ + WARPS * (STAGES * kTmaInBytes + kTmaCtlBytes);
+    static_assert(STAGES >= 2 && STAGES <= 8, "stages");
+};
+
+template <int LAYOUT, bool ADAPTIVE, typename CFG>
+__global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_u8_tma(const __grid_constant__ InvTmaParams P)
 {
+    constexpr int kW = CFG::kWarpsT, kS = CFG::kStages;
     extern __shared__ uint8_t smem_raw[];
     const InvParams &p = P.f;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // tells the compiler it is warp-uniform
     uint8_t *sm = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
-    uint8_t *in_p = sm + warp * (kInStages * kTmaInBytes);
-    uint32_t *ctl_p = reinterpret_cast<uint32_t *>(sm + kWarps * kInStages * kTmaInBytes + warp * 32);
+    uint8_t *in_p = sm + warp * (kS * kTmaInBytes);
+    uint32_t *ctl_p = reinterpret_cast<uint32_t *>(sm + kW * kS * kTmaInBytes + warp * kTmaCtlBytes);
     const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in_p);
-    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(ctl_p);           // two 8-byte mbarriers
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(ctl_p);           // kS 8-byte mbarriers
 
     if (lane == 0) {
-        tma::mbar_init(bar_s, 1);
-        tma::mbar_init(bar_s + 8, 1);
+#pragma unroll
+        for (int i = 0; i < kS; ++i) tma::mbar_init(bar_s + 8 * i, 1);
         tma::fence_barrier_init();
     }
     __syncwarp();
+    pdl_launch_dependents();    // the replay kernel may start its prologue while this grid runs
+    pdl_wait();                 // everything below touches memory the previous kernels on the stream wrote or read
 
-    uint32_t ty, tx;            // block row and tile-in-row of the next tile to fetch
+    // (ty, tx): block row and tile-in-row of the tile being transformed; (fy, fx): of the next tile to fetch, kS - 1 ahead
+    uint32_t ty, tx;
     {
-        const uint32_t t = blockIdx.x * kWarps + warp;
+        const uint32_t t = blockIdx.x * kW + warp;
         ty = t / P.tpr;
         tx = t - ty * P.tpr;
     }
-    auto issue = [&](uint32_t stage) {
-        if (lane == 0) {
-            tma::mbar_expect_tx(bar_s + stage * 8, kTmaInBytes);
-            tma::load_2d(in_s + stage * kTmaInBytes, &P.map_rec, 0, (int)(ty * p.bw + tx * 32), bar_s + stage * 8);
+    uint32_t fy = ty, fx = tx, fstage = 0;
+    auto fetch = [&]() {        // fetch tile (fy, fx) into stage fstage, then advance both
+        if (fy < P.nby && lane == 0) {
+            tma::mbar_expect_tx(bar_s + fstage * 8, kTmaInBytes);
+            tma::load_2d(in_s + fstage * kTmaInBytes, &P.map_rec, 0, (int)(fy * p.bw + fx * 32), bar_s + fstage * 8);
         }
+        fx += P.step_tx;
+        fy += P.step_ty;
+        if (fx >= P.tpr) fx -= P.tpr, ++fy;
+        fstage = fstage + 1 == kS ? 0 : fstage + 1;
     };
-    if (ty < P.nby) issue(0);
+#pragma unroll
+    for (int i = 0; i < kS - 1; ++i) fetch();
     const uint32_t swz = (lane & 7) << 4;
     uint32_t wl_n = 0;          // entries this warp has appended to its worklist segment
-    const uint32_t gwarp = blockIdx.x * kWarps + warp;
+    const uint32_t gwarp = blockIdx.x * kW + warp;
 
-    for (uint32_t it = 0; ty < P.nby; ++it) {
-        const uint32_t stage = it & 1;
+    uint32_t stage = 0, phase = 0;
+    while (ty < P.nby) {
         const uint32_t bx0 = tx * 32;
         const uint32_t warp_base = ty * p.bw + bx0;
         const uint32_t nvalid = min(32u, p.bw - bx0);
         uint8_t *dst = p.px + (long long)ty * 8 * p.pitch + (long long)(bx0 + lane) * 8;
-        tx += P.step_tx;
-        ty += P.step_ty;
-        if (tx >= P.tpr) tx -= P.tpr, ++ty;
-        if (ty < P.nby) issue(stage ^ 1);
-        tma::mbar_wait(bar_s + stage * 8, (it >> 1) & 1);
+        fetch();                                                  // into the stage the previous iteration consumed
+        tma::mbar_wait(bar_s + stage * 8, phase);
 
         const uint32_t b = warp_base + lane;
         const bool valid = lane < nvalid;
@@ -276,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8_tma(const __gri
             const uint4 t = *reinterpret_cast<const uint4 *>(rec + ((j << 4) ^ swz));
             w[4 * j] = t.x, w[4 * j + 1] = t.y, w[4 * j + 2] = t.z, w[4 * j + 3] = t.w;
         }
-        __syncwarp();           // every lane has its record: the fetch after next may overwrite this stage
+        __syncwarp();           // every lane has its record: the next fetch overwrites this stage
 
         const bool flag = inv_block<LAYOUT, ADAPTIVE>(p, w, valid, b, dst);
         const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
@@ -284,6 +297,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8_tma(const __gri
             if (flag && valid) p.worklist[(size_t)gwarp * P.seg_cap + wl_n + __popc(ballot & ((1u << lane) - 1u))] = b;
             wl_n += __popc(ballot);
         }
+        tx += P.step_tx;
+        ty += P.step_ty;
+        if (tx >= P.tpr) tx -= P.tpr, ++ty;
+        if (++stage == kS) stage = 0, phase ^= 1;
     }
     if (lane == 0) P.seg_count[gwarp] = wl_n;     // <= 32 per tile visited, < seg_cap by construction
 }
@@ -409,30 +426,30 @@ static int sm_count_k2()
     return n;
 }
 
-template <typename K>
+template <typename CFG, typename K>
 static cudaError_t launch_persistent_tma(K kernel, const InvParams &p, cudaStream_t s, WorklistSegments *segments)
 {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+    constexpr int kW = CFG::kWarpsT;
+    cudaError_t e = ensure_smem_attributes(reinterpret_cast<const void *>(kernel), CFG::kSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    static int per_sm = 0;   // same for every variant: identical launch bounds and shared memory
+    static int per_sm = 0;   // one instance per CFG; the same for every variant of it: identical launch bounds and shared memory
     if (per_sm == 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, kTmaSmemBytes) != cudaSuccess || n < 1) n = 1;
-        per_sm = n;
-        if (getenv("DCT_CUDA_DEBUG")) fprintf(stderr, "libdct_cuda: K2 (bulk tensor): %d CTAs/SM, %d B smem\n", n, kTmaSmemBytes);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, CFG::kThreadsT, CFG::kSmem) != cudaSuccess || n < 1) n = 1;
+        per_sm = n < CFG::kMinCtas ? n : CFG::kMinCtas;
+        if (getenv("DCT_CUDA_DEBUG"))
+            fprintf(stderr, "libdct_cuda: K2 (bulk tensor, %d warps, %d stages): %d CTAs/SM (occupancy %d), %d B smem\n", kW, CFG::kStages,
+                    per_sm, n, CFG::kSmem);
     }
     InvTmaParams q;
     q.f = p;
     q.nby = p.nblocks / p.bw;
     q.tpr = (p.bw + 31) / 32;
     const unsigned ntiles = q.nby * q.tpr;
-    static const int cap = getenv("DCT_CUDA_CTAS_PER_SM") ? atoi(getenv("DCT_CUDA_CTAS_PER_SM")) : 0;   // tuning aid
-    const unsigned resident = (unsigned)sm_count_k2() * (unsigned)((cap > 0 && cap < per_sm) ? cap : per_sm);
-    const unsigned want = (ntiles + kWarps - 1) / kWarps;
+    const unsigned resident = (unsigned)sm_count_k2() * (unsigned)per_sm;
+    const unsigned want = (ntiles + kW - 1) / kW;
     const unsigned grid = want < resident ? want : resident;
-    const unsigned n_segs = grid * kWarps;
+    const unsigned n_segs = grid * kW;
     q.step_ty = n_segs / q.tpr;
     q.step_tx = n_segs - q.step_ty * q.tpr;
     const unsigned tiles_per_warp = (ntiles + n_segs - 1) / n_segs;
@@ -441,8 +458,17 @@ static cudaError_t launch_persistent_tma(K kernel, const InvParams &p, cudaStrea
     if (n_segs > kMaxWorklistSegments - 128 || q.seg_cap < tiles_per_warp * 32 || p.seg_count == nullptr) return cudaErrorInvalidValue;
     if ((e = make_record_map(&q.map_rec, p.coef, p.nblocks, 32)) != cudaSuccess) return e;
     if (segments) *segments = WorklistSegments{n_segs, q.seg_cap, 0};
-    kernel<<<grid, kThreads, kTmaSmemBytes, s>>>(q);
-    return cudaGetLastError();
+    return launch_pdl(kernel, grid, CFG::kThreadsT, CFG::kSmem, s, q);
+}
+
+template <typename CFG>
+static cudaError_t launch_k2_tma(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments)
+{
+    if (layout == LAYOUT_ZIGZAG)
+        return adaptive ? launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, true, CFG>, p, s, segments)
+                        : launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, false, CFG>, p, s, segments);
+    return adaptive ? launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_NATURAL, true, CFG>, p, s, segments)
+                    : launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_NATURAL, false, CFG>, p, s, segments);
 }
 
 static bool tma_eligible(const InvParams &p)
@@ -459,11 +485,15 @@ cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive,
     if (segments) *segments = WorklistSegments{0, 0, 0};
     if (p.nblocks == 0) return cudaSuccess;
     if (tma_eligible(p)) {
-        if (layout == LAYOUT_ZIGZAG)
-            return adaptive ? launch_persistent_tma(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, true>, p, s, segments)
-                            : launch_persistent_tma(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, false>, p, s, segments);
-        return adaptive ? launch_persistent_tma(k_dequant_idct_u8_tma<LAYOUT_NATURAL, true>, p, s, segments)
-                        : launch_persistent_tma(k_dequant_idct_u8_tma<LAYOUT_NATURAL, false>, p, s, segments);
+        // Geometry (measured on B200, 64 4K frames, profiles/r2_geometry.md): ONE CTA of 16 warps per SM with 128
+        // registers per thread beats 3 x 8 warps at 80 registers (0.91 against 0.83 of the copy peak).
+        // DCT_CUDA_K2_GEOMETRY (tuning aid): 1 = 12 warps x 1 CTA, 2 = 8 warps x 3 CTAs.
+        static const int variant = getenv("DCT_CUDA_K2_GEOMETRY") ? atoi(getenv("DCT_CUDA_K2_GEOMETRY")) : 0;
+        switch (variant) {
+        case 1: return launch_k2_tma<TmaCfg<12, 1, 2>>(p, layout, adaptive, s, segments);
+        case 2: return launch_k2_tma<TmaCfg<8, 3, 2>>(p, layout, adaptive, s, segments);
+        default: return launch_k2_tma<TmaCfg<16, 1, 2>>(p, layout, adaptive, s, segments);
+        }
     }
     const unsigned grid = (p.nblocks + kThreads - 1) / kThreads;
     if (layout == LAYOUT_ZIGZAG) {

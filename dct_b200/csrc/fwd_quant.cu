@@ -267,60 +267,73 @@ struct alignas(64) FwdTmaParams {
 
 constexpr int kTmaOutBytes = 4096;                                  // per warp: 32 records
 constexpr int kTmaInBytes = 2048;                                   // per warp and stage: 8 rows x 256 B
-constexpr int kTmaSmemBytes = 1024 /* alignment slack */ + kWarps * (kTmaOutBytes + kInStages * kTmaInBytes) + kWarps * 32;
+constexpr int kTmaCtlBytes = 64;                                    // per warp: up to 7 mbarriers, then the worklist count
 
-template <int LAYOUT, bool ADAPTIVE, bool UNIFORM>
-__global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8_tma(const __grid_constant__ FwdTmaParams P)
+// geometry of one kernel variant: warps per CTA, CTAs per SM the register budget is cut for, input stages per warp
+template <int WARPS, int MIN_CTAS, int STAGES> struct TmaCfg {
+    static constexpr int kWarpsT = WARPS, kMinCtas = MIN_CTAS, kStages = STAGES, kThreadsT = 32 * WARPS;
+    static constexpr int kSmem = 1024 /* alignment slack */ + WARPS * (kTmaOutBytes + STAGES * kTmaInBytes + kTmaCtlBytes);
+    static_assert(STAGES >= 2 && STAGES <= 7, "stages");
+};
+
+template <int LAYOUT, bool ADAPTIVE, bool UNIFORM, typename CFG>
+__global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_fwd_quant_u8_tma(const __grid_constant__ FwdTmaParams P)
 {
+    constexpr int kW = CFG::kWarpsT, kS = CFG::kStages;
     extern __shared__ uint8_t smem_raw[];
     const FwdParams &p = P.f;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // tells the compiler it is warp-uniform
-    // carve: [8 x 4 KB record stages, 1024-aligned for the swizzle][8 x 2 x 2 KB pixel stages][8 x (2 mbarriers + count)]
+    // carve: [record stages, 1024-aligned for the swizzle][pixel stages][per warp: mbarriers + count]
     uint8_t *sm = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     uint8_t *out_p = sm + warp * kTmaOutBytes;
-    uint8_t *in_p = sm + kWarps * kTmaOutBytes + warp * (kInStages * kTmaInBytes);
-    uint32_t *ctl_p = reinterpret_cast<uint32_t *>(sm + kWarps * (kTmaOutBytes + kInStages * kTmaInBytes) + warp * 32);
+    uint8_t *in_p = sm + kW * kTmaOutBytes + warp * (kS * kTmaInBytes);
+    uint32_t *ctl_p = reinterpret_cast<uint32_t *>(sm + kW * (kTmaOutBytes + kS * kTmaInBytes) + warp * kTmaCtlBytes);
+    uint32_t *const cnt_p = ctl_p + 2 * kS;                                       // after the mbarriers
     const uint32_t out_s = (uint32_t)__cvta_generic_to_shared(out_p), in_s = (uint32_t)__cvta_generic_to_shared(in_p);
-    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(ctl_p);           // two 8-byte mbarriers, then the count
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(ctl_p);           // kS 8-byte mbarriers
 
     if (lane == 0) {
-        tma::mbar_init(bar_s, 1);
-        tma::mbar_init(bar_s + 8, 1);
-        ctl_p[4] = 0;                        // entries this warp has appended to its worklist segment
+#pragma unroll
+        for (int i = 0; i < kS; ++i) tma::mbar_init(bar_s + 8 * i, 1);
+        *cnt_p = 0;                          // entries this warp has appended to its worklist segment
         tma::fence_barrier_init();
     }
     __syncwarp();
+    pdl_launch_dependents();    // the replay kernel may start its prologue while this grid runs
+    pdl_wait();                 // everything below touches memory the previous kernels on the stream wrote or read
 
-    // (ty, tx): block row and tile-in-row of the next tile to fetch
+    // (ty, tx): block row and tile-in-row of the tile being transformed; (fy, fx): of the next tile to fetch, kS - 1 ahead
     uint32_t ty, tx;
     {
-        const uint32_t t = blockIdx.x * kWarps + warp;
+        const uint32_t t = blockIdx.x * kW + warp;
         ty = t / P.tpr;
         tx = t - ty * P.tpr;
     }
-    auto issue = [&](uint32_t stage) {
-        if (lane == 0) {
-            tma::mbar_expect_tx(bar_s + stage * 8, kTmaInBytes);
-            tma::load_2d(in_s + stage * kTmaInBytes, &P.map_px, (int)(tx * 256), (int)(ty * 8), bar_s + stage * 8);
+    uint32_t fy = ty, fx = tx, fstage = 0;
+    auto fetch = [&]() {        // fetch tile (fy, fx) into stage fstage, then advance both
+        if (fy < P.nby && lane == 0) {
+            tma::mbar_expect_tx(bar_s + fstage * 8, kTmaInBytes);
+            tma::load_2d(in_s + fstage * kTmaInBytes, &P.map_px, (int)(fx * 256), (int)(fy * 8), bar_s + fstage * 8);
         }
+        fx += P.step_tx;
+        fy += P.step_ty;
+        if (fx >= P.tpr) fx -= P.tpr, ++fy;
+        fstage = fstage + 1 == kS ? 0 : fstage + 1;
     };
-    if (ty < P.nby) issue(0);
+#pragma unroll
+    for (int i = 0; i < kS - 1; ++i) fetch();
     // my chunk j goes to 16-byte slot j ^ (lane & 7) of my 128-byte row
     uint8_t *const my_out = out_p + lane * 128;
     const uint32_t swz = (lane & 7) << 4;
 
-    for (uint32_t it = 0; ty < P.nby; ++it) {
-        const uint32_t stage = it & 1;
+    uint32_t stage = 0, phase = 0;
+    while (ty < P.nby) {
         const uint32_t bx0 = tx * 32;
         const uint32_t warp_base = ty * p.bw + bx0;               // first record of this tile
         const uint32_t nvalid = min(32u, p.bw - bx0);
-        // advance to the next tile and fetch it
-        tx += P.step_tx;
-        ty += P.step_ty;
-        if (tx >= P.tpr) tx -= P.tpr, ++ty;
-        if (ty < P.nby) issue(stage ^ 1);
-        tma::mbar_wait(bar_s + stage * 8, (it >> 1) & 1);
+        fetch();                                                  // into the stage the previous iteration consumed
+        tma::mbar_wait(bar_s + stage * 8, phase);
 
         const uint32_t b = warp_base + lane;
         const bool valid = lane < nvalid;
@@ -349,10 +362,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8_tma(const __grid_c
         if (ballot != 0) {
             // The warp appends to its own segment of the worklist (no global atomic); lane 8 writes the entry,
             // lanes 0-7 copy one pixel row each from the input stage to the 64 bytes that go with it (read by K3).
-            const uint32_t gwarp = blockIdx.x * kWarps + warp;
-            uint32_t wl_n = ctl_p[4];
+            const uint32_t gwarp = blockIdx.x * kW + warp;
+            uint32_t wl_n = *cnt_p;
             __syncwarp();
-            if (lane == 0) ctl_p[4] = wl_n + __popc(ballot);
+            if (lane == 0) *cnt_p = wl_n + __popc(ballot);
             for (unsigned todo = ballot; todo != 0; todo &= todo - 1, ++wl_n) {
                 const unsigned f = __ffs(todo) - 1;
                 if (lane < 8) {
@@ -364,10 +377,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_fwd_quant_u8_tma(const __grid_c
                 }
             }
         }
-        __syncwarp();   // every lane is done with this input stage: the fetch after next may overwrite it
+        __syncwarp();   // every lane is done with this input stage: the next fetch overwrites it
+        tx += P.step_tx;
+        ty += P.step_ty;
+        if (tx >= P.tpr) tx -= P.tpr, ++ty;
+        if (++stage == kS) stage = 0, phase ^= 1;
     }
     if (lane == 0) {
-        p.seg_count[blockIdx.x * kWarps + warp] = ctl_p[4];
+        p.seg_count[blockIdx.x * kW + warp] = *cnt_p;
         tma::store_wait_read();               // shared memory must outlive the last store's reads
     }
 }
@@ -483,9 +500,7 @@ static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t 
     // NB: K is the same function-pointer type for every kernel variant, so this template has ONE instance and its
     // statics are shared by all variants: nothing per-kernel may be cached here (the attributes are set on every launch;
     // per_sm is the same for all variants: identical launch bounds and shared memory).
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = ensure_smem_attributes(reinterpret_cast<const void *>(kernel), kSmemBytes);
     if (e != cudaSuccess) return e;
     static int per_sm = 0;   // resident CTAs per SM for this instantiation (3 by design: registers and shared memory)
     if (per_sm == 0) {
@@ -522,30 +537,30 @@ static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t 
 }
 
 // bulk-tensor kernel: persistent grid like the cp.async one, tiles = 32 blocks of one block row
-template <typename K>
+template <typename CFG, typename K>
 static cudaError_t launch_persistent_tma(K kernel, const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
 {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+    constexpr int kW = CFG::kWarpsT;
+    cudaError_t e = ensure_smem_attributes(reinterpret_cast<const void *>(kernel), CFG::kSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    static int per_sm = 0;   // same for every variant: identical launch bounds and shared memory
+    static int per_sm = 0;   // one instance per CFG; the same for every variant of it: identical launch bounds and shared memory
     if (per_sm == 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, kTmaSmemBytes) != cudaSuccess || n < 1) n = 1;
-        per_sm = n;
-        if (getenv("DCT_CUDA_DEBUG")) fprintf(stderr, "libdct_cuda: K1 (bulk tensor): %d CTAs/SM, %d B smem\n", n, kTmaSmemBytes);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, CFG::kThreadsT, CFG::kSmem) != cudaSuccess || n < 1) n = 1;
+        per_sm = n < CFG::kMinCtas ? n : CFG::kMinCtas;
+        if (getenv("DCT_CUDA_DEBUG"))
+            fprintf(stderr, "libdct_cuda: K1 (bulk tensor, %d warps, %d stages): %d CTAs/SM (occupancy %d), %d B smem\n", kW, CFG::kStages,
+                    per_sm, n, CFG::kSmem);
     }
     FwdTmaParams q;
     q.f = p;
     q.nby = p.nblocks / p.bw;
     q.tpr = (p.bw + 31) / 32;
     const unsigned ntiles = q.nby * q.tpr;
-    static const int cap = getenv("DCT_CUDA_CTAS_PER_SM") ? atoi(getenv("DCT_CUDA_CTAS_PER_SM")) : 0;   // tuning aid
-    const unsigned resident = (unsigned)sm_count() * (unsigned)((cap > 0 && cap < per_sm) ? cap : per_sm);
-    const unsigned want = (ntiles + kWarps - 1) / kWarps;
+    const unsigned resident = (unsigned)sm_count() * (unsigned)per_sm;
+    const unsigned want = (ntiles + kW - 1) / kW;
     const unsigned grid = want < resident ? want : resident;
-    const unsigned n_segs = grid * kWarps;
+    const unsigned n_segs = grid * kW;
     q.step_ty = n_segs / q.tpr;
     q.step_tx = n_segs - q.step_ty * q.tpr;
     const unsigned tiles_per_warp = (ntiles + n_segs - 1) / n_segs;
@@ -558,9 +573,16 @@ static cudaError_t launch_persistent_tma(K kernel, const FwdParams &p, cudaStrea
     const int tail = (int)(p.bw % 32);
     if ((e = make_record_map(&q.map_rec_tail, p.coef, p.nblocks, tail ? tail : 32)) != cudaSuccess) return e;
     if (segments) *segments = WorklistSegments{n_segs, q.f.seg_cap, q.f.side_seg_cap};
-    kernel<<<grid, kThreads, kTmaSmemBytes, s>>>(q);
+    e = launch_pdl(kernel, grid, CFG::kThreadsT, CFG::kSmem, s, q);
     if (launches) ++*launches;
-    return cudaGetLastError();
+    return e;
+}
+
+template <int LAYOUT, bool ADAPTIVE, typename CFG>
+static cudaError_t launch_k1_tma(const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
+{
+    return p.uniform_band ? launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, true, CFG>, p, s, launches, segments)
+                          : launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, false, CFG>, p, s, launches, segments);
 }
 
 // the bulk-tensor kernel needs: the driver's tensor-map encoder, a 16-byte aligned plane whose pitch is a multiple
@@ -577,9 +599,18 @@ static bool tma_eligible(const FwdParams &p)
 template <int LAYOUT, bool ADAPTIVE>
 static cudaError_t launch_k1(const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
 {
-    if (tma_eligible(p))
-        return p.uniform_band ? launch_persistent_tma(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, true>, p, s, launches, segments)
-                              : launch_persistent_tma(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, false>, p, s, launches, segments);
+    if (tma_eligible(p)) {
+        // Geometry (measured on B200, 64 4K frames, profiles/r2_geometry.md): ONE CTA of 12 warps per SM with up to 168
+        // registers per thread beats 3 x 8 warps at 80 registers (0.93 against 0.85 of the copy peak): fewer, fatter
+        // warps keep more of a block's arithmetic in flight per warp and leave the memory system shallower queues.
+        // DCT_CUDA_K1_GEOMETRY (tuning aid): 1 = 16 warps x 1 CTA, 2 = 8 warps x 3 CTAs.
+        static const int variant = getenv("DCT_CUDA_K1_GEOMETRY") ? atoi(getenv("DCT_CUDA_K1_GEOMETRY")) : 0;
+        switch (variant) {
+        case 1: return launch_k1_tma<LAYOUT, ADAPTIVE, TmaCfg<16, 1, 2>>(p, s, launches, segments);
+        case 2: return launch_k1_tma<LAYOUT, ADAPTIVE, TmaCfg<8, 3, 2>>(p, s, launches, segments);
+        default: return launch_k1_tma<LAYOUT, ADAPTIVE, TmaCfg<12, 1, 2>>(p, s, launches, segments);
+        }
+    }
     return p.uniform_band ? launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, true>, p, s, launches, segments)
                           : launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, false>, p, s, launches, segments);
 }

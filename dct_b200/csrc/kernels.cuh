@@ -34,6 +34,9 @@ struct ExactTables {
     float rg32[64];     // K2 (non-adaptive): rs32 * gain32 rounded up
     float band_floor;   // K2
     float pad_[3];
+    // K3 inverse (one lane per block): sum_k gain_k * |mp64_k| * max(2 - nv), so that bound_per_q * max_k |q_k| bounds
+    // sum_k gain_k * |dequantised value k| without a pass over the 64 values
+    double bound_per_q;
 };
 
 // K1: forward DCT + quantise.  One thread per 8x8 block.
@@ -105,6 +108,7 @@ struct InvParams {
 // K3: exact fp64 replay of the blocks on the worklist (or of every block when wl == null).
 struct ReplayParams {
     const ExactTables *tab;
+    const ExactTables *h_tab;   // the same tables in host memory (launchers copy what a kernel takes as parameters)
     const uint32_t *worklist;   // null => replay all nblocks
     Counters *ctr;
     uint32_t nblocks;
@@ -188,6 +192,33 @@ cudaError_t launch_block_quantize_f64(int n, const double *d_Q, int adaptive, do
                                       const double *d_c, int *d_q, cudaStream_t s);
 cudaError_t launch_block_dequantize_f64(int n, const double *d_R, int adaptive, double variance,
                                         const int *d_q, double *d_c, cudaStream_t s);
+
+// cudaFuncSetAttribute(max dynamic shared memory, carveout) once per (device, kernel): the two calls cost more host
+// time than the launch itself, which matters for single frames (launch-bound).  Thread-safe.
+cudaError_t ensure_smem_attributes(const void *kernel, int smem_bytes);
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// A step is four short launches on one stream (K1, K3, K2, K3).  Launched with programmatic stream serialisation, a
+// kernel's CTAs are scheduled while its predecessor drains, run their prologue (tables to shared memory, barrier
+// set-up) and block in pdl_wait() until the predecessor's results are visible -- the launch gap and the prologue
+// disappear from the critical path, which is most of a single frame's latency.  Every such kernel calls pdl_wait()
+// BEFORE its first access to memory another kernel may have written or may still read, so the results are those of
+// plain stream order.  DCT_CUDA_NO_PDL=1 (measurement aid) launches them the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename P>
+cudaError_t launch_pdl(void (*kernel)(P), unsigned grid, unsigned block, size_t smem, cudaStream_t s, const P &params)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, params);
+}
 
 // compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
 template <int B, int E, typename F> __device__ __forceinline__ void static_for(F &&f)

@@ -11,6 +11,8 @@
 // and non-contracted __dmul_rn/__dadd_rn/__ddiv_rn, so the integers are bit-identical to
 // the reference's, exact ties included.  The same code, generalised to n x n, backs the
 // per-block drop-in entry points dct_forward/dct_inverse/quantize/dequantize.
+#include <cstring>
+
 #include "fast_core.cuh"
 #include "kernels.cuh"
 
@@ -353,6 +355,8 @@ __global__ void __launch_bounds__(kLaneThreads, 4) k_replay_fwd_lane(const Repla
         for (int i = threadIdx.x; i < (int)(sizeof(ExactTables) / 4); i += kLaneThreads) dst[i] = src[i];
     }
     __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();                 // the tables above are the plan's own; everything below is K1's output
     const ExactTables &tab = sh.tab;
     // K1 left one worklist segment per warp of its grid and the segments' counts; entry e of the concatenation lives
     // in the segment s with prefix[s] <= e < prefix[s + 1].  Every CTA builds the prefix sums for itself.
@@ -707,56 +711,80 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
 // ------------------------------------------------------------------------------------------
 // K3 inverse, worklist mode: ONE LANE PER FLAGGED BLOCK (the decoder's counterpart of k_replay_fwd_lane).
 // The reference path being reproduced: dequantize (src/quantization.c:133-151) and dct_inverse (src/dct.c:80-105).
-// A lane redoes its whole block with the butterfly in fp64: its error (~1e-13 of the bound) is five orders of magnitude
-// below the fp32 band that flagged the block, so every pixel farther than band64 (~2e-9) from a .5 boundary is
-// settled right there -- with a wide dynamic fp32 band (high-quality tables) that is all of them.  What is left, a
-// value within 2e-9 of a boundary, is replayed by the same lane in the reference's own operation order: 64 + 8
-// non-contracted multiply-adds on the reference's dequantised values, ascending index, then the pixel rule.
-// The block's 64 pixels are rewritten as whole rows (the unflagged ones with the values K2 already wrote).
-// Against the 8-lanes-per-block kernel: no shared-memory transposes, no shuffles, no fp32 re-flagging pass.
+//   1. RE-FLAG: the lane repeats K2's fp32 arithmetic for its whole block in registers (the same fast_core.cuh /
+//      butterfly.cuh functions, scalar instantiation: bit-identical per element to K2's packed lanes) to find WHICH
+//      pixels sit inside the band -- with a wide dynamic band (high-quality tables) that is typically ONE pixel of
+//      the block; every other pixel is already right in memory and is not touched;
+//   2. the warp compacts the flagged (block, pixel) pairs into a list and every lane replays ONE pixel on its own,
+//      in the reference's own operation order: 64 + 8 non-contracted multiply-adds on the reference's dequantised
+//      values, ascending index, then the pixel rule; one byte store.
+// Against the 8-lanes-per-block kernel: no shared-memory transposes, no shuffles, no lanes idling during the replay.
+// (A first version redid the whole block with an fp64 butterfly per lane: 3 300 instructions per warp at 204
+// registers, latency-bound at two warps per scheduler -- slower than the kernel it replaced.)
 // ------------------------------------------------------------------------------------------
-// Pixel (i, j) of one block in the reference's own operation order (rare: values within ~2e-9 of a .5 boundary):
-// in = the reference's dequantised values (src/quantization.c:133-151), temp[i][k] = sum_m D[m][i] * in[m][k]
-// (src/dct.c:85-92), out = sum_k temp[i][k] * D[k][j] (:95-102), both sums from 0.0 in ascending order; then the
-// pixel rule.  Returns round(out + 128) unclamped to int range [-1, 256].
+// Sample (i, j) of one block in the reference's own operation order, non-adaptive tables:
+// in[m][k] = q * R (src/quantization.c:139,144), temp[i][k] = sum_m D[m][i] * in[m][k] (src/dct.c:85-92),
+// out = sum_k temp[i][k] * D[k][j] (:95-102), every sum from 0.0 in ascending order, no contraction.
+// The eight sums temp[i][0..7] advance together, m ascending for each of them (the reference's order per sum): eight
+// independent chains, and only row m of the coefficients is live at a time.  Not inlined: its registers are its own.
 template <int LAYOUT>
-__device__ __noinline__ int exact_inverse_pixel(const ExactTables &tab, const int16_t *rec, int adaptive, double inv_two_minus_nv,
-                                                int i, int j, unsigned &ties)
+__device__ __noinline__ double exact_inverse_sample(const uint4 *q4, const double *D, const double *R, int i, int j)
 {
-    double out = 0.0;
-    for (int k = 0; k < 8; ++k) {
-        double temp = 0.0;
-        for (int m = 0; m < 8; ++m) {
-            const int nat = 8 * m + k;
-            const int q = rec[LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[nat] : nat];
-            temp = __dadd_rn(temp, __dmul_rn(tab.D[m * 8 + i], exact_dequant(tab, adaptive, inv_two_minus_nv, nat, q)));
-        }
-        out = __dadd_rn(out, __dmul_rn(temp, tab.D[k * 8 + j]));
+    uint32_t w[32];       // the record: one 128-byte line, eight 16-byte loads, indexed statically below
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 t = q4[c];
+        w[4 * c] = t.x, w[4 * c + 1] = t.y, w[4 * c + 2] = t.z, w[4 * c + 3] = t.w;
     }
-    const double val = __dadd_rn(out, 128.0);
-    const double rr = round_half_away(val);
-    ties += near_half(val);
-    return rr < 0.0 ? -1 : (rr > 255.0 ? 256 : (int)rr);
+    double di[8], temp[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) di[m] = D[m * 8 + i], temp[m] = 0.0;
+    static_for<0, 8>([&](auto M) {
+        constexpr int m = decltype(M)::value;
+        static_for<0, 8>([&](auto K) {
+            constexpr int k = decltype(K)::value;
+            constexpr int nat = 8 * m + k;
+            constexpr int pos = LAYOUT == LAYOUT_ZIGZAG ? ZigZagInv{}.pos[nat] : nat;
+            const int qq = (int)(int16_t)(pos & 1 ? (w[pos >> 1] >> 16) : (w[pos >> 1] & 0xFFFFu));
+            // (double)qq without a conversion instruction: (2^52 + 2^31 + qq) - (2^52 + 2^31), exact
+            const double qd = __dsub_rn(__hiloint2double(0x43300000, (int)((unsigned)qq ^ 0x80000000u)), 4503601774854144.0);
+            temp[k] = __dadd_rn(temp[k], __dmul_rn(di[m], __dmul_rn(qd, R[nat])));
+        });
+    });
+    double out = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out = __dadd_rn(out, __dmul_rn(temp[k], D[k * 8 + j]));
+    return out;
 }
 
-constexpr double kMagic52_128r = 6755399441055744.0 + 128.0;   // 1.5 * 2^52 + 128
+// The tables this kernel indexes with compile-time constants travel as kernel parameters: they are read through the
+// constant bank as instruction operands instead of ~200 shared-memory loads per block (the first version of this
+// kernel stalled on exactly those: short_scoreboard / mio_throttle on top of its stall list).
+struct InvLaneParams {
+    ReplayParams p;
+    float rs32[64], rg32[64], gain32[64];          // K2's fp32 tables (ExactTables)
+    double R[64];                                  // dequant_matrix as the host made it
+    float band_floor;
+};
 
 struct LaneInvShared {
-    ExactTables tab;
+    double D[64];                                  // dct_matrix: indexed by the replayed pixel's (i, j), per lane
+    double R[64];                                  // dequant_matrix, for the (not inlined) exact replay
+    unsigned blk[kLaneWarps][32];
+    double inv_s[kLaneWarps][32];                  // adaptive: 1 / (2 - nv) of each block (src/quantization.c:193)
+    unsigned short pairs[kLaneWarps][32 * kPairsPerRound];   // (source lane << 6) | pixel index 8i + j
     unsigned prefix[kMaxWorklistSegments + 1];
 };
 
-template <int LAYOUT>
-__global__ void __launch_bounds__(kLaneThreads, 2) k_replay_inv_lane(const ReplayParams p)
+template <int LAYOUT, bool ADAPTIVE>
+__global__ void __launch_bounds__(kLaneThreads, 5) k_replay_inv_lane(const __grid_constant__ InvLaneParams P)
 {
     __shared__ LaneInvShared sh;
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.tab);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(ExactTables) / 4); i += kLaneThreads) dst[i] = src[i];
-    }
+    const ReplayParams &p = P.p;
+    if (threadIdx.x < 64) sh.D[threadIdx.x] = p.tab->D[threadIdx.x], sh.R[threadIdx.x] = p.tab->R[threadIdx.x];
     __syncthreads();
-    const ExactTables &tab = sh.tab;
+    pdl_launch_dependents();
+    pdl_wait();                 // the table above is the plan's own; everything below is K2's output
     // segmented worklist (bulk-tensor K2: one segment per warp of its grid) or a flat one counted in ctr->wl_count
     const bool segmented = p.seg_count != nullptr && p.seg.n_segs != 0;
     const unsigned n_segs = p.seg.n_segs;
@@ -769,71 +797,164 @@ __global__ void __launch_bounds__(kLaneThreads, 2) k_replay_inv_lane(const Repla
         if (count > p.wl_cap) count = p.wl_cap;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned warps_per_grid = gridDim.x * kLaneWarps;
+    const unsigned tiles = (count + 31) / 32, warps_per_grid = gridDim.x * kLaneWarps;
     unsigned ties = 0;
 
-    for (unsigned entry = (blockIdx.x * kLaneWarps + warp) * 32 + lane; entry < count; entry += warps_per_grid * 32) {
-        unsigned b;
-        if (segmented) {
-            unsigned seg, local;
-            find_segment(sh.prefix, n_segs, entry, seg, local);
-            b = p.worklist[(size_t)seg * p.seg.seg_cap + local];
-        } else {
-            b = p.worklist[entry];
+    // worklist entry -> block index; the entry of the NEXT tile is looked up, and its record's line requested from
+    // L2, one tile ahead (two dependent global loads would otherwise sit at the head of every tile)
+    auto lookup = [&](unsigned tile_, bool &active_, unsigned &b_) {
+        const unsigned entry = tile_ * 32 + lane;
+        active_ = tile_ < tiles && entry < count;
+        b_ = 0;
+        if (active_) {
+            if (segmented) {
+                unsigned seg, local;
+                find_segment(sh.prefix, n_segs, entry, seg, local);
+                b_ = p.worklist[(size_t)seg * p.seg.seg_cap + local];
+            } else {
+                b_ = p.worklist[entry];
+            }
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.coef_in + (size_t)b_ * 64));
         }
-        const unsigned by = b / p.bw, bx = b - by * p.bw;
-        uint8_t *dst = p.px_out + (long long)by * 8 * p.pitch + (long long)bx * 8;
+    };
+    bool active_n;
+    unsigned b_n;
+    lookup(blockIdx.x * kLaneWarps + warp, active_n, b_n);
+    for (unsigned tile = blockIdx.x * kLaneWarps + warp; tile < tiles; tile += warps_per_grid) {
+        const bool active = active_n;
+        const unsigned b = b_n;
+        lookup(tile + warps_per_grid, active_n, b_n);
         const int16_t *rec = p.coef_in + (size_t)b * 64;
 
-        double two_minus_nv = 1.0, inv_two_minus_nv = 1.0;
-        if (p.adaptive) {
-            const double var = p.var_in ? p.var_in[b] : 0.0;
-            two_minus_nv = __dsub_rn(2.0, norm_variance(var));
-            inv_two_minus_nv = __ddiv_rn(1.0, two_minus_nv);   // src/quantization.c:193
+        float s32 = 1.0f;
+        if constexpr (ADAPTIVE) {
+            const double var = (p.var_in && active) ? p.var_in[b] : 0.0;
+            sh.inv_s[warp][lane] = __ddiv_rn(1.0, __dsub_rn(2.0, norm_variance(var)));
+            s32 = adaptive_scale(var);
         }
+        sh.blk[warp][lane] = b;
 
-        // the block in fp64: q * multiplier * (2-nv) instead of the reference's reciprocal chain (a few ulps apart,
-        // inside the 8 * 2^-53 relative input error the bound allows for), columns then rows as src/dct.c:85-102
-        double v[64];
-        double bound64 = 0.0;
+        // ---- phase 1: K2's fp32 arithmetic for the whole block (inv_block of dequant_idct.cu, scalar), flagged pixels
+        float v[64];
+        float bound = 0.f;
         static_for<0, 8>([&](auto J) {
             constexpr int j = decltype(J)::value;
-            const uint4 t = reinterpret_cast<const uint4 *>(rec)[j];
+            const uint4 t = active ? reinterpret_cast<const uint4 *>(rec)[j] : make_uint4(0, 0, 0, 0);
             const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
-            static_for<0, 8>([&](auto Hh) {
+            static_for<0, 4>([&](auto Hh) {
                 constexpr int h = decltype(Hh)::value;
-                constexpr int k = storage_to_natural<LAYOUT>(8 * j + h);
-                const int q = (int)(int16_t)(h & 1 ? (w4[h >> 1] >> 16) : (w4[h >> 1] & 0xFFFFu));
-                double x = (double)q * tab.mp64[k];
-                if (k != 0) x *= two_minus_nv;
-                v[k] = x;
-                bound64 = fma(fabs(x), (double)tab.gain32[k], bound64);
+                constexpr int k0 = storage_to_natural<LAYOUT>(8 * j + 2 * h), k1 = storage_to_natural<LAYOUT>(8 * j + 2 * h + 1);
+                float f0 = half_to_float<0>(w4[h]), f1 = half_to_float<1>(w4[h]);
+                if constexpr (ADAPTIVE) {
+                    if (k0 != 0) f0 = __fmul_rn(f0, s32);
+                    f1 = __fmul_rn(f1, s32);
+                    v[k0] = __fmul_rn(f0, P.rs32[k0]);
+                    v[k1] = __fmul_rn(f1, P.rs32[k1]);
+                    bound = __fmaf_rn(fabsf(v[k0]), P.gain32[k0], bound);
+                    bound = __fmaf_rn(fabsf(v[k1]), P.gain32[k1], bound);
+                } else {
+                    v[k0] = f0, v[k1] = f1;
+                    bound = __fmaf_rn(fabsf(f0), P.rg32[k0], bound);
+                    bound = __fmaf_rn(fabsf(f1), P.rg32[k1], bound);
+                }
             });
         });
+        if constexpr (ADAPTIVE) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) idct8<double, 8>(&v[j]);
+            for (int c = 0; c < 8; ++c) idct8<float, 8>(&v[c]);
+        } else {
+            // K2's folded first stage (idct8_dequant), scalar: same operations on the same operands
+            constexpr int ra[4] = {0, 2, 5, 1}, rb[4] = {4, 6, 3, 7};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) idct8<double, 1>(&v[8 * i]);
-
-        // 1e-9: the tie-accounting margin; 8 * 2^-53 * bound: fp64 butterfly + the reference's own rounding
-        const double thr = 0.5 - (2e-9 + bound64 * 8.9e-16);
-        const bool sane = bound64 < 1e12;
+            for (int c = 0; c < 8; ++c) {
+                float ma[4];
+                PosNeg1 mb[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            uint32_t lo = 0, hi = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const double x = v[8 * i + j];
-                const double t = x + kMagic52_128r;           // low mantissa bits: round-to-nearest(x) + 128
-                const double e = x - (t - kMagic52_128r);
-                int px = __double2loint(t);
-                if (!(fabs(e) < thr) || !sane)                // within band64 of a .5 boundary: the reference's own arithmetic
-                    px = exact_inverse_pixel<LAYOUT>(tab, rec, p.adaptive, inv_two_minus_nv, i, j, ties);
-                px = px < 0 ? 0 : (px > 255 ? 255 : px);
-                if (j < 4) lo |= (uint32_t)px << (8 * j);
-                else hi |= (uint32_t)px << (8 * (j - 4));
+                for (int j = 0; j < 4; ++j) {
+                    ma[j] = P.rs32[8 * ra[j] + c];
+                    mb[j].pos = P.rs32[8 * rb[j] + c];
+                    mb[j].neg = -mb[j].pos;
+                }
+                idct8_dequant<float, 8>(&v[c], ma, mb);
             }
-            *reinterpret_cast<uint2 *>(dst + i * p.pitch) = make_uint2(lo, hi);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) idct8<float, 1>(&v[8 * i]);
+        const float thr = pixel_threshold(bound, P.band_floor);
+        unsigned need_lo = 0, need_hi = 0;
+        if (!(bound < 1.4e5f)) {
+            need_lo = need_hi = 0xffffffffu;               // outside the int16 trick's range: K2 wrote nothing reliable
+        } else {
+#pragma unroll
+            for (int e = 0; e < 64; ++e) {
+                float t, r;
+                pixel_residual(v[e], t, r);
+                if (fabsf(r) >= thr) (e < 32 ? need_lo : need_hi) |= 1u << (e & 31);
+            }
+        }
+        if (!active) need_lo = need_hi = 0;
+
+        // ---- phase 2: rounds of (compact the pairs, one lane replays one pixel) until no lane has any left
+        while (__any_sync(0xffffffffu, (need_lo | need_hi) != 0)) {
+            const int mine = min(__popc(need_lo) + __popc(need_hi), kPairsPerRound);
+            int before = mine;                                       // inclusive prefix sum over the lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int x = __shfl_up_sync(0xffffffffu, before, d);
+                if (lane >= d) before += x;
+            }
+            const int total = __shfl_sync(0xffffffffu, before, 31);
+            before -= mine;
+            for (int n = 0; n < mine; ++n) {
+                int e;
+                if (need_lo) {
+                    e = __ffs(need_lo) - 1;
+                    need_lo &= need_lo - 1;
+                } else {
+                    e = 32 + __ffs(need_hi) - 1;
+                    need_hi &= need_hi - 1;
+                }
+                sh.pairs[warp][before + n] = (unsigned short)((lane << 6) | e);
+            }
+            __syncwarp();
+            for (int pi = lane; pi < total; pi += 32) {
+                const unsigned pr = sh.pairs[warp][pi];
+                const int sl = pr >> 6, e = pr & 63, i = e >> 3, j = e & 7;
+                const unsigned bb = sh.blk[warp][sl];
+                const uint4 *q4 = reinterpret_cast<const uint4 *>(p.coef_in + (size_t)bb * 64);
+                const double inv_two_minus_nv = ADAPTIVE ? sh.inv_s[warp][sl] : 1.0;
+                // temp[i][k] = sum_m D[m][i] * in[m][k] (src/dct.c:85-92), out = sum_k temp[i][k] * D[k][j] (:95-102),
+                // both from 0.0 in ascending order; in = the reference's dequantised values (src/quantization.c:133-151)
+                double out = 0.0;
+                if constexpr (ADAPTIVE) {
+                    double di[8];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) di[m] = sh.D[m * 8 + i];
+                    // rare here (adaptive plans decode through the fp64 kernel, whose band flags true near-ties only):
+                    // compact loops, the reciprocal chain of src/quantization.c:137,144 value by value
+                    const int16_t *q = p.coef_in + (size_t)bb * 64;
+                    for (int k = 0; k < 8; ++k) {
+                        double temp = 0.0;
+                        for (int m = 0; m < 8; ++m) {
+                            const int nat = 8 * m + k;
+                            const int qq = q[LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[nat] : nat];
+                            double mm = P.R[nat];
+                            if (nat != 0) mm = __dmul_rn(mm, inv_two_minus_nv);
+                            temp = __dadd_rn(temp, __dmul_rn(di[m], __dmul_rn((double)qq, __ddiv_rn(1.0, mm))));
+                        }
+                        out = __dadd_rn(out, __dmul_rn(temp, sh.D[k * 8 + j]));
+                    }
+                } else {
+                    out = exact_inverse_sample<LAYOUT>(q4, sh.D, sh.R, i, j);
+                }
+                const double val = __dadd_rn(out, 128.0);
+                double rr = round_half_away(val);
+                rr = rr < 0.0 ? 0.0 : (rr > 255.0 ? 255.0 : rr);
+                ties += near_half(val);
+                const unsigned by = bb / p.bw, bx = bb - by * p.bw;
+                p.px_out[((long long)by * 8 + i) * p.pitch + (long long)bx * 8 + j] = (uint8_t)rr;
+            }
+            __syncwarp();
         }
     }
 
@@ -931,9 +1052,8 @@ cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s)
         // one CTA per ~1024 blocks of the plane (a tenth of them flagged would keep its four warps busy), at most 4 per SM
         unsigned grid = (p.nblocks + 1023) / 1024;
         grid = grid < 16u ? 16u : (grid > 148u * 4u ? 148u * 4u : grid);
-        if (p.layout == LAYOUT_ZIGZAG) k_replay_fwd_lane<LAYOUT_ZIGZAG><<<grid, kLaneThreads, 0, s>>>(p);
-        else k_replay_fwd_lane<LAYOUT_NATURAL><<<grid, kLaneThreads, 0, s>>>(p);
-        return cudaGetLastError();
+        return p.layout == LAYOUT_ZIGZAG ? launch_pdl(k_replay_fwd_lane<LAYOUT_ZIGZAG>, grid, kLaneThreads, 0, s, p)
+                                         : launch_pdl(k_replay_fwd_lane<LAYOUT_NATURAL>, grid, kLaneThreads, 0, s, p);
     }
     if (p.px_is_f32)
         return p.layout == LAYOUT_ZIGZAG ? launch_replay(k_replay_fwd<LAYOUT_ZIGZAG, true>, p, s)
@@ -944,13 +1064,22 @@ cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s)
 
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s)
 {
-    if (p.worklist != nullptr) {                         // the fused kernel ran: one lane per flagged block
-        // one CTA per ~1024 blocks of the plane (a tenth of them flagged would keep its four warps busy), at most 2 per SM
+    if (p.worklist != nullptr && p.h_tab != nullptr) {   // the fused kernel ran: one lane per flagged block
+        // one CTA per ~1024 blocks of the plane (a tenth of them flagged would keep its four warps busy), at most 4 per SM
         unsigned grid = (p.nblocks + 1023) / 1024;
-        grid = grid < 16u ? 16u : (grid > 148u * 2u ? 148u * 2u : grid);     // two CTAs per SM are resident (registers)
-        if (p.layout == LAYOUT_ZIGZAG) k_replay_inv_lane<LAYOUT_ZIGZAG><<<grid, kLaneThreads, 0, s>>>(p);
-        else k_replay_inv_lane<LAYOUT_NATURAL><<<grid, kLaneThreads, 0, s>>>(p);
-        return cudaGetLastError();
+        grid = grid < 16u ? 16u : (grid > 148u * 5u ? 148u * 5u : grid);
+        InvLaneParams q;
+        q.p = p;
+        memcpy(q.rs32, p.h_tab->rs32, sizeof q.rs32);
+        memcpy(q.rg32, p.h_tab->rg32, sizeof q.rg32);
+        memcpy(q.gain32, p.h_tab->gain32, sizeof q.gain32);
+        memcpy(q.R, p.h_tab->R, sizeof q.R);
+        q.band_floor = p.h_tab->band_floor;
+        if (p.adaptive)
+            return p.layout == LAYOUT_ZIGZAG ? launch_pdl(k_replay_inv_lane<LAYOUT_ZIGZAG, true>, grid, kLaneThreads, 0, s, q)
+                                             : launch_pdl(k_replay_inv_lane<LAYOUT_NATURAL, true>, grid, kLaneThreads, 0, s, q);
+        return p.layout == LAYOUT_ZIGZAG ? launch_pdl(k_replay_inv_lane<LAYOUT_ZIGZAG, false>, grid, kLaneThreads, 0, s, q)
+                                         : launch_pdl(k_replay_inv_lane<LAYOUT_NATURAL, false>, grid, kLaneThreads, 0, s, q);
     }
     return p.layout == LAYOUT_ZIGZAG ? launch_replay(k_replay_inv<LAYOUT_ZIGZAG>, p, s)
                                      : launch_replay(k_replay_inv<LAYOUT_NATURAL>, p, s);

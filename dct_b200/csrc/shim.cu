@@ -112,6 +112,9 @@ int read_tables(dct_cuda_plan *p)
     memcpy(p->h_tab.rg32, p->rg, sizeof p->rg);
     p->h_tab.band_floor = p->band_floor;
     p->h_tab.pad_[0] = p->h_tab.pad_[1] = p->h_tab.pad_[2] = 0.f;
+    double per_q = 0.0;
+    for (int k = 0; k < 64; ++k) per_q += (double)p->gain[k] * std::fabs(p->h_tab.mp64[k]);
+    p->h_tab.bound_per_q = per_q * (p->adaptive ? 1.9 : 1.0);      // 2 - nv <= 1.9 (src/quantization.c:186-190)
     return DCT_CUDA_OK;
 }
 
@@ -250,6 +253,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
 
     ReplayParams rp{};
     rp.tab = p->d_tab;
+    rp.h_tab = &p->h_tab;
     rp.ctr = ln.d_ctr;
     rp.nblocks = nblocks;
     rp.wl_cap = ln.wl_cap;
@@ -330,6 +334,7 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
 
     ReplayParams rp{};
     rp.tab = p->d_tab;
+    rp.h_tab = &p->h_tab;
     rp.ctr = ln.d_ctr;
     rp.nblocks = nblocks;
     rp.wl_cap = ln.wl_cap;

@@ -3,7 +3,10 @@
 // link-time dependency (the static CUDA runtime) and still loads on a box without a driver.
 #include <cstdlib>
 #include <mutex>
+#include <set>
+#include <utility>
 
+#include "kernels.cuh"
 #include "tma.cuh"
 
 namespace dctb {
@@ -41,6 +44,28 @@ static CUtensorMapL2promotion l2_promotion()
 }
 
 bool tma_available() { return encode_fn() != nullptr; }
+
+bool pdl_enabled()
+{
+    static const bool on = getenv("DCT_CUDA_NO_PDL") == nullptr;
+    return on;
+}
+
+cudaError_t ensure_smem_attributes(const void *kernel, int smem_bytes)
+{
+    static std::mutex mu;
+    static std::set<std::pair<int, const void *>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({dev, kernel})) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    done.insert({dev, kernel});
+    return cudaSuccess;
+}
 
 cudaError_t make_pixel_map(CUtensorMap *map, const void *base, long long pitch, int W, int H)
 {

@@ -1010,14 +1010,15 @@ def test_int8_records_are_refused_when_a_value_could_overflow(api, oracle):
         assert np.array_equal(cx.plan.dequant_idct_i8(c8, 320, 240), want)
 
 
-@pytest.mark.parametrize("n,ok", [(4, True), (16, True), (3, False), (6, False)])
-def test_int8_records_with_other_block_sizes(api, oracle, n, ok):
-    """The int8 record calls move whole 16-value groups: offered when n*n is a multiple of 16 (n = 4: the custom
-    table of src/quantization.c:78-96 starts at 8 >= 4 * 128 / 127.5), refused with an error otherwise."""
+@pytest.mark.parametrize("n,quality,ok", [(4, 50, True), (16, 10, True), (3, 50, False), (6, 50, False)])
+def test_int8_records_with_other_block_sizes(api, oracle, n, quality, ok):
+    """The int8 record calls move whole 16-value groups: offered when n*n is a multiple of 16 (and every table entry is
+    >= n * 128 / 127.5: the custom table of src/quantization.c:78-96 starts at 8 at q50, at 40 at q10), refused with
+    an error otherwise."""
     rng = np.random.default_rng(500 + n)
     H, W = n * 9, n * 9                                    # 81 blocks: an odd count, records end off any 16-byte grid for odd n
     px = rng.integers(0, 256, size=(H, W), dtype=np.uint8)
-    d, q = api.dct_init(n), api.quant_init(n, 50, 0)
+    d, q = api.dct_init(n), api.quant_init(n, quality, 0)
     plan = api.Plan(d, q)
     try:
         if not ok:
@@ -1026,9 +1027,10 @@ def test_int8_records_with_other_block_sizes(api, oracle, n, ok):
             with pytest.raises(api.DctCudaError, match="multiple of 16"):
                 plan.dequant_idct_i8(np.zeros((81, n * n), np.int8), W, H)
             return
-        Q = oracle.quant_table(50, n)
-        want_c, _, _ = oracle.fwd_quant_plane_n(n, px, Q, 0, 0, nthreads=2)
-        want_p, _ = oracle.dequant_idct_plane_n(n, want_c, W, H, Q, 0, 0, None, nthreads=2)
+        Q = oracle.quant_table(quality, n)
+        want_c = oracle.fwd_quant_plane_n(n, px, Q, 0, 0, nthreads=2)[0]
+        want_p = oracle.dequant_idct_plane_n(n, want_c, W, H, Q, 0, 0, None, nthreads=2)
+        want_p = want_p[0] if isinstance(want_p, tuple) else want_p
         assert plan.records_fit_i8 and np.abs(want_c).max() <= 127
         c8 = plan.fwd_quant_i8(px)
         assert c8.shape == (81, n * n) and np.array_equal(c8.astype(np.int16), want_c)

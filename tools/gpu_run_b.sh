@@ -17,3 +17,6 @@ DCT_CUDA_INV_FP32=1 python tools/kbench.py --tag adaptive_fp32inv --adaptive 1 >
 python tools/kbench.py --tag 1080p --W 1920 --H 1080 --frames 256 >> $out 2>&1
 python tools/kbench.py --tag c5strip --W 65536 --H 8192 --frames 1 >> $out 2>&1
 cat $out
+echo "--- latency (PDL on)"; timeout 120 tools/latency | tee gpurun_out/r2b_latency.jsonl
+echo "--- latency (PDL off)"; DCT_CUDA_NO_PDL=1 timeout 120 tools/latency | tee gpurun_out/r2b_latency_nopdl.jsonl
+DCT_CUDA_NO_PDL=1 python tools/kbench.py --tag no_pdl >> $out 2>&1; tail -1 $out
