@@ -16,6 +16,7 @@
 
 #include "fast_core.cuh"
 #include "kernels.cuh"
+#include "replay_lane.cuh"
 #include "tma.cuh"
 
 namespace dctb {
@@ -220,11 +221,11 @@ constexpr int kTmaCtlBytes = 64;                                    // per warp:
 // geometry of one kernel variant: warps per CTA, CTAs per SM the register budget is cut for, record stages per warp
 template <int WARPS, int MIN_CTAS, int STAGES> struct TmaCfg {
     static constexpr int kWarpsT = WARPS, kMinCtas = MIN_CTAS, kStages = STAGES, kThreadsT = 32 * WARPS;
-    static constexpr int kSmem = 1024 /* alignment slack */ + WARPS * (STAGES * kTmaInBytes + kTmaCtlBytes);
+    static constexpr int kSmem = 1024 /* alignment slack */ + WARPS * (STAGES * kTmaInBytes + kTmaCtlBytes + (int)sizeof(InvLaneScratch));
     static_assert(STAGES >= 2 && STAGES <= 8, "stages");
 };
 
-template <int LAYOUT, bool ADAPTIVE, typename CFG>
+template <int LAYOUT, bool ADAPTIVE, typename CFG, bool FOLD>
 __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_u8_tma(const __grid_constant__ InvTmaParams P)
 {
     constexpr int kW = CFG::kWarpsT, kS = CFG::kStages;
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
     uint8_t *sm = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     uint8_t *in_p = sm + warp * (kS * kTmaInBytes);
     uint32_t *ctl_p = reinterpret_cast<uint32_t *>(sm + kW * kS * kTmaInBytes + warp * kTmaCtlBytes);
+    InvLaneScratch *ws = reinterpret_cast<InvLaneScratch *>(sm + kW * (kS * kTmaInBytes + kTmaCtlBytes)) + warp;
     const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in_p);
     const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(ctl_p);           // kS 8-byte mbarriers
 
@@ -271,6 +273,18 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
     uint32_t wl_n = 0;          // entries this warp has appended to its worklist segment
     const uint32_t gwarp = blockIdx.x * kW + warp;
 
+    // Entries [replayed_n, replayed_n + n) of this warp's worklist segment, one per lane, through replay_lane.cuh
+    uint32_t replayed_n = 0;
+    auto replay_batch = [&](uint32_t n) {
+        if constexpr (!FOLD) return;
+        __syncwarp();                                     // the pixels K2 stored above are patched by other lanes below
+        const InvReplayCtx cx{p.rs, p.rg, p.gain, p.band_floor, p.tab->D, p.tab->R, p.coef, p.var_in, p.px, p.pitch, p.bw, p.ctr};
+        const bool active = lane < n;
+        const uint32_t b = active ? p.worklist[(size_t)gwarp * P.seg_cap + replayed_n + lane] : 0u;
+        replay_inv_lanes<LAYOUT, ADAPTIVE>(cx, ws, active, b);
+        replayed_n += n;
+    };
+
     uint32_t stage = 0, phase = 0;
     while (ty < P.nby) {
         const uint32_t bx0 = tx * 32;
@@ -302,7 +316,13 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
         if (tx >= P.tpr) tx -= P.tpr, ++ty;
         if (++stage == kS) stage = 0, phase ^= 1;
     }
-    if (lane == 0) P.seg_count[gwarp] = wl_n;     // <= 32 per tile visited, < seg_cap by construction
+    // ---- tail.  FOLD (small planes): the warp replays the blocks of its own segment right here (replay_lane.cuh) and no
+    // K3 is launched; large planes leave them to K3's grid of replay-only warps (see K1's tail, fwd_quant.cu).
+    if constexpr (FOLD) {
+        while (replayed_n < wl_n) replay_batch(min(32u, wl_n - replayed_n));
+        if (lane == 0 && wl_n != 0) atomicAdd(&p.ctr->replayed, (unsigned long long)wl_n);
+    }
+    if (lane == 0) P.seg_count[gwarp] = FOLD ? 0u : wl_n;     // <= 32 per tile visited, < seg_cap by construction
 }
 
 // ------------------------------------------------------------------------------------------
@@ -461,14 +481,26 @@ static cudaError_t launch_persistent_tma(K kernel, const InvParams &p, cudaStrea
     return launch_pdl(kernel, grid, CFG::kThreadsT, CFG::kSmem, s, q);
 }
 
-template <typename CFG>
-static cudaError_t launch_k2_tma(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments)
+template <typename CFG, bool FOLD>
+static cudaError_t launch_k2_tma_fold(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments)
 {
     if (layout == LAYOUT_ZIGZAG)
-        return adaptive ? launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, true, CFG>, p, s, segments)
-                        : launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, false, CFG>, p, s, segments);
-    return adaptive ? launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_NATURAL, true, CFG>, p, s, segments)
-                    : launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_NATURAL, false, CFG>, p, s, segments);
+        return adaptive ? launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, true, CFG, FOLD>, p, s, segments)
+                        : launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, false, CFG, FOLD>, p, s, segments);
+    return adaptive ? launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_NATURAL, true, CFG, FOLD>, p, s, segments)
+                    : launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_NATURAL, false, CFG, FOLD>, p, s, segments);
+}
+
+// small planes fold the replay into K2's tail (one launch instead of two)
+template <typename CFG>
+static cudaError_t launch_k2_tma(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments, bool *folded)
+{
+    static const bool no_fold = getenv("DCT_CUDA_NO_FOLD") != nullptr;   // measurement aid
+    if (!no_fold && p.tab != nullptr && p.ctr != nullptr && p.nblocks <= kFoldMaxBlocks) {
+        if (folded) *folded = true;
+        return launch_k2_tma_fold<CFG, true>(p, layout, adaptive, s, segments);
+    }
+    return launch_k2_tma_fold<CFG, false>(p, layout, adaptive, s, segments);
 }
 
 static bool tma_eligible(const InvParams &p)
@@ -480,20 +512,18 @@ static bool tma_eligible(const InvParams &p)
     return padded + (unsigned long long)kMaxWorklistSegments * 64 <= p.wl_cap;
 }
 
-cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments)
+cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments, bool *folded)
 {
+    if (folded) *folded = false;
     if (segments) *segments = WorklistSegments{0, 0, 0};
     if (p.nblocks == 0) return cudaSuccess;
     if (tma_eligible(p)) {
         // Geometry (measured on B200, 64 4K frames, profiles/r2_geometry.md): ONE CTA of 16 warps per SM with 128
         // registers per thread beats 3 x 8 warps at 80 registers (0.91 against 0.83 of the copy peak).
-        // DCT_CUDA_K2_GEOMETRY (tuning aid): 1 = 12 warps x 1 CTA, 2 = 8 warps x 3 CTAs.
+        // DCT_CUDA_K2_GEOMETRY=2 (tuning aid): 8 warps x 3 CTAs.
         static const int variant = getenv("DCT_CUDA_K2_GEOMETRY") ? atoi(getenv("DCT_CUDA_K2_GEOMETRY")) : 0;
-        switch (variant) {
-        case 1: return launch_k2_tma<TmaCfg<12, 1, 2>>(p, layout, adaptive, s, segments);
-        case 2: return launch_k2_tma<TmaCfg<8, 3, 2>>(p, layout, adaptive, s, segments);
-        default: return launch_k2_tma<TmaCfg<16, 1, 2>>(p, layout, adaptive, s, segments);
-        }
+        if (variant == 2) return launch_k2_tma<TmaCfg<8, 3, 2>>(p, layout, adaptive, s, segments, folded);
+        return launch_k2_tma<TmaCfg<16, 1, 2>>(p, layout, adaptive, s, segments, folded);
     }
     const unsigned grid = (p.nblocks + kThreads - 1) / kThreads;
     if (layout == LAYOUT_ZIGZAG) {

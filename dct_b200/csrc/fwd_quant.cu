@@ -24,6 +24,7 @@
 
 #include "fast_core.cuh"
 #include "kernels.cuh"
+#include "replay_lane.cuh"
 #include "tma.cuh"
 
 namespace dctb {
@@ -276,7 +277,7 @@ template <int WARPS, int MIN_CTAS, int STAGES> struct TmaCfg {
     static_assert(STAGES >= 2 && STAGES <= 7, "stages");
 };
 
-template <int LAYOUT, bool ADAPTIVE, bool UNIFORM, typename CFG>
+template <int LAYOUT, bool ADAPTIVE, bool UNIFORM, typename CFG, bool FOLD>
 __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_fwd_quant_u8_tma(const __grid_constant__ FwdTmaParams P)
 {
     constexpr int kW = CFG::kWarpsT, kS = CFG::kStages;
@@ -326,6 +327,31 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_fwd_quant_u8_
     // my chunk j goes to 16-byte slot j ^ (lane & 7) of my 128-byte row
     uint8_t *const my_out = out_p + lane * 128;
     const uint32_t swz = (lane & 7) << 4;
+
+    // Entries [first, first + n) of this warp's worklist segment, one per lane, through replay_lane.cuh.  The record
+    // stage doubles as the replay's scratch, and the patches are generic-proxy stores to records that bulk stores wrote:
+    // every bulk store of this warp must be complete (not just read) first.
+    uint32_t replayed_n = 0;                                      // entries of my segment already replayed
+    auto replay_batch = [&](uint32_t n) {
+        if constexpr (!FOLD) return;
+        if (lane == 0) {
+            tma::store_wait_all();
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __syncwarp();
+        const uint32_t gwarp = blockIdx.x * kW + warp;
+        LaneScratch *ws = reinterpret_cast<LaneScratch *>(out_p);
+        const FwdReplayCtx cx{p.r, p.thr, p.tab->D, p.tab->Q, ADAPTIVE ? 1 : 0, p.coef, p.ctr};
+        const uint32_t e = replayed_n + lane;
+        const bool active = lane < n;
+        const uint32_t b = active ? p.worklist[(size_t)gwarp * p.seg_cap + e] : 0u;
+        const bool side = e < p.side_seg_cap;             // the block's pixels sit next to its entry (8-byte rows), else in the plane
+        const uint32_t by = b / p.bw, bx = b - by * p.bw;
+        const uint8_t *src = side ? p.side + ((size_t)gwarp * p.side_seg_cap + e) * 64 : p.px + ((long long)by * p.pitch + bx) * 8;
+        replay_fwd_lanes<LAYOUT>(cx, ws, active, b, src, side ? 8 : p.pitch);
+        replayed_n += n;
+        __syncwarp();                                     // the scratch is the record stage again
+    };
 
     uint32_t stage = 0, phase = 0;
     while (ty < P.nby) {
@@ -383,8 +409,17 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_fwd_quant_u8_
         if (tx >= P.tpr) tx -= P.tpr, ++ty;
         if (++stage == kS) stage = 0, phase ^= 1;
     }
+    // ---- tail.  FOLD (small planes, where a launch costs more than the work): the warp replays the blocks of its own
+    // segment right here (replay_lane.cuh) and no K3 is launched.  Large planes leave the segments to K3, whose grid
+    // of replay-only warps hides the replay's latency better than a tile-loop warp that stops to do it (measured: in
+    // the tile loop a batch of 32 costs the warp its full latency, and 1/12 of the SM's tile throughput with it).
+    const uint32_t n_mine = *cnt_p;
+    if constexpr (FOLD) {
+        while (replayed_n < n_mine) replay_batch(min(32u, n_mine - replayed_n));
+        if (lane == 0 && n_mine != 0) atomicAdd(&p.ctr->replayed, (unsigned long long)n_mine);
+    }
     if (lane == 0) {
-        p.seg_count[blockIdx.x * kW + warp] = *cnt_p;
+        p.seg_count[blockIdx.x * kW + warp] = FOLD ? 0u : n_mine;
         tma::store_wait_read();               // shared memory must outlive the last store's reads
     }
 }
@@ -578,11 +613,23 @@ static cudaError_t launch_persistent_tma(K kernel, const FwdParams &p, cudaStrea
     return e;
 }
 
-template <int LAYOUT, bool ADAPTIVE, typename CFG>
-static cudaError_t launch_k1_tma(const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
+// Small planes fold the replay into K1's tail (one launch instead of two); see the kernel's tail for why large ones do not.
+static bool fold_small_plane(const FwdParams &p)
 {
-    return p.uniform_band ? launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, true, CFG>, p, s, launches, segments)
-                          : launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, false, CFG>, p, s, launches, segments);
+    static const bool no_fold = getenv("DCT_CUDA_NO_FOLD") != nullptr;   // measurement aid
+    return !no_fold && p.tab != nullptr && p.ctr != nullptr && p.nblocks <= kFoldMaxBlocks;
+}
+
+template <int LAYOUT, bool ADAPTIVE, typename CFG>
+static cudaError_t launch_k1_tma(const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments, bool *folded)
+{
+    if (fold_small_plane(p)) {
+        if (folded) *folded = true;
+        return p.uniform_band ? launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, true, CFG, true>, p, s, launches, segments)
+                              : launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, false, CFG, true>, p, s, launches, segments);
+    }
+    return p.uniform_band ? launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, true, CFG, false>, p, s, launches, segments)
+                          : launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, false, CFG, false>, p, s, launches, segments);
 }
 
 // the bulk-tensor kernel needs: the driver's tensor-map encoder, a 16-byte aligned plane whose pitch is a multiple
@@ -597,19 +644,16 @@ static bool tma_eligible(const FwdParams &p)
 }
 
 template <int LAYOUT, bool ADAPTIVE>
-static cudaError_t launch_k1(const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
+static cudaError_t launch_k1(const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments, bool *folded)
 {
     if (tma_eligible(p)) {
         // Geometry (measured on B200, 64 4K frames, profiles/r2_geometry.md): ONE CTA of 12 warps per SM with up to 168
         // registers per thread beats 3 x 8 warps at 80 registers (0.93 against 0.85 of the copy peak): fewer, fatter
         // warps keep more of a block's arithmetic in flight per warp and leave the memory system shallower queues.
-        // DCT_CUDA_K1_GEOMETRY (tuning aid): 1 = 16 warps x 1 CTA, 2 = 8 warps x 3 CTAs.
+        // DCT_CUDA_K1_GEOMETRY=2 (tuning aid): 8 warps x 3 CTAs.
         static const int variant = getenv("DCT_CUDA_K1_GEOMETRY") ? atoi(getenv("DCT_CUDA_K1_GEOMETRY")) : 0;
-        switch (variant) {
-        case 1: return launch_k1_tma<LAYOUT, ADAPTIVE, TmaCfg<16, 1, 2>>(p, s, launches, segments);
-        case 2: return launch_k1_tma<LAYOUT, ADAPTIVE, TmaCfg<8, 3, 2>>(p, s, launches, segments);
-        default: return launch_k1_tma<LAYOUT, ADAPTIVE, TmaCfg<12, 1, 2>>(p, s, launches, segments);
-        }
+        if (variant == 2) return launch_k1_tma<LAYOUT, ADAPTIVE, TmaCfg<8, 3, 2>>(p, s, launches, segments, folded);
+        return launch_k1_tma<LAYOUT, ADAPTIVE, TmaCfg<12, 1, 2>>(p, s, launches, segments, folded);
     }
     return p.uniform_band ? launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, true>, p, s, launches, segments)
                           : launch_persistent(k_fwd_quant_u8<LAYOUT, ADAPTIVE, false>, p, s, launches, segments);
@@ -625,16 +669,17 @@ cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s)
 }
 
 cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s, unsigned *launches,
-                                WorklistSegments *segments)
+                                WorklistSegments *segments, bool *folded)
 {
+    if (folded) *folded = false;
     if (launches) *launches = 0;
     if (segments) *segments = WorklistSegments{0, 0, 0};
     if (p.nblocks == 0) return cudaSuccess;
     if (layout == LAYOUT_ZIGZAG)
-        return adaptive ? launch_k1<LAYOUT_ZIGZAG, true>(p, s, launches, segments)
-                        : launch_k1<LAYOUT_ZIGZAG, false>(p, s, launches, segments);
-    return adaptive ? launch_k1<LAYOUT_NATURAL, true>(p, s, launches, segments)
-                    : launch_k1<LAYOUT_NATURAL, false>(p, s, launches, segments);
+        return adaptive ? launch_k1<LAYOUT_ZIGZAG, true>(p, s, launches, segments, folded)
+                        : launch_k1<LAYOUT_ZIGZAG, false>(p, s, launches, segments, folded);
+    return adaptive ? launch_k1<LAYOUT_NATURAL, true>(p, s, launches, segments, folded)
+                    : launch_k1<LAYOUT_NATURAL, false>(p, s, launches, segments, folded);
 }
 
 }  // namespace dctb

@@ -66,7 +66,13 @@ struct FwdParams {
     uint32_t seg_cap;          // worklist entries per segment (>= 32 * tiles per warp)
     uint32_t side_seg_cap;     // side slots per segment (entries beyond it have no pixel copy)
     int no_tma;                // 1: keep the cp.async kernel (planes mapped from a peer GPU)
+    // bulk-tensor kernel only: every warp replays the blocks of its own worklist segment at the end of its tile loop
+    // (replay_lane.cuh) instead of leaving them to a K3 launch; needs the exact tables
+    const ExactTables *tab;
 };
+
+// planes up to this many blocks (a 7680x4320 luma plane) replay their flagged blocks in the tail of K1 / K2 instead of a K3 launch
+constexpr uint32_t kFoldMaxBlocks = 600000;
 
 // geometry of the segmented worklist a k_fwd_quant_u8 launch produced (consumed by k_replay_fwd_lane)
 struct WorklistSegments {
@@ -103,6 +109,9 @@ struct InvParams {
     // bulk-tensor kernel only: every warp of the persistent grid appends to its OWN worklist segment (see FwdParams)
     uint32_t *seg_count;   // one entry per warp of the grid, or null (keeps the one-shot kernel and its atomic append)
     int no_tma;            // 1: keep the one-shot kernel (planes mapped from a peer GPU)
+    // bulk-tensor kernel only: every warp replays the blocks of its own worklist segment itself (replay_lane.cuh),
+    // in batches of 32 between tiles, instead of leaving them to a K3 launch; needs the exact tables
+    const ExactTables *tab;
 };
 
 // K3: exact fp64 replay of the blocks on the worklist (or of every block when wl == null).
@@ -131,12 +140,14 @@ struct ReplayParams {
 };
 
 // `launches` (optional) is incremented by the number of kernel launches made
+// `*folded` (optional) is set when the kernel replayed its flagged blocks itself (no K3 launch needed)
 cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s, unsigned *launches = nullptr,
-                                WorklistSegments *segments = nullptr);
+                                WorklistSegments *segments = nullptr, bool *folded = nullptr);
 constexpr uint32_t kMaxWorklistSegments = 4096;   // warps of the largest persistent grid this library launches
 cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s);
 // `segments`: geometry of the segmented worklist the launch produced (n_segs == 0: flat worklist counted in ctr->wl_count)
-cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments = nullptr);
+cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments = nullptr,
+                                   bool *folded = nullptr);
 cudaError_t launch_dequant_idct_u8_f64(const InvParams &p, const ExactTables *d_tab, int layout, cudaStream_t s);
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s);
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s);

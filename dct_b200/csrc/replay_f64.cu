@@ -15,41 +15,11 @@
 
 #include "fast_core.cuh"
 #include "kernels.cuh"
+#include "replay_lane.cuh"
 
 namespace dctb {
 
 namespace {
-
-// natural index -> zigzag position (inverse of the scan), for run-time indexing on the device
-struct ZigZagInv {
-    int pos[64];
-    constexpr ZigZagInv() : pos{}
-    {
-        ZigZag z{};
-        for (int p = 0; p < 64; ++p) pos[z.nat[p]] = p;
-    }
-};
-__constant__ ZigZagInv cZigZagInv{};
-
-// C99 round(): half away from zero.  (y - trunc(y)) is exact for |y| < 2^52.
-__device__ __forceinline__ double round_half_away(double y)
-{
-    const double t = trunc(y);
-    return (fabs(__dsub_rn(y, t)) >= 0.5) ? __dadd_rn(t, copysign(1.0, y)) : t;
-}
-
-__device__ __forceinline__ bool near_half(double a)
-{
-    a = fabs(a);
-    const double f = __dsub_rn(a, floor(a));
-    return fabs(__dsub_rn(f, 0.5)) <= 1e-9;
-}
-
-// src/quantization.c:186: fmin(1.0, fmax(0.1, variance / 1000.0))
-__device__ __forceinline__ double norm_variance(double variance)
-{
-    return fmin(1.0, fmax(0.1, __ddiv_rn(variance, 1000.0)));
-}
 
 constexpr int kReplayThreads = 256;                // 8 warps; a warp holds 4 blocks, 8 threads each
 
@@ -81,12 +51,6 @@ __device__ __forceinline__ unsigned long long group_or(unsigned long long m)
         m |= ((unsigned long long)hi << 32) | lo;
     }
     return m;
-}
-
-__device__ __forceinline__ double byte_centered(uint2 raw, int m)
-{
-    const unsigned w = m < 4 ? raw.x : raw.y;
-    return __dsub_rn((double)((w >> (8 * (m & 3))) & 0xFFu), 128.0);   // src/dct.c:115
 }
 
 struct ReplayShared {
@@ -334,14 +298,10 @@ __device__ __forceinline__ void find_segment(const unsigned *prefix, unsigned n_
 // value on its own: the reference's 64 + 8 non-contracted fp64 multiply-adds in its own order
 // (src/dct.c:57-74), true division, half-away rounding (src/quantization.c:122-126).
 // ------------------------------------------------------------------------------------------
-constexpr int kPairsPerRound = 4;                  // pairs one lane may append per round
 
 struct LaneShared {
     ExactTables tab;
-    uint2 px[kLaneWarps][32][9];                   // [warp][block][row + pad]: the blocks' pixels for the replay phase
-    unsigned blk[kLaneWarps][32];
-    double scale[kLaneWarps][32];                  // adaptive: 2 - nv of each block
-    unsigned short pairs[kLaneWarps][32 * kPairsPerRound];   // (source lane << 6) | natural index
+    LaneScratch scratch[kLaneWarps];
     unsigned prefix[kMaxWorklistSegments + 1];     // exclusive prefix sums of K1's per-warp worklist counts
 };
 
@@ -365,7 +325,7 @@ __global__ void __launch_bounds__(kLaneThreads, 4) k_replay_fwd_lane(const Repla
     const unsigned count = sh.prefix[n_segs];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned tiles = (count + 31) / 32, warps_per_grid = gridDim.x * kLaneWarps;
-    unsigned ties = 0, sat = 0;
+    const FwdReplayCtx cx{tab.r32, tab.thr32, tab.D, tab.Q, p.adaptive, p.coef_out, p.ctr};
 
     for (unsigned tile = blockIdx.x * kLaneWarps + warp; tile < tiles; tile += warps_per_grid) {
         const unsigned entry = tile * 32 + lane;
@@ -375,117 +335,12 @@ __global__ void __launch_bounds__(kLaneThreads, 4) k_replay_fwd_lane(const Repla
         const unsigned slot = local < p.seg.side_seg_cap ? seg * p.seg.side_seg_cap + local : 0xffffffffu;   // side slot
         const unsigned b = active ? p.worklist[(size_t)seg * p.seg.seg_cap + local] : 0;
         const unsigned by = b / p.bw, bx = b - by * p.bw;
-        const uint8_t *src = p.px_in + (long long)by * 8 * p.pitch + (long long)bx * 8;
-        uint2 row[8];
-        if (slot != 0xffffffffu && active) {      // K1 left the block's 64 pixels next to its worklist entry
-            const uint4 *sd = reinterpret_cast<const uint4 *>(p.side + (size_t)slot * 64);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint4 v = sd[i];
-                row[2 * i] = make_uint2(v.x, v.y), row[2 * i + 1] = make_uint2(v.z, v.w);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                row[i] = active ? *reinterpret_cast<const uint2 *>(src + i * p.pitch) : make_uint2(0x80808080u, 0x80808080u);
-        }
-
-        // ---- phase 1: K1's fp32 arithmetic for the whole block (rows, then columns), find the flagged coefficients
-        float c[64];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) fdct8_row_from_bytes(&c[8 * i], row[i]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) fdct8<float, 8>(&c[j]);          // c[8u + j] = scaled coefficient (u, j)
-        // adaptive tables: the block's variance from exact integer moments, as in K1 (src/quantization.c:153-190)
-        float inv_s = 1.0f;
-        double scale = 1.0;
-        if (p.adaptive) {
-            int isum = 0, isq = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) row_moments(row[i], isum, isq);
-            const double mean = __ddiv_rn((double)isum, 64.0);
-            const double var = __dsub_rn(__ddiv_rn((double)isq, 64.0), __dmul_rn(mean, mean));
-            scale = __dsub_rn(2.0, norm_variance(var));   // src/quantization.c:190
-            inv_s = adaptive_inv_scale(64 * isq - isum * isum);
-        }
-        unsigned need_lo = 0, need_hi = 0;
-#pragma unroll
-        for (int k = 0; k < 64; ++k) {
-            float t, e;
-            float rk = tab.r32[k];
-            if (k != 0) rk = __fmul_rn(rk, inv_s);        // inv_s == 1.0f exactly when the table is not adaptive
-            quant_residual(c[k], rk, t, e);
-            if (fabsf(e) >= tab.thr32[k]) (k < 32 ? need_lo : need_hi) |= 1u << (k & 31);
-        }
-        if (!active) need_lo = need_hi = 0;
-        if (p.adaptive) sh.scale[warp][lane] = scale;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sh.px[warp][lane][i] = row[i];
-        sh.blk[warp][lane] = b;
-
-        // ---- phase 2: rounds of (compact the pairs, one lane replays one value) until no lane has any left
-        while (__any_sync(0xffffffffu, (need_lo | need_hi) != 0)) {
-            const int mine = min(__popc(need_lo) + __popc(need_hi), kPairsPerRound);
-            int before = mine;                                       // inclusive prefix sum over the lanes
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, before, d);
-                if (lane >= d) before += v;
-            }
-            const int total = __shfl_sync(0xffffffffu, before, 31);
-            before -= mine;
-            for (int n = 0; n < mine; ++n) {
-                int k;
-                if (need_lo) {
-                    k = __ffs(need_lo) - 1;
-                    need_lo &= need_lo - 1;
-                } else {
-                    k = 32 + __ffs(need_hi) - 1;
-                    need_hi &= need_hi - 1;
-                }
-                sh.pairs[warp][before + n] = (unsigned short)((lane << 6) | k);
-            }
-            __syncwarp();
-            for (int pi = lane; pi < total; pi += 32) {
-                const unsigned pr = sh.pairs[warp][pi];
-                const int sl = pr >> 6, k = pr & 63, i = k >> 3, j = k & 7;
-                const double *Dj = &tab.D[j * 8], *Di = &tab.D[i * 8];
-                double dj[8];
-#pragma unroll
-                for (int m = 0; m < 8; ++m) dj[m] = Dj[m];
-                double out = 0.0;    // out[i][j] = sum_kk D[i][kk] * temp[kk][j]  (src/dct.c:67-74), kk ascending
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const uint2 raw = sh.px[warp][sl][kk];
-                    double temp = 0.0;   // temp[kk][j] = sum_m X[kk][m] * D[j][m]  (src/dct.c:57-64), m ascending
-#pragma unroll
-                    for (int m = 0; m < 8; ++m) temp = __dadd_rn(temp, __dmul_rn(byte_centered(raw, m), dj[m]));
-                    out = __dadd_rn(out, __dmul_rn(Di[kk], temp));
-                }
-                double mq = tab.Q[k];
-                if (p.adaptive && k != 0) {                          // src/quantization.c:196-204
-                    mq = __dmul_rn(mq, sh.scale[warp][sl]);
-                    if (mq < 1.0) mq = 1.0;
-                }
-                const double y = __ddiv_rn(out, mq);                 // src/quantization.c:124
-                const double rr = round_half_away(y);
-                int q = (int)rr;
-                if (rr > 32767.0) q = 32767, ++sat;
-                if (rr < -32768.0) q = -32768, ++sat;
-                ties += near_half(y);
-                const int pos = LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[k] : k;
-                p.coef_out[(size_t)sh.blk[warp][sl] * 64 + pos] = (int16_t)q;
-            }
-            __syncwarp();
-        }
+        // K1 left the block's 64 pixels next to its worklist entry (8-byte rows back to back); later slots read the plane
+        const bool side = slot != 0xffffffffu;
+        const uint8_t *src = side ? p.side + (size_t)slot * 64 : p.px_in + (long long)by * 8 * p.pitch + (long long)bx * 8;
+        replay_fwd_lanes<LAYOUT>(cx, &sh.scratch[warp], active, b, src, side ? 8 : p.pitch);
     }
 
-    ties = __reduce_add_sync(0xffffffffu, ties);
-    sat = __reduce_add_sync(0xffffffffu, sat);
-    if (lane == 0) {
-        if (ties) atomicAdd(&p.ctr->near_ties, (unsigned long long)ties);
-        if (sat) atomicAdd(&p.ctr->saturated, (unsigned long long)sat);
-    }
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
     // nothing to reset: the next K1 overwrites every segment count
 }
@@ -722,57 +577,18 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
 // (A first version redid the whole block with an fp64 butterfly per lane: 3 300 instructions per warp at 204
 // registers, latency-bound at two warps per scheduler -- slower than the kernel it replaced.)
 // ------------------------------------------------------------------------------------------
-// Sample (i, j) of one block in the reference's own operation order, non-adaptive tables:
-// in[m][k] = q * R (src/quantization.c:139,144), temp[i][k] = sum_m D[m][i] * in[m][k] (src/dct.c:85-92),
-// out = sum_k temp[i][k] * D[k][j] (:95-102), every sum from 0.0 in ascending order, no contraction.
-// The eight sums temp[i][0..7] advance together, m ascending for each of them (the reference's order per sum): eight
-// independent chains, and only row m of the coefficients is live at a time.  Not inlined: its registers are its own.
-template <int LAYOUT>
-__device__ __noinline__ double exact_inverse_sample(const uint4 *q4, const double *D, const double *R, int i, int j)
-{
-    uint32_t w[32];       // the record: one 128-byte line, eight 16-byte loads, indexed statically below
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint4 t = q4[c];
-        w[4 * c] = t.x, w[4 * c + 1] = t.y, w[4 * c + 2] = t.z, w[4 * c + 3] = t.w;
-    }
-    double di[8], temp[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) di[m] = D[m * 8 + i], temp[m] = 0.0;
-    static_for<0, 8>([&](auto M) {
-        constexpr int m = decltype(M)::value;
-        static_for<0, 8>([&](auto K) {
-            constexpr int k = decltype(K)::value;
-            constexpr int nat = 8 * m + k;
-            constexpr int pos = LAYOUT == LAYOUT_ZIGZAG ? ZigZagInv{}.pos[nat] : nat;
-            const int qq = (int)(int16_t)(pos & 1 ? (w[pos >> 1] >> 16) : (w[pos >> 1] & 0xFFFFu));
-            // (double)qq without a conversion instruction: (2^52 + 2^31 + qq) - (2^52 + 2^31), exact
-            const double qd = __dsub_rn(__hiloint2double(0x43300000, (int)((unsigned)qq ^ 0x80000000u)), 4503601774854144.0);
-            temp[k] = __dadd_rn(temp[k], __dmul_rn(di[m], __dmul_rn(qd, R[nat])));
-        });
-    });
-    double out = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) out = __dadd_rn(out, __dmul_rn(temp[k], D[k * 8 + j]));
-    return out;
-}
-
-// The tables this kernel indexes with compile-time constants travel as kernel parameters: they are read through the
-// constant bank as instruction operands instead of ~200 shared-memory loads per block (the first version of this
-// kernel stalled on exactly those: short_scoreboard / mio_throttle on top of its stall list).
+// The fp32 tables travel as kernel parameters (no table copy in the prologue); D and R, which the exact replay indexes
+// per lane, go to shared memory.
 struct InvLaneParams {
     ReplayParams p;
     float rs32[64], rg32[64], gain32[64];          // K2's fp32 tables (ExactTables)
-    double R[64];                                  // dequant_matrix as the host made it
     float band_floor;
 };
 
 struct LaneInvShared {
     double D[64];                                  // dct_matrix: indexed by the replayed pixel's (i, j), per lane
-    double R[64];                                  // dequant_matrix, for the (not inlined) exact replay
-    unsigned blk[kLaneWarps][32];
-    double inv_s[kLaneWarps][32];                  // adaptive: 1 / (2 - nv) of each block (src/quantization.c:193)
-    unsigned short pairs[kLaneWarps][32 * kPairsPerRound];   // (source lane << 6) | pixel index 8i + j
+    double R[64];                                  // dequant_matrix
+    InvLaneScratch scratch[kLaneWarps];
     unsigned prefix[kMaxWorklistSegments + 1];
 };
 
@@ -784,7 +600,7 @@ __global__ void __launch_bounds__(kLaneThreads, 5) k_replay_inv_lane(const __gri
     if (threadIdx.x < 64) sh.D[threadIdx.x] = p.tab->D[threadIdx.x], sh.R[threadIdx.x] = p.tab->R[threadIdx.x];
     __syncthreads();
     pdl_launch_dependents();
-    pdl_wait();                 // the table above is the plan's own; everything below is K2's output
+    pdl_wait();                 // the tables above are the plan's own; everything below is K2's output
     // segmented worklist (bulk-tensor K2: one segment per warp of its grid) or a flat one counted in ctr->wl_count
     const bool segmented = p.seg_count != nullptr && p.seg.n_segs != 0;
     const unsigned n_segs = p.seg.n_segs;
@@ -798,7 +614,7 @@ __global__ void __launch_bounds__(kLaneThreads, 5) k_replay_inv_lane(const __gri
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned tiles = (count + 31) / 32, warps_per_grid = gridDim.x * kLaneWarps;
-    unsigned ties = 0;
+    const InvReplayCtx cx{P.rs32, P.rg32, P.gain32, P.band_floor, sh.D, sh.R, p.coef_in, p.var_in, p.px_out, p.pitch, p.bw, p.ctr};
 
     // worklist entry -> block index; the entry of the NEXT tile is looked up, and its record's line requested from
     // L2, one tile ahead (two dependent global loads would otherwise sit at the head of every tile)
@@ -824,142 +640,9 @@ __global__ void __launch_bounds__(kLaneThreads, 5) k_replay_inv_lane(const __gri
         const bool active = active_n;
         const unsigned b = b_n;
         lookup(tile + warps_per_grid, active_n, b_n);
-        const int16_t *rec = p.coef_in + (size_t)b * 64;
-
-        float s32 = 1.0f;
-        if constexpr (ADAPTIVE) {
-            const double var = (p.var_in && active) ? p.var_in[b] : 0.0;
-            sh.inv_s[warp][lane] = __ddiv_rn(1.0, __dsub_rn(2.0, norm_variance(var)));
-            s32 = adaptive_scale(var);
-        }
-        sh.blk[warp][lane] = b;
-
-        // ---- phase 1: K2's fp32 arithmetic for the whole block (inv_block of dequant_idct.cu, scalar), flagged pixels
-        float v[64];
-        float bound = 0.f;
-        static_for<0, 8>([&](auto J) {
-            constexpr int j = decltype(J)::value;
-            const uint4 t = active ? reinterpret_cast<const uint4 *>(rec)[j] : make_uint4(0, 0, 0, 0);
-            const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
-            static_for<0, 4>([&](auto Hh) {
-                constexpr int h = decltype(Hh)::value;
-                constexpr int k0 = storage_to_natural<LAYOUT>(8 * j + 2 * h), k1 = storage_to_natural<LAYOUT>(8 * j + 2 * h + 1);
-                float f0 = half_to_float<0>(w4[h]), f1 = half_to_float<1>(w4[h]);
-                if constexpr (ADAPTIVE) {
-                    if (k0 != 0) f0 = __fmul_rn(f0, s32);
-                    f1 = __fmul_rn(f1, s32);
-                    v[k0] = __fmul_rn(f0, P.rs32[k0]);
-                    v[k1] = __fmul_rn(f1, P.rs32[k1]);
-                    bound = __fmaf_rn(fabsf(v[k0]), P.gain32[k0], bound);
-                    bound = __fmaf_rn(fabsf(v[k1]), P.gain32[k1], bound);
-                } else {
-                    v[k0] = f0, v[k1] = f1;
-                    bound = __fmaf_rn(fabsf(f0), P.rg32[k0], bound);
-                    bound = __fmaf_rn(fabsf(f1), P.rg32[k1], bound);
-                }
-            });
-        });
-        if constexpr (ADAPTIVE) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) idct8<float, 8>(&v[c]);
-        } else {
-            // K2's folded first stage (idct8_dequant), scalar: same operations on the same operands
-            constexpr int ra[4] = {0, 2, 5, 1}, rb[4] = {4, 6, 3, 7};
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float ma[4];
-                PosNeg1 mb[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ma[j] = P.rs32[8 * ra[j] + c];
-                    mb[j].pos = P.rs32[8 * rb[j] + c];
-                    mb[j].neg = -mb[j].pos;
-                }
-                idct8_dequant<float, 8>(&v[c], ma, mb);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) idct8<float, 1>(&v[8 * i]);
-        const float thr = pixel_threshold(bound, P.band_floor);
-        unsigned need_lo = 0, need_hi = 0;
-        if (!(bound < 1.4e5f)) {
-            need_lo = need_hi = 0xffffffffu;               // outside the int16 trick's range: K2 wrote nothing reliable
-        } else {
-#pragma unroll
-            for (int e = 0; e < 64; ++e) {
-                float t, r;
-                pixel_residual(v[e], t, r);
-                if (fabsf(r) >= thr) (e < 32 ? need_lo : need_hi) |= 1u << (e & 31);
-            }
-        }
-        if (!active) need_lo = need_hi = 0;
-
-        // ---- phase 2: rounds of (compact the pairs, one lane replays one pixel) until no lane has any left
-        while (__any_sync(0xffffffffu, (need_lo | need_hi) != 0)) {
-            const int mine = min(__popc(need_lo) + __popc(need_hi), kPairsPerRound);
-            int before = mine;                                       // inclusive prefix sum over the lanes
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int x = __shfl_up_sync(0xffffffffu, before, d);
-                if (lane >= d) before += x;
-            }
-            const int total = __shfl_sync(0xffffffffu, before, 31);
-            before -= mine;
-            for (int n = 0; n < mine; ++n) {
-                int e;
-                if (need_lo) {
-                    e = __ffs(need_lo) - 1;
-                    need_lo &= need_lo - 1;
-                } else {
-                    e = 32 + __ffs(need_hi) - 1;
-                    need_hi &= need_hi - 1;
-                }
-                sh.pairs[warp][before + n] = (unsigned short)((lane << 6) | e);
-            }
-            __syncwarp();
-            for (int pi = lane; pi < total; pi += 32) {
-                const unsigned pr = sh.pairs[warp][pi];
-                const int sl = pr >> 6, e = pr & 63, i = e >> 3, j = e & 7;
-                const unsigned bb = sh.blk[warp][sl];
-                const uint4 *q4 = reinterpret_cast<const uint4 *>(p.coef_in + (size_t)bb * 64);
-                const double inv_two_minus_nv = ADAPTIVE ? sh.inv_s[warp][sl] : 1.0;
-                // temp[i][k] = sum_m D[m][i] * in[m][k] (src/dct.c:85-92), out = sum_k temp[i][k] * D[k][j] (:95-102),
-                // both from 0.0 in ascending order; in = the reference's dequantised values (src/quantization.c:133-151)
-                double out = 0.0;
-                if constexpr (ADAPTIVE) {
-                    double di[8];
-#pragma unroll
-                    for (int m = 0; m < 8; ++m) di[m] = sh.D[m * 8 + i];
-                    // rare here (adaptive plans decode through the fp64 kernel, whose band flags true near-ties only):
-                    // compact loops, the reciprocal chain of src/quantization.c:137,144 value by value
-                    const int16_t *q = p.coef_in + (size_t)bb * 64;
-                    for (int k = 0; k < 8; ++k) {
-                        double temp = 0.0;
-                        for (int m = 0; m < 8; ++m) {
-                            const int nat = 8 * m + k;
-                            const int qq = q[LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[nat] : nat];
-                            double mm = P.R[nat];
-                            if (nat != 0) mm = __dmul_rn(mm, inv_two_minus_nv);
-                            temp = __dadd_rn(temp, __dmul_rn(di[m], __dmul_rn((double)qq, __ddiv_rn(1.0, mm))));
-                        }
-                        out = __dadd_rn(out, __dmul_rn(temp, sh.D[k * 8 + j]));
-                    }
-                } else {
-                    out = exact_inverse_sample<LAYOUT>(q4, sh.D, sh.R, i, j);
-                }
-                const double val = __dadd_rn(out, 128.0);
-                double rr = round_half_away(val);
-                rr = rr < 0.0 ? 0.0 : (rr > 255.0 ? 255.0 : rr);
-                ties += near_half(val);
-                const unsigned by = bb / p.bw, bx = bb - by * p.bw;
-                p.px_out[((long long)by * 8 + i) * p.pitch + (long long)bx * 8 + j] = (uint8_t)rr;
-            }
-            __syncwarp();
-        }
+        replay_inv_lanes<LAYOUT, ADAPTIVE>(cx, &sh.scratch[warp], active, b);
     }
 
-    ties = __reduce_add_sync(0xffffffffu, ties);
-    if (lane == 0 && ties) atomicAdd(&p.ctr->near_ties, (unsigned long long)ties);
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&p.ctr->replayed, (unsigned long long)count);
     if (!segmented) {
         // the last CTA to finish empties the flat worklist for the next K2 on this lane (saves a memset launch);
@@ -1073,7 +756,6 @@ cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s)
         memcpy(q.rs32, p.h_tab->rs32, sizeof q.rs32);
         memcpy(q.rg32, p.h_tab->rg32, sizeof q.rg32);
         memcpy(q.gain32, p.h_tab->gain32, sizeof q.gain32);
-        memcpy(q.R, p.h_tab->R, sizeof q.R);
         q.band_floor = p.h_tab->band_floor;
         if (p.adaptive)
             return p.layout == LAYOUT_ZIGZAG ? launch_pdl(k_replay_inv_lane<LAYOUT_ZIGZAG, true>, grid, kLaneThreads, 0, s, q)

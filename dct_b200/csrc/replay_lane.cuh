@@ -1,0 +1,381 @@
+// replay_lane.cuh -- the one-lane-per-block replay of flagged blocks, as device functions.
+//
+// K1 / K2 hand every block whose fp32 result sits inside the error band of a .5 rounding boundary to this code, which
+// repeats what the reference does (dct_forward src/dct.c:57-74, quantize src/quantization.c:113-131, dequantize
+// :133-151, dct_inverse src/dct.c:85-102) with the HOST-computed tables and non-contracted fp64 operations.
+// The functions are called from two places: the stand-alone replay kernels of replay_f64.cu (worklists of the cp.async /
+// one-shot kernels, float tiles) and the TAILS of the bulk-tensor kernels, where every warp replays the blocks of
+// its own worklist segment as soon as its tile loop is done -- no separate launch, no worklist round trip through
+// another grid, which is most of a single frame's latency and ~4 % of a large batch's time.
+// They are not inlined: their registers are their own and do not weigh on the tile loops that call them.
+#pragma once
+#include "fast_core.cuh"
+#include "kernels.cuh"
+
+namespace dctb {
+
+// natural index -> zigzag position (inverse of the scan), for run-time indexing on the device
+struct ZigZagInv {
+    int pos[64];
+    constexpr ZigZagInv() : pos{}
+    {
+        ZigZag z{};
+        for (int p = 0; p < 64; ++p) pos[z.nat[p]] = p;
+    }
+};
+__device__ __constant__ const ZigZagInv cZigZagInv{};
+
+// C99 round(): half away from zero.  (y - trunc(y)) is exact for |y| < 2^52.
+__device__ __forceinline__ double round_half_away(double y)
+{
+    const double t = trunc(y);
+    return (fabs(__dsub_rn(y, t)) >= 0.5) ? __dadd_rn(t, copysign(1.0, y)) : t;
+}
+
+__device__ __forceinline__ bool near_half(double a)
+{
+    a = fabs(a);
+    const double f = __dsub_rn(a, floor(a));
+    return fabs(__dsub_rn(f, 0.5)) <= 1e-9;
+}
+
+// src/quantization.c:186: fmin(1.0, fmax(0.1, variance / 1000.0))
+__device__ __forceinline__ double norm_variance(double variance)
+{
+    return fmin(1.0, fmax(0.1, __ddiv_rn(variance, 1000.0)));
+}
+
+__device__ __forceinline__ double byte_centered(uint2 raw, int m)
+{
+    const unsigned w = m < 4 ? raw.x : raw.y;
+    return __dsub_rn((double)((w >> (8 * (m & 3))) & 0xFFu), 128.0);   // src/dct.c:115
+}
+
+constexpr int kPairsPerRound = 4;                  // (block, value) pairs one lane may append per round
+
+// per-warp scratch of the lane replays (2 944 bytes; the bulk-tensor kernels lend their idle record stage)
+struct alignas(16) LaneScratch {
+    uint2 px[32][9];                               // [block][row + pad]: the blocks' pixels for the replay phase
+    unsigned blk[32];
+    double scale[32];                              // adaptive: 2 - nv (forward) or 1 / (2 - nv) (inverse) of each block
+    unsigned short pairs[32 * kPairsPerRound];     // (source lane << 6) | natural index
+};
+
+// where the forward replay finds its tables and its output (any address space behind the pointers)
+struct FwdReplayCtx {
+    const float *r32, *thr32;                      // K1's multipliers and thresholds, natural index
+    const double *D, *Q;                           // dct_matrix, quant_matrix as the host made them
+    int adaptive;
+    int16_t *coef;
+    Counters *ctr;
+};
+
+// One warp, up to 32 flagged blocks, one per lane (`active`, block index `b`, its 64 pixels at src + i * src_pitch).
+//   1. RE-FLAG: the lane repeats K1's fp32 arithmetic for its whole block in registers (the same fast_core.cuh
+//      functions, the same operation order per element, hence the same bits) to find WHICH coefficients sit inside
+//      the band; everything else in the block was already written correctly by K1 and is left alone;
+//   2. the warp compacts the flagged (block, coefficient) pairs into a list and every lane replays ONE value on its
+//      own: the reference's 64 + 8 non-contracted fp64 multiply-adds in its own order (src/dct.c:57-74), true
+//      division, half-away rounding (src/quantization.c:122-126), and patches it into the record.
+// Adds the near-tie / saturation counts to cx.ctr.  Every lane of the warp must call it.
+template <int LAYOUT>
+__device__ __noinline__ void replay_fwd_lanes(const FwdReplayCtx cx, LaneScratch *ws, bool active, unsigned b, const uint8_t *src,
+                                              long long src_pitch)
+{
+    const int lane = threadIdx.x & 31;
+    uint2 row[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        row[i] = active ? *reinterpret_cast<const uint2 *>(src + i * src_pitch) : make_uint2(0x80808080u, 0x80808080u);
+
+    // ---- phase 1: K1's fp32 arithmetic for the whole block (rows, then columns), find the flagged coefficients
+    float c[64];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fdct8_row_from_bytes(&c[8 * i], row[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fdct8<float, 8>(&c[j]);          // c[8u + j] = scaled coefficient (u, j)
+    // adaptive tables: the block's variance from exact integer moments, as in K1 (src/quantization.c:153-190)
+    float inv_s = 1.0f;
+    double scale = 1.0;
+    if (cx.adaptive) {
+        int isum = 0, isq = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) row_moments(row[i], isum, isq);
+        const double mean = __ddiv_rn((double)isum, 64.0);
+        const double var = __dsub_rn(__ddiv_rn((double)isq, 64.0), __dmul_rn(mean, mean));
+        scale = __dsub_rn(2.0, norm_variance(var));   // src/quantization.c:190
+        inv_s = adaptive_inv_scale(64 * isq - isum * isum);
+    }
+    unsigned need_lo = 0, need_hi = 0;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {
+        float t, e;
+        float rk = cx.r32[k];
+        if (k != 0) rk = __fmul_rn(rk, inv_s);        // inv_s == 1.0f exactly when the table is not adaptive
+        quant_residual(c[k], rk, t, e);
+        if (fabsf(e) >= cx.thr32[k]) (k < 32 ? need_lo : need_hi) |= 1u << (k & 31);
+    }
+    if (!active) need_lo = need_hi = 0;
+    __syncwarp();                                      // the scratch may still be read by the previous call's last round
+    if (cx.adaptive) ws->scale[lane] = scale;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ws->px[lane][i] = row[i];
+    ws->blk[lane] = b;
+    unsigned ties = 0, sat = 0;
+
+    // ---- phase 2: rounds of (compact the pairs, one lane replays one value) until no lane has any left
+    while (__any_sync(0xffffffffu, (need_lo | need_hi) != 0)) {
+        const int mine = min(__popc(need_lo) + __popc(need_hi), kPairsPerRound);
+        int before = mine;                                       // inclusive prefix sum over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, before, d);
+            if (lane >= d) before += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, before, 31);
+        before -= mine;
+        for (int n = 0; n < mine; ++n) {
+            int k;
+            if (need_lo) {
+                k = __ffs(need_lo) - 1;
+                need_lo &= need_lo - 1;
+            } else {
+                k = 32 + __ffs(need_hi) - 1;
+                need_hi &= need_hi - 1;
+            }
+            ws->pairs[before + n] = (unsigned short)((lane << 6) | k);
+        }
+        __syncwarp();
+        for (int pi = lane; pi < total; pi += 32) {
+            const unsigned pr = ws->pairs[pi];
+            const int sl = pr >> 6, k = pr & 63, i = k >> 3, j = k & 7;
+            const double *Dj = &cx.D[j * 8], *Di = &cx.D[i * 8];
+            double dj[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) dj[m] = Dj[m];
+            double out = 0.0;    // out[i][j] = sum_kk D[i][kk] * temp[kk][j]  (src/dct.c:67-74), kk ascending
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const uint2 raw = ws->px[sl][kk];
+                double temp = 0.0;   // temp[kk][j] = sum_m X[kk][m] * D[j][m]  (src/dct.c:57-64), m ascending
+#pragma unroll
+                for (int m = 0; m < 8; ++m) temp = __dadd_rn(temp, __dmul_rn(byte_centered(raw, m), dj[m]));
+                out = __dadd_rn(out, __dmul_rn(Di[kk], temp));
+            }
+            double mq = cx.Q[k];
+            if (cx.adaptive && k != 0) {                          // src/quantization.c:196-204
+                mq = __dmul_rn(mq, ws->scale[sl]);
+                if (mq < 1.0) mq = 1.0;
+            }
+            const double y = __ddiv_rn(out, mq);                 // src/quantization.c:124
+            const double rr = round_half_away(y);
+            int q = (int)rr;
+            if (rr > 32767.0) q = 32767, ++sat;
+            if (rr < -32768.0) q = -32768, ++sat;
+            ties += near_half(y);
+            const int pos = LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[k] : k;
+            cx.coef[(size_t)ws->blk[sl] * 64 + pos] = (int16_t)q;
+        }
+        __syncwarp();
+    }
+    ties = __reduce_add_sync(0xffffffffu, ties);
+    sat = __reduce_add_sync(0xffffffffu, sat);
+    if (lane == 0) {
+        if (ties) atomicAdd(&cx.ctr->near_ties, (unsigned long long)ties);
+        if (sat) atomicAdd(&cx.ctr->saturated, (unsigned long long)sat);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// inverse: dequantize (src/quantization.c:133-151) and dct_inverse (src/dct.c:80-105), one lane per flagged block
+// ------------------------------------------------------------------------------------------------------------------
+struct alignas(16) InvLaneScratch {
+    unsigned blk[32];
+    double inv_s[32];                              // adaptive: 1 / (2 - nv) of each block (src/quantization.c:193)
+    unsigned short pairs[32 * kPairsPerRound];     // (source lane << 6) | pixel index 8i + j
+};
+
+struct InvReplayCtx {
+    const float *rs32, *rg32, *gain32;             // K2's fp32 tables, natural index
+    float band_floor;
+    const double *D, *R;                           // dct_matrix, dequant_matrix as the host made them
+    const int16_t *coef;
+    const double *var;                             // adaptive: per-block variance (may be null)
+    uint8_t *px;
+    long long pitch;
+    uint32_t bw;
+    Counters *ctr;
+};
+
+// Sample (i, j) of one block in the reference's own operation order:
+// in[m][k] = the reference's dequantised value (src/quantization.c:133-151), temp[i][k] = sum_m D[m][i] * in[m][k] (src/dct.c:85-92),
+// out = sum_k temp[i][k] * D[k][j] (:95-102), every sum from 0.0 in ascending order, no contraction.
+// The eight sums temp[i][0..7] advance together, m ascending for each of them (the reference's order per sum): eight
+// independent chains, and only row m of the coefficients is live at a time.  Not inlined: its registers are its own.
+template <int LAYOUT, bool ADAPTIVE>
+__device__ __noinline__ double exact_inverse_sample(const uint4 *q4, const double *D, const double *R, double inv_two_minus_nv, int i, int j)
+{
+    uint32_t w[32];       // the record: one 128-byte line, eight 16-byte loads, indexed statically below
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 t = q4[c];
+        w[4 * c] = t.x, w[4 * c + 1] = t.y, w[4 * c + 2] = t.z, w[4 * c + 3] = t.w;
+    }
+    double di[8], temp[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) di[m] = D[m * 8 + i], temp[m] = 0.0;
+    static_for<0, 8>([&](auto M) {
+        constexpr int m = decltype(M)::value;
+        static_for<0, 8>([&](auto K) {
+            constexpr int k = decltype(K)::value;
+            constexpr int nat = 8 * m + k;
+            constexpr int pos = LAYOUT == LAYOUT_ZIGZAG ? ZigZagInv{}.pos[nat] : nat;
+            const int qq = (int)(int16_t)(pos & 1 ? (w[pos >> 1] >> 16) : (w[pos >> 1] & 0xFFFFu));
+            // (double)qq without a conversion instruction: (2^52 + 2^31 + qq) - (2^52 + 2^31), exact
+            const double qd = __dsub_rn(__hiloint2double(0x43300000, (int)((unsigned)qq ^ 0x80000000u)), 4503601774854144.0);
+            double in;
+            if constexpr (ADAPTIVE) {      // q * (1.0 / (R * (1/(2-nv)))), DC unscaled (src/quantization.c:137,144,193-201)
+                double mm = R[nat];
+                if (nat != 0) mm = __dmul_rn(mm, inv_two_minus_nv);
+                in = __dmul_rn(qd, __ddiv_rn(1.0, mm));
+            } else {
+                in = __dmul_rn(qd, R[nat]);    // q * R (src/quantization.c:139,144)
+            }
+            temp[k] = __dadd_rn(temp[k], __dmul_rn(di[m], in));
+        });
+    });
+    double out = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out = __dadd_rn(out, __dmul_rn(temp[k], D[k * 8 + j]));
+    return out;
+}
+
+
+// One warp, up to 32 flagged blocks, one per lane.
+//   1. RE-FLAG: the lane repeats K2's fp32 arithmetic for its whole block in registers (the same fast_core.cuh /
+//      butterfly.cuh functions, scalar instantiation: bit-identical per element to K2's packed lanes) to find WHICH
+//      pixels sit inside the band -- with a wide dynamic band (high-quality tables) that is typically ONE pixel of
+//      the block; every other pixel is already right in memory and is not touched;
+//   2. the warp compacts the flagged (block, pixel) pairs into a list and every lane replays ONE pixel on its own,
+//      in the reference's own operation order (exact_inverse_sample), then the pixel rule; one byte store.
+// Adds the near-tie count to cx.ctr.  Every lane of the warp must call it.
+template <int LAYOUT, bool ADAPTIVE>
+__device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScratch *ws, bool active, unsigned b)
+{
+    const int lane = threadIdx.x & 31;
+    const int16_t *rec = cx.coef + (size_t)b * 64;
+    float s32 = 1.0f;
+    __syncwarp();                                      // the scratch may still be read by the previous call's last round
+    if constexpr (ADAPTIVE) {
+        const double var = (cx.var && active) ? cx.var[b] : 0.0;
+        ws->inv_s[lane] = __ddiv_rn(1.0, __dsub_rn(2.0, norm_variance(var)));
+        s32 = adaptive_scale(var);
+    }
+    ws->blk[lane] = b;
+
+    // ---- phase 1: K2's fp32 arithmetic for the whole block (inv_block of dequant_idct.cu, scalar), flagged pixels
+    float v[64];
+    float bound = 0.f;
+    static_for<0, 8>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        const uint4 t = active ? reinterpret_cast<const uint4 *>(rec)[j] : make_uint4(0, 0, 0, 0);
+        const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+        static_for<0, 4>([&](auto Hh) {
+            constexpr int h = decltype(Hh)::value;
+            constexpr int k0 = storage_to_natural<LAYOUT>(8 * j + 2 * h), k1 = storage_to_natural<LAYOUT>(8 * j + 2 * h + 1);
+            float f0 = half_to_float<0>(w4[h]), f1 = half_to_float<1>(w4[h]);
+            if constexpr (ADAPTIVE) {
+                if (k0 != 0) f0 = __fmul_rn(f0, s32);
+                f1 = __fmul_rn(f1, s32);
+                v[k0] = __fmul_rn(f0, cx.rs32[k0]);
+                v[k1] = __fmul_rn(f1, cx.rs32[k1]);
+                bound = __fmaf_rn(fabsf(v[k0]), cx.gain32[k0], bound);
+                bound = __fmaf_rn(fabsf(v[k1]), cx.gain32[k1], bound);
+            } else {
+                v[k0] = f0, v[k1] = f1;
+                bound = __fmaf_rn(fabsf(f0), cx.rg32[k0], bound);
+                bound = __fmaf_rn(fabsf(f1), cx.rg32[k1], bound);
+            }
+        });
+    });
+    if constexpr (ADAPTIVE) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) idct8<float, 8>(&v[c]);
+    } else {
+        // K2's folded first stage (idct8_dequant), scalar: same operations on the same operands
+        constexpr int ra[4] = {0, 2, 5, 1}, rb[4] = {4, 6, 3, 7};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float ma[4];
+            PosNeg1 mb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ma[j] = cx.rs32[8 * ra[j] + c];
+                mb[j].pos = cx.rs32[8 * rb[j] + c];
+                mb[j].neg = -mb[j].pos;
+            }
+            idct8_dequant<float, 8>(&v[c], ma, mb);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) idct8<float, 1>(&v[8 * i]);
+    const float thr = pixel_threshold(bound, cx.band_floor);
+    unsigned need_lo = 0, need_hi = 0;
+    if (!(bound < 1.4e5f)) {
+        need_lo = need_hi = 0xffffffffu;               // outside the int16 trick's range: K2 wrote nothing reliable
+    } else {
+#pragma unroll
+        for (int e = 0; e < 64; ++e) {
+            float t, r;
+            pixel_residual(v[e], t, r);
+            if (fabsf(r) >= thr) (e < 32 ? need_lo : need_hi) |= 1u << (e & 31);
+        }
+    }
+    if (!active) need_lo = need_hi = 0;
+    unsigned ties = 0;
+
+    // ---- phase 2: rounds of (compact the pairs, one lane replays one pixel) until no lane has any left
+    while (__any_sync(0xffffffffu, (need_lo | need_hi) != 0)) {
+        const int mine = min(__popc(need_lo) + __popc(need_hi), kPairsPerRound);
+        int before = mine;                                       // inclusive prefix sum over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, before, d);
+            if (lane >= d) before += x;
+        }
+        const int total = __shfl_sync(0xffffffffu, before, 31);
+        before -= mine;
+        for (int n = 0; n < mine; ++n) {
+            int e;
+            if (need_lo) {
+                e = __ffs(need_lo) - 1;
+                need_lo &= need_lo - 1;
+            } else {
+                e = 32 + __ffs(need_hi) - 1;
+                need_hi &= need_hi - 1;
+            }
+            ws->pairs[before + n] = (unsigned short)((lane << 6) | e);
+        }
+        __syncwarp();
+        for (int pi = lane; pi < total; pi += 32) {
+            const unsigned pr = ws->pairs[pi];
+            const int sl = pr >> 6, e = pr & 63, i = e >> 3, j = e & 7;
+            const unsigned bb = ws->blk[sl];
+            const uint4 *q4 = reinterpret_cast<const uint4 *>(cx.coef + (size_t)bb * 64);
+            const double inv_two_minus_nv = ADAPTIVE ? ws->inv_s[sl] : 1.0;
+            const double out = exact_inverse_sample<LAYOUT, ADAPTIVE>(q4, cx.D, cx.R, inv_two_minus_nv, i, j);
+            const double val = __dadd_rn(out, 128.0);
+            double rr = round_half_away(val);
+            rr = rr < 0.0 ? 0.0 : (rr > 255.0 ? 255.0 : rr);
+            ties += near_half(val);
+            const unsigned by = bb / cx.bw, bx = bb - by * cx.bw;
+            cx.px[((long long)by * 8 + i) * cx.pitch + (long long)bx * 8 + j] = (uint8_t)rr;
+        }
+        __syncwarp();
+    }
+    ties = __reduce_add_sync(0xffffffffu, ties);
+    if (lane == 0 && ties) atomicAdd(&cx.ctr->near_ties, (unsigned long long)ties);
+}
+
+}  // namespace dctb

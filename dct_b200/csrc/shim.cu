@@ -269,6 +269,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
     rp.side_cap = use_side ? ln.side_cap : 0;
     rp.coef_out = d_coef;
     rp.var_out = p->adaptive ? d_var : nullptr;
+    bool folded = false;                                  // K1 replayed its flagged blocks itself: no K3 launch
     if (!p->exotic) {
         FwdParams fp{};
         fp.px = d_px;
@@ -288,6 +289,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
         fp.side_cap = use_side ? ln.side_cap : 0;
         fp.seg_count = ln.d_seg_count;
         fp.no_tma = p->no_tma ? 1 : 0;
+        fp.tab = p->skip_replay ? nullptr : p->d_tab;     // lets the bulk-tensor kernel replay its own flagged blocks
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (p->profile) {
             CU_TRY(cudaEventCreate(&e0));
@@ -298,7 +300,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
         if (elem == 4) {
             CU_TRY(launch_fwd_quant_f32(fp, layout, s));
         } else {
-            CU_TRY(launch_fwd_quant_u8(fp, layout, p->adaptive, s, &k1_launches, &rp.seg));
+            CU_TRY(launch_fwd_quant_u8(fp, layout, p->adaptive, s, &k1_launches, &rp.seg, &folded));
             rp.seg_count = ln.d_seg_count;
         }
         p->launches += k1_launches;
@@ -308,7 +310,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
         }
         rp.worklist = ln.d_wl;
     }
-    if (!p->skip_replay || p->exotic) {
+    if ((!p->skip_replay || p->exotic) && !folded) {
         CU_TRY(launch_replay_fwd(rp, s));
         ++p->launches;
     }
@@ -345,6 +347,7 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
     rp.coef_in = d_coef;
     rp.var_in = p->adaptive ? d_var : nullptr;
     rp.px_out = d_px;
+    bool folded = false;                                  // K2 replayed its flagged blocks itself: no K3 launch
     if (!p->exotic) {
         InvParams ip{};
         ip.coef = d_coef;
@@ -362,6 +365,7 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
         ip.band_floor = p->band_floor;
         ip.seg_count = ln.d_seg_count;
         ip.no_tma = p->no_tma ? 1 : 0;
+        ip.tab = p->skip_replay ? nullptr : p->d_tab;     // lets the bulk-tensor kernel replay its own flagged blocks
         {   // multipliers of the folded first stage, in the kernel's pair order
             static const int colA[4] = {0, 2, 5, 1}, colB[4] = {4, 6, 3, 7};
             for (int c = 0; c < 4; ++c)
@@ -382,7 +386,7 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
         if (p->adaptive && !p->force_fp32_inverse) {
             CU_TRY(launch_dequant_idct_u8_f64(ip, p->d_tab, layout, s));
         } else {
-            CU_TRY(launch_dequant_idct_u8(ip, layout, p->adaptive, s, &rp.seg));
+            CU_TRY(launch_dequant_idct_u8(ip, layout, p->adaptive, s, &rp.seg, &folded));
             if (rp.seg.n_segs) rp.seg_count = ln.d_seg_count;     // segmented worklist (bulk-tensor kernel)
         }
         ++p->launches;
@@ -392,7 +396,7 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
         }
         rp.worklist = ln.d_wl;
     }
-    if (!p->skip_replay || p->exotic) {
+    if ((!p->skip_replay || p->exotic) && !folded) {
         CU_TRY(launch_replay_inv(rp, s));
         ++p->launches;
     }

@@ -6,6 +6,7 @@ allows).  Full BASELINE.json sizes are covered by direct comparison where the or
 seconds and by size-independent properties otherwise."""
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -1038,3 +1039,27 @@ def test_int8_records_with_other_block_sizes(api, oracle, n, quality, ok):
     finally:
         plan.close()
         api.dct_free(d), api.quant_free(q)
+
+
+# ---------------------------------------------------------------------------------------------
+# every kernel path gives the same bytes: bulk-tensor (default) / cp.async and one-shot kernels, the kernel
+# geometries behind the tuning knobs, programmatic dependent launch on and off.  The switches are read once per
+# process, hence one subprocess per setting (tools/kbench.py prints a hash of the records and the pixels).
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("extra", [["--quality", "50"], ["--quality", "92", "--layout", "1"], ["--adaptive", "1"]])
+def test_kernel_paths_are_interchangeable(extra):
+    import json
+    import subprocess
+
+    def run(env):
+        e = dict(os.environ, **env)
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "kbench.py"), "--W", "1920", "--H", "1080", "--frames", "3",
+                              "--steps", "1"] + extra, env=e, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return json.loads(out.stdout.strip().splitlines()[-1])
+
+    base = run({})
+    for env in ({"DCT_CUDA_NO_TMA": "1"}, {"DCT_CUDA_K1_GEOMETRY": "2", "DCT_CUDA_K2_GEOMETRY": "2"},
+                {"DCT_CUDA_NO_PDL": "1"}, {"DCT_CUDA_NO_FOLD": "1"}):
+        got = run(env)
+        assert got["sha1"] == base["sha1"] and got["ties"] == base["ties"] and got["replayed_frac"] == base["replayed_frac"], (env, got, base)
