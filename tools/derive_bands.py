@@ -11,6 +11,10 @@ below op for op), and writes dct_b200/csrc/band_tables.h.
     python tools/derive_bands.py            # regenerate the header
     python tools/derive_bands.py --check    # empirical check of the bound with an fp32 emulation
 
+(The byte loader of fast_core.cuh feeds the first two forward stages with a 2^15 bias per sample; every value there is
+an integer below 2^19, so those operations are exact with or without it and the model below, which sees the centred
+samples, describes the same values.)
+
 Model of one fp32 operation (round-to-nearest, u = 2^-24):
     fl(a+b)   = (a+b)(1+d), |d| <= u ; exact when both are error-free integers and |a+b| < 2^24
     fl(a*c+b) = (a*c+b)(1+d)          (fused, single rounding; c is a float32 constant)
