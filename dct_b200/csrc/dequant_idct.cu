@@ -46,36 +46,30 @@ __device__ __forceinline__ void stg_stream_u2(void *p, uint32_t a, uint32_t b)
 // The arithmetic of one block, shared by the one-shot and the bulk-tensor kernels: w[m] = packed int16 pair m of the
 // record in storage order; writes the block's 64 pixels (if valid); returns "replay this block in fp64".
 template <int LAYOUT, bool ADAPTIVE>
-__device__ __forceinline__ bool inv_block(const InvParams &p, const uint32_t (&w)[32], bool valid, uint32_t b, uint8_t *dst)
+__device__ __forceinline__ bool inv_block(const InvParams &p, const uint32_t (&w)[32], bool valid, uint8_t *dst, double var)
 {
     float s = 1.0f;
-    if constexpr (ADAPTIVE) {
-        // multiplier 1/((1/Q)*(1/(2-nv))) = Q*(2-nv) up to fp64 rounding; exact form in K3
-        const double var = (p.var_in != nullptr && valid) ? p.var_in[b] : 0.0;
-        s = adaptive_scale(var);
-    }
+    // ADAPTIVE: `var` = the block's variance (side information); multiplier 1/((1/Q)*(1/(2-nv))) = Q*(2-nv) up to
+    // fp64 rounding (rs holds Q * prescale); exact form in K3
+    if constexpr (ADAPTIVE) s = adaptive_scale(var);
 
-    // ADAPTIVE: v = (q * s) * rs, then the plain butterfly.  Otherwise v holds the converted q themselves and the
-    // multiplication happens inside the first butterfly stage (idct8_dequant: one FMA gives v_a +- q_b * rs_b).
+    // v holds the converted q themselves: the multiplication by the table happens inside the first butterfly stage
+    // (idct8_dequant: one FMA gives v_a +- q_b * rs_b).  ADAPTIVE: the block's factor (2 - nv) goes into the 32
+    // multiplier pairs (48 packed multiplications per block; the DC entry keeps the unscaled table,
+    // src/quantization.c:199-201) -- the product rs_k * s is one more rounding inside the 8u the inputs are allowed.
     float v[64];
-    float bound = 0.f;   // >= sum gain_k * |v_k|
+    float bound = 0.f, bound_dc = 0.f;   // bound >= sum gain_k * |v_k|
     static_for<0, 32>([&](auto M) {
         constexpr int m = decltype(M)::value;
         constexpr int k0 = storage_to_natural<LAYOUT>(2 * m), k1 = storage_to_natural<LAYOUT>(2 * m + 1);
-        float f0 = half_to_float<0>(w[m]), f1 = half_to_float<1>(w[m]);
-        if constexpr (ADAPTIVE) {
-            if (k0 != 0) f0 = __fmul_rn(f0, s);
-            f1 = __fmul_rn(f1, s);
-            v[k0] = __fmul_rn(f0, p.rs[k0]);
-            v[k1] = __fmul_rn(f1, p.rs[k1]);
-            bound = __fmaf_rn(fabsf(v[k0]), p.gain[k0], bound);
-            bound = __fmaf_rn(fabsf(v[k1]), p.gain[k1], bound);
-        } else {
-            v[k0] = f0, v[k1] = f1;
-            bound = __fmaf_rn(fabsf(f0), p.rg[k0], bound);
-            bound = __fmaf_rn(fabsf(f1), p.rg[k1], bound);
-        }
+        const float f0 = half_to_float<0>(w[m]), f1 = half_to_float<1>(w[m]);
+        v[k0] = f0, v[k1] = f1;
+        if (ADAPTIVE && k0 == 0) bound_dc = __fmul_rn(fabsf(f0), p.rg[0]);
+        else bound = __fmaf_rn(fabsf(f0), p.rg[k0], bound);
+        if (ADAPTIVE && k1 == 0) bound_dc = __fmul_rn(fabsf(f1), p.rg[0]);
+        else bound = __fmaf_rn(fabsf(f1), p.rg[k1], bound);
     });
+    if constexpr (ADAPTIVE) bound = adaptive_bound(bound, bound_dc, s);
     // |fp32 pixel - exact pixel| <= 2^-24 * bound (derive_bands.py) ; + floor for the residual's own rounding
     const float thr = pixel_threshold(bound, p.band_floor);
 
@@ -90,8 +84,21 @@ __device__ __forceinline__ bool inv_block(const InvParams &p, const uint32_t (&w
     for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) cpv[c][i] = make_float2(v[8 * i + kPairA[c]], v[8 * i + kPairB[c]]);
-        if constexpr (ADAPTIVE) idct8<float2, 1>(cpv[c]);
-        else idct8_dequant<float2, 1>(cpv[c], p.ma[c], p.mb[c]);
+        if constexpr (ADAPTIVE) {
+            const float2 s2 = make_float2(s, s);
+            float2 mas[4];
+            PosNeg2 mbs[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                mas[j] = Ops<float2>::mul(p.ma[c][j], s2);
+                mbs[j].pos = Ops<float2>::mul(p.mb[c][j].pos, s2);
+                mbs[j].neg = Ops<float2>::mul(p.mb[c][j].neg, s2);
+            }
+            if (c == 0) mas[0].x = p.ma[0][0].x;          // natural index 0: the DC entry is not scaled
+            idct8_dequant<float2, 1>(cpv[c], mas, mbs);
+        } else {
+            idct8_dequant<float2, 1>(cpv[c], p.ma[c], p.mb[c]);
+        }
     }
 
     // Row pass on row pairs (2a, 2a+1), then per pixel: t = x + (1.5*2^23 + 128): the low 16 mantissa bits
@@ -178,7 +185,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_dequant_idct_u8(const __grid_co
 
     const uint32_t bb = valid ? b : p.nblocks - 1;
     const uint32_t by = bb / p.bw, bx = bb - by * p.bw;
-    const bool flag = inv_block<LAYOUT, ADAPTIVE>(p, w, valid, b, p.px + (long long)by * 8 * p.pitch + (long long)bx * 8);
+    const double var = (ADAPTIVE && p.var_in != nullptr && valid) ? p.var_in[b] : 0.0;
+    const bool flag = inv_block<LAYOUT, ADAPTIVE>(p, w, valid, p.px + (long long)by * 8 * p.pitch + (long long)bx * 8, var);
 
     const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
     if (ballot != 0) {
@@ -278,7 +286,7 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
     auto replay_batch = [&](uint32_t n) {
         if constexpr (!FOLD) return;
         __syncwarp();                                     // the pixels K2 stored above are patched by other lanes below
-        const InvReplayCtx cx{p.rs, p.rg, p.gain, p.band_floor, p.tab->D, p.tab->R, p.coef, p.var_in, p.px, p.pitch, p.bw, p.ctr};
+        const InvReplayCtx cx{p.rs, p.rg, p.band_floor, p.tab->D, p.tab->R, p.tab->mult64, p.coef, p.var_in, p.px, p.pitch, p.bw, p.ctr};
         const bool active = lane < n;
         const uint32_t b = active ? p.worklist[(size_t)gwarp * P.seg_cap + replayed_n + lane] : 0u;
         replay_inv_lanes<LAYOUT, ADAPTIVE>(cx, ws, active, b);
@@ -292,6 +300,9 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
         const uint32_t nvalid = min(32u, p.bw - bx0);
         uint8_t *dst = p.px + (long long)ty * 8 * p.pitch + (long long)(bx0 + lane) * 8;
         fetch();                                                  // into the stage the previous iteration consumed
+        // adaptive plans: the lane's variance (8 bytes of side information per block).  Loading it one tile ahead was
+        // measured slower (353 against 334 us per 64 4K frames: the kernel sits on its 128 registers)
+        const double var = (ADAPTIVE && p.var_in != nullptr && lane < nvalid) ? p.var_in[warp_base + lane] : 0.0;
         tma::mbar_wait(bar_s + stage * 8, phase);
 
         const uint32_t b = warp_base + lane;
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
         }
         __syncwarp();           // every lane has its record: the next fetch overwrites this stage
 
-        const bool flag = inv_block<LAYOUT, ADAPTIVE>(p, w, valid, b, dst);
+        const bool flag = inv_block<LAYOUT, ADAPTIVE>(p, w, valid, dst, var);
         const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
         if (ballot != 0) {
             if (flag && valid) p.worklist[(size_t)gwarp * P.seg_cap + wl_n + __popc(ballot & ((1u << lane) - 1u))] = b;

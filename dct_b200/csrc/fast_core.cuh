@@ -94,6 +94,13 @@ __device__ __forceinline__ float adaptive_scale(double var)
     return __fsub_rn(2.0f, nv);
 }
 
+// K2, adaptive plans: bound >= sum_k gain_k |q_k rs_k s| from the sum over the AC entries taken with the unscaled table
+// (`ac`), the DC entry's own term (`dc`) and the block's factor s = 2 - nv; 1.00001 covers the rounding of rs_k * s
+__device__ __forceinline__ float adaptive_bound(float ac, float dc, float s)
+{
+    return __fmaf_rn(ac, __fmul_rn(s, 1.00001f), dc);
+}
+
 // quantise one coefficient: t holds round(c*r) in its low mantissa bits, e = c*r - round(c*r)
 __device__ __forceinline__ void quant_residual(float c, float r, float &t, float &e)
 {

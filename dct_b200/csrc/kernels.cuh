@@ -37,6 +37,7 @@ struct ExactTables {
     // K3 inverse (one lane per block): sum_k gain_k * |mp64_k| * max(2 - nv), so that bound_per_q * max_k |q_k| bounds
     // sum_k gain_k * |dequantised value k| without a pass over the 64 values
     double bound_per_q;
+    double mult64[64];  // dequantisation multiplier in fp64: R (non-adaptive, sic) or 1/R (adaptive); for the fast fp64 settle in K3
 };
 
 // K1: forward DCT + quantise.  One thread per 8x8 block.

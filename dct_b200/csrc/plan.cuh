@@ -88,7 +88,7 @@ struct dct_cuda_plan {
     uint32_t *d_rle_sums = nullptr;             // K5 workspace: per-CTA symbol totals + the grand total
     size_t rle_sums_cap = 0;
     unsigned long long *d_rle_total = nullptr;
-    bool force_fp32_inverse = false;            // DCT_CUDA_INV_FP32=1: keep the fp32 inverse for adaptive plans too
+    bool fp64_inverse = false;                  // DCT_CUDA_INV_FP64=1: adaptive plans decode through the fp64 K2
     bool skip_replay = false;                   // test hook: leave K1/K2's fast-path values unpatched
     // whole-frame RGB 4:2:0 calls (luma plan only): device copy of the frame, its planes and records
     uint8_t *d_frame = nullptr;

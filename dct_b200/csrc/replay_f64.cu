@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
 // per lane, go to shared memory.
 struct InvLaneParams {
     ReplayParams p;
-    float rs32[64], rg32[64], gain32[64];          // K2's fp32 tables (ExactTables)
+    float rs32[64], rg32[64];                      // K2's fp32 tables (ExactTables)
     float band_floor;
 };
 
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(kLaneThreads, 5) k_replay_inv_lane(const __gri
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned tiles = (count + 31) / 32, warps_per_grid = gridDim.x * kLaneWarps;
-    const InvReplayCtx cx{P.rs32, P.rg32, P.gain32, P.band_floor, sh.D, sh.R, p.coef_in, p.var_in, p.px_out, p.pitch, p.bw, p.ctr};
+    const InvReplayCtx cx{P.rs32, P.rg32, P.band_floor, sh.D, sh.R, p.tab->mult64, p.coef_in, p.var_in, p.px_out, p.pitch, p.bw, p.ctr};
 
     // worklist entry -> block index; the entry of the NEXT tile is looked up, and its record's line requested from
     // L2, one tile ahead (two dependent global loads would otherwise sit at the head of every tile)
@@ -755,7 +755,6 @@ cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s)
         q.p = p;
         memcpy(q.rs32, p.h_tab->rs32, sizeof q.rs32);
         memcpy(q.rg32, p.h_tab->rg32, sizeof q.rg32);
-        memcpy(q.gain32, p.h_tab->gain32, sizeof q.gain32);
         q.band_floor = p.h_tab->band_floor;
         if (p.adaptive)
             return p.layout == LAYOUT_ZIGZAG ? launch_pdl(k_replay_inv_lane<LAYOUT_ZIGZAG, true>, grid, kLaneThreads, 0, s, q)

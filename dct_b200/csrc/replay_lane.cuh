@@ -193,13 +193,16 @@ __device__ __noinline__ void replay_fwd_lanes(const FwdReplayCtx cx, LaneScratch
 struct alignas(16) InvLaneScratch {
     unsigned blk[32];
     double inv_s[32];                              // adaptive: 1 / (2 - nv) of each block (src/quantization.c:193)
+    double s[32];                                  // adaptive: 2 - nv
+    float bound[32];                               // the block's fp32 bound (sum gain_k |v_k|)
     unsigned short pairs[32 * kPairsPerRound];     // (source lane << 6) | pixel index 8i + j
 };
 
 struct InvReplayCtx {
-    const float *rs32, *rg32, *gain32;             // K2's fp32 tables, natural index
+    const float *rs32, *rg32;                      // K2's fp32 tables, natural index
     float band_floor;
     const double *D, *R;                           // dct_matrix, dequant_matrix as the host made them
+    const double *mult;                            // adaptive: 1 / R in fp64 (ExactTables::mult64), for the fast settle
     const int16_t *coef;
     const double *var;                             // adaptive: per-block variance (may be null)
     uint8_t *px;
@@ -252,6 +255,40 @@ __device__ __noinline__ double exact_inverse_sample(const uint4 *q4, const doubl
 }
 
 
+// Sample (i, j) of one block in plain fp64 (fused multiply-adds, any order): sum_uv q_uv * mult_uv * s_uv * D[u][i] * D[v][j].
+// Within ~1e-13 of the reference's value, at an eighth of the cost of its reciprocal chain (src/quantization.c:137,144
+// divides once per coefficient): settles every flagged pixel of an adaptive plan that is not a true near-tie.
+template <int LAYOUT>
+__device__ __noinline__ double fast_inverse_sample(const uint4 *q4, const double *D, const double *mult, double s, int i, int j)
+{
+    uint32_t w[32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 t = q4[c];
+        w[4 * c] = t.x, w[4 * c + 1] = t.y, w[4 * c + 2] = t.z, w[4 * c + 3] = t.w;
+    }
+    double di[8], temp[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) di[m] = D[m * 8 + i], temp[m] = 0.0;
+    static_for<0, 8>([&](auto M) {
+        constexpr int m = decltype(M)::value;
+        static_for<0, 8>([&](auto K) {
+            constexpr int k = decltype(K)::value;
+            constexpr int nat = 8 * m + k;
+            constexpr int pos = LAYOUT == LAYOUT_ZIGZAG ? ZigZagInv{}.pos[nat] : nat;
+            const int qq = (int)(int16_t)(pos & 1 ? (w[pos >> 1] >> 16) : (w[pos >> 1] & 0xFFFFu));
+            const double qd = __hiloint2double(0x43300000, (int)((unsigned)qq ^ 0x80000000u)) - 4503601774854144.0;
+            double c = qd * mult[nat];
+            if (nat != 0) c *= s;
+            temp[k] = fma(di[m], c, temp[k]);
+        });
+    });
+    double out = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out = fma(temp[k], D[k * 8 + j], out);
+    return out;
+}
+
 // One warp, up to 32 flagged blocks, one per lane.
 //   1. RE-FLAG: the lane repeats K2's fp32 arithmetic for its whole block in registers (the same fast_core.cuh /
 //      butterfly.cuh functions, scalar instantiation: bit-identical per element to K2's packed lanes) to find WHICH
@@ -269,14 +306,16 @@ __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScra
     __syncwarp();                                      // the scratch may still be read by the previous call's last round
     if constexpr (ADAPTIVE) {
         const double var = (cx.var && active) ? cx.var[b] : 0.0;
-        ws->inv_s[lane] = __ddiv_rn(1.0, __dsub_rn(2.0, norm_variance(var)));
+        const double two_minus_nv = __dsub_rn(2.0, norm_variance(var));
+        ws->s[lane] = two_minus_nv;
+        ws->inv_s[lane] = __ddiv_rn(1.0, two_minus_nv);
         s32 = adaptive_scale(var);
     }
     ws->blk[lane] = b;
 
     // ---- phase 1: K2's fp32 arithmetic for the whole block (inv_block of dequant_idct.cu, scalar), flagged pixels
     float v[64];
-    float bound = 0.f;
+    float bound = 0.f, bound_dc = 0.f;
     static_for<0, 8>([&](auto J) {
         constexpr int j = decltype(J)::value;
         const uint4 t = active ? reinterpret_cast<const uint4 *>(rec)[j] : make_uint4(0, 0, 0, 0);
@@ -284,26 +323,18 @@ __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScra
         static_for<0, 4>([&](auto Hh) {
             constexpr int h = decltype(Hh)::value;
             constexpr int k0 = storage_to_natural<LAYOUT>(8 * j + 2 * h), k1 = storage_to_natural<LAYOUT>(8 * j + 2 * h + 1);
-            float f0 = half_to_float<0>(w4[h]), f1 = half_to_float<1>(w4[h]);
-            if constexpr (ADAPTIVE) {
-                if (k0 != 0) f0 = __fmul_rn(f0, s32);
-                f1 = __fmul_rn(f1, s32);
-                v[k0] = __fmul_rn(f0, cx.rs32[k0]);
-                v[k1] = __fmul_rn(f1, cx.rs32[k1]);
-                bound = __fmaf_rn(fabsf(v[k0]), cx.gain32[k0], bound);
-                bound = __fmaf_rn(fabsf(v[k1]), cx.gain32[k1], bound);
-            } else {
-                v[k0] = f0, v[k1] = f1;
-                bound = __fmaf_rn(fabsf(f0), cx.rg32[k0], bound);
-                bound = __fmaf_rn(fabsf(f1), cx.rg32[k1], bound);
-            }
+            const float f0 = half_to_float<0>(w4[h]), f1 = half_to_float<1>(w4[h]);
+            v[k0] = f0, v[k1] = f1;
+            if (ADAPTIVE && k0 == 0) bound_dc = __fmul_rn(fabsf(f0), cx.rg32[0]);
+            else bound = __fmaf_rn(fabsf(f0), cx.rg32[k0], bound);
+            if (ADAPTIVE && k1 == 0) bound_dc = __fmul_rn(fabsf(f1), cx.rg32[0]);
+            else bound = __fmaf_rn(fabsf(f1), cx.rg32[k1], bound);
         });
     });
-    if constexpr (ADAPTIVE) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) idct8<float, 8>(&v[c]);
-    } else {
-        // K2's folded first stage (idct8_dequant), scalar: same operations on the same operands
+    if constexpr (ADAPTIVE) bound = adaptive_bound(bound, bound_dc, s32);
+    {
+        // K2's folded first stage (idct8_dequant), scalar: same operations on the same operands; adaptive plans scale
+        // the multipliers by the block's (2 - nv), the DC entry excepted
         constexpr int ra[4] = {0, 2, 5, 1}, rb[4] = {4, 6, 3, 7};
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -313,6 +344,10 @@ __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScra
             for (int j = 0; j < 4; ++j) {
                 ma[j] = cx.rs32[8 * ra[j] + c];
                 mb[j].pos = cx.rs32[8 * rb[j] + c];
+                if constexpr (ADAPTIVE) {
+                    if (!(c == 0 && j == 0)) ma[j] = __fmul_rn(ma[j], s32);
+                    mb[j].pos = __fmul_rn(mb[j].pos, s32);
+                }
                 mb[j].neg = -mb[j].pos;
             }
             idct8_dequant<float, 8>(&v[c], ma, mb);
@@ -321,6 +356,7 @@ __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScra
 #pragma unroll
     for (int i = 0; i < 8; ++i) idct8<float, 1>(&v[8 * i]);
     const float thr = pixel_threshold(bound, cx.band_floor);
+    if constexpr (ADAPTIVE) ws->bound[lane] = bound;
     unsigned need_lo = 0, need_hi = 0;
     if (!(bound < 1.4e5f)) {
         need_lo = need_hi = 0xffffffffu;               // outside the int16 trick's range: K2 wrote nothing reliable
@@ -364,13 +400,25 @@ __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScra
             const unsigned bb = ws->blk[sl];
             const uint4 *q4 = reinterpret_cast<const uint4 *>(cx.coef + (size_t)bb * 64);
             const double inv_two_minus_nv = ADAPTIVE ? ws->inv_s[sl] : 1.0;
+            const unsigned by = bb / cx.bw, bx = bb - by * cx.bw;
+            uint8_t *px = cx.px + ((long long)by * 8 + i) * cx.pitch + (long long)bx * 8 + j;
+            if constexpr (ADAPTIVE) {
+                // plain fp64 first: |fast - reference| <= 1e-14 * bound (64 products, each within 2^-52 of terms that
+                // sum gain_k |v_k| dominates); farther than that (+ the 1e-9 tie-accounting margin) from a boundary
+                // the pixel is settled.  Adaptive plans flag two or three pixels per block on busy content.
+                const double fast = fast_inverse_sample<LAYOUT>(q4, cx.D, cx.mult, ws->s[sl], i, j) + 128.0;
+                const double n = rint(fast);
+                if (fabs(fast - n) < 0.5 - (2e-9 + 1e-14 * (double)ws->bound[sl]) && fabs(fast) < 1e9) {
+                    *px = (uint8_t)(n < 0.0 ? 0.0 : (n > 255.0 ? 255.0 : n));
+                    continue;
+                }
+            }
             const double out = exact_inverse_sample<LAYOUT, ADAPTIVE>(q4, cx.D, cx.R, inv_two_minus_nv, i, j);
             const double val = __dadd_rn(out, 128.0);
             double rr = round_half_away(val);
             rr = rr < 0.0 ? 0.0 : (rr > 255.0 ? 255.0 : rr);
             ties += near_half(val);
-            const unsigned by = bb / cx.bw, bx = bb - by * cx.bw;
-            cx.px[((long long)by * 8 + i) * cx.pitch + (long long)bx * 8 + j] = (uint8_t)rr;
+            *px = (uint8_t)rr;
         }
         __syncwarp();
     }

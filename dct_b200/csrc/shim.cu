@@ -96,6 +96,7 @@ int read_tables(dct_cuda_plan *p)
         // bound on the raw quantised value: |q| * rg >= gain * |q * rs| with room for the fp32 product's rounding
         p->rg[k] = exotic ? 1e30f : std::nextafterf((float)((double)std::fabs(p->rs[k]) * (double)p->gain[k] * (1.0 + 1e-6)), INFINITY);
         p->h_tab.mp64[k] = mult * kInvPrescale[k];
+        p->h_tab.mult64[k] = mult;
     }
     p->band_floor = 1.0e-6f;
     // One band for all coefficients costs half the instructions of 64 separate compares but replays
@@ -382,8 +383,9 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
             CU_TRY(cudaEventCreate(&e1));
             CU_TRY(cudaEventRecord(e0, s));
         }
-        // adaptive plans decode full-scale values: the fp64 butterfly keeps the replay list short
-        if (p->adaptive && !p->force_fp32_inverse) {
+        // DCT_CUDA_INV_FP64=1: adaptive plans through the fp64 butterfly (content-independent 0.40 of peak; the fp32
+        // kernel with its replay is faster even on uniform noise since the bands were re-derived)
+        if (p->adaptive && p->fp64_inverse) {
             CU_TRY(launch_dequant_idct_u8_f64(ip, p->d_tab, layout, s));
         } else {
             CU_TRY(launch_dequant_idct_u8(ip, layout, p->adaptive, s, &rp.seg, &folded));
@@ -469,7 +471,7 @@ extern "C" dct_cuda_plan *dct_cuda_plan_create(const DCTContext *dct, const Quan
         return nullptr;
     }
     p->device = device;
-    p->force_fp32_inverse = getenv("DCT_CUDA_INV_FP32") != nullptr;
+    p->fp64_inverse = getenv("DCT_CUDA_INV_FP64") != nullptr;
     p->dct = dct;
     p->quant = quant;
     DeviceGuard g(device);
