@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     inc = os.path.join(ROOT, "include")
     pub_headers = [os.path.join(inc, h) for h in ("dct.h", "quantization.h", "utils.h", "dct_cuda.h")]
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + pub_headers
-    objs = []
+    objs, cmds = [], []
     for src in CU_SOURCES:
         s, o = os.path.join(CSRC, src), os.path.join(BUILD, src + ".o")
         if force or _newer(o, [s] + hdrs):
@@ -46,8 +46,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
                    "-I" + inc, "-I" + CSRC, "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
-            subprocess.check_call(cmd)
+            cmds.append(cmd)
         objs.append(o)
+    if verbose or len(cmds) < 2:          # -v: keep ptxas' output in source order
+        for cmd in cmds:
+            subprocess.check_call(cmd)
+    else:                                 # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 1)) as pool:
+            list(pool.map(subprocess.check_call, cmds))
     for src in C_SOURCES:
         s, o = os.path.join(CSRC, src), os.path.join(BUILD, src + ".o")
         if force or _newer(o, [s] + pub_headers):

@@ -147,6 +147,15 @@ def test_band_tables_are_current():
     m.emit(tmp)
     assert open(tmp).read() == open(os.path.join(ROOT, "dct_b200", "csrc", "band_tables.h")).read()
     m.check(nblocks=2000)
+    assert m.check_inverse_sparse(trials=300) <= 1.0
+    # the transfer-coefficient bound can only be tighter than the path-by-path one it replaces, and the inverse
+    # gains are symmetric under transposition to first order (the flowgraph treats rows and columns alike)
+    G, _ = m.inv_tables()
+    assert np.allclose(G.reshape(8, 8), G.reshape(8, 8).T, rtol=1e-5)
+    o = m.BoundOps(np.full(64, 128.0))
+    X = [[o.inp(np.eye(64)[8 * i + j], 0.0, True) for j in range(8)] for i in range(8)]
+    Y = m.two_d(o, m.fdct8, X, rows_first=True)
+    assert all(o.transfer_error(Y[u][v]) <= Y[u][v].E * (1 + 1e-12) for u in range(8) for v in range(8))
 
 
 def test_frame420_geometry_is_pure_host_arithmetic():

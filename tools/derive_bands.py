@@ -294,11 +294,44 @@ def check(nblocks=20000):
     assert np.all(err <= bound)
 
 
+def check_inverse_sparse(trials=2000, seed=5):
+    """The inverse gains one at a time: a single coefficient (then three) at random magnitudes.  Dense random inputs
+    average the gains out; these inputs stress each kInvGain[k] on its own.  Returns the worst err / bound."""
+    D = np.array([[(1 / math.sqrt(8) if i == 0 else 0.5) * math.cos(math.pi * (2 * j + 1) * i / 16)
+                   for j in range(8)] for i in range(8)])
+    G, P = inv_tables()
+    rng = np.random.default_rng(seed)
+    o32 = F32Ops()
+
+    def ratio(V):
+        Vl = [[V[:, 8 * i + j] for j in range(8)] for i in range(8)]
+        Xr = two_d(o32, idct8, Vl, rows_first=False)
+        Xr = np.stack([np.stack(r, -1) for r in Xr], -2).astype(np.float64)
+        exact = np.einsum("ui,nuv,vj->nij", D, (V.astype(np.float64) / P).reshape(-1, 8, 8), D)
+        bound = U * (np.abs(V.astype(np.float64)) @ G)
+        return float((np.abs(Xr - exact).reshape(-1, 64).max(1) / np.maximum(bound, 1e-300)).max())
+
+    worst = 0.0
+    for k in range(64):
+        V = np.zeros((trials, 64), np.float32)
+        V[:, k] = (rng.random(trials) * 2000 - 1000).astype(np.float32)
+        worst = max(worst, ratio(V))
+    V = np.zeros((20 * trials, 64), np.float32)
+    for _ in range(3):
+        idx = rng.integers(0, 64, V.shape[0])
+        V[np.arange(V.shape[0]), idx] = (rng.random(V.shape[0]) * 2000 - 1000).astype(np.float32)
+    worst = max(worst, ratio(V))
+    print("inv, single-coefficient and sparse inputs: worst ratio err/bound %.3f" % worst)
+    assert worst <= 1.0
+    return worst
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
     args = ap.parse_args()
     if args.check:
         check()
+        check_inverse_sparse()
     else:
         emit(os.path.join(ROOT, "dct_b200", "csrc", "band_tables.h"))
