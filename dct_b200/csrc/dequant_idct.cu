@@ -6,11 +6,18 @@
 //   adaptive q * (1.0 / ((1/Q) * (1/(2-nv)))), DC unscaled), dct_inverse (src/dct.c:80-105)
 // and the pixel rule p = clamp(round(x + 128.0), 0, 255) into one pass: 128 B in, 64 B out.
 //
-// Mapping mirrors K1: one thread per block, a warp owns 32 consecutive records (4 KB, read
-// with 512-byte contiguous LDG.128 through a padded shared-memory stage) and writes a
-// 256-pixel x 8-row tile with 8 STG.64 per lane (256 contiguous bytes per warp instruction).
-// Both butterfly passes and the pixel residuals run on packed fp32 instructions (FADD2 / FFMA2).
-// The fp32 error bound is dynamic here (inputs are arbitrary int16): 2^-24 * sum gain_k |v_k|.
+// Mapping mirrors K1: one thread per block, a warp owns a tile of 32 records (4 KB) and writes a 256-pixel x 8-row
+// tile with 8 STG.64 per lane (256 contiguous bytes per warp instruction).  Both butterfly passes and the pixel
+// residuals run on packed fp32 instructions (FADD2 / FFMA2); the table multiplication is folded into the first
+// butterfly stage (inv_block below, shared by the kernels).  The fp32 error bound is dynamic here (inputs are
+// arbitrary int16): 2^-24 * sum gain_k |v_k|.
+//
+//   k_dequant_idct_u8_tma (default)  persistent, ONE CTA of 16 warps per SM; per warp a two-stage bulk-tensor pipeline:
+//                         one cp.async.bulk.tensor.2d (UTMALDG) per tile into a 128B-swizzled stage, read back with
+//                         conflict-free LDS.128; per-warp worklist segments; small planes replay in the tail (FOLD).
+//   k_dequant_idct_u8     (fallback: unaligned records, planes under 256 pixels wide, peer memory)  one-shot grid,
+//                         LDG.128 through a padded stage, atomic worklist append.
+//   k_dequant_idct_u8_f64 the butterfly in fp64 (adaptive plans with DCT_CUDA_INV_FP64=1).
 #include <cstdio>
 #include <cstdlib>
 

@@ -7,18 +7,21 @@
 //   (src/entropy.c:158-178)
 // into one pass: each block is read once (64 B) and written once (128 B).
 //
-// Mapping: one thread owns one block; a warp owns a TILE of 32 consecutive records, i.e. a
-// 256-pixel wide, 8-row strip.  The kernel is persistent (one CTA per SM slot, grid-stride over
-// tiles) and every warp runs its own two-stage cp.async pipeline, with no CTA-wide barrier:
-// while a warp transforms tile t, the 2 KB of tile t+1 are already in flight into its second
-// shared-memory stage (a warp LDGSTS instruction covers 256 contiguous bytes).  A lane keeps its
-// block in 64 registers through both butterfly passes (no transpose, no shuffles), both passes and
-// the quantisation on sm_100's packed fp32 instructions (FADD2 / FFMA2: two IEEE lanes per
-// instruction, half the issue slots of scalar code, bit-identical results): one FFMA2 quantises two
-// coefficients (round-to-nearest via the 1.5*2^23 trick), the fp32 residual is checked against the
-// band, and the records leave through a padded per-warp stage so that every STG.128 of the warp
-// covers 512 contiguous bytes of the record array.
-// Blocks with a coefficient inside the band go to the worklist and are replayed in fp64 (K3).
+// Mapping: one thread owns one block; a warp owns a TILE of 32 blocks, i.e. a 256-pixel wide, 8-row strip.  A lane
+// keeps its block in 64 registers through both butterfly passes (no transpose, no shuffles); both passes and the
+// quantisation run on sm_100's packed fp32 instructions (FADD2 / FFMA2: two IEEE lanes per instruction, half the
+// issue slots of scalar code, bit-identical results): one FFMA2 quantises two coefficients (round-to-nearest via the
+// 1.5*2^23 trick) and the fp32 residual is checked against the band (fwd_block below, shared by both kernels).
+// Blocks with a coefficient inside the band go to the warp's worklist segment and are replayed in fp64 (K3).
+//
+// Two kernels move the tiles:
+//   k_fwd_quant_u8_tma  (default)  persistent, ONE CTA of 12 warps per SM; per warp a two-stage bulk-tensor pipeline:
+//                       cp.async.bulk.tensor.2d (UTMALDG) brings a 256 B x 8-row box of the plane per tile, the 32
+//                       records leave through a 128B-swizzled stage with one bulk-tensor store (UTMASTG).
+//                       Small planes replay their flagged blocks in the kernel's tail (FOLD, replay_lane.cuh).
+//   k_fwd_quant_u8      (fallback: pitch not a multiple of 16, unaligned base, planes under 256 pixels wide, peer
+//                       memory)  persistent, 3 CTAs of 8 warps per SM, per-warp two-stage cp.async pipeline, records
+//                       through a padded stage so that every STG.128 of the warp covers 512 contiguous bytes.
 #include <cstdio>
 #include <cstdlib>
 

@@ -11,6 +11,9 @@
 // and non-contracted __dmul_rn/__dadd_rn/__ddiv_rn, so the integers are bit-identical to
 // the reference's, exact ties included.  The same code, generalised to n x n, backs the
 // per-block drop-in entry points dct_forward/dct_inverse/quantize/dequantize.
+// The one-lane-per-block replay bodies live in replay_lane.cuh (they are also called from the tails of K1 / K2);
+// this file holds the stand-alone kernels around them, the 8-threads-per-block kernels for float tiles and for
+// tables outside the fast path's domain (everything replayed), and the per-block kernels.
 #include <cstring>
 
 #include "fast_core.cuh"
@@ -374,7 +377,6 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
         count = p.ctr->wl_count;
         if (count > p.wl_cap) count = p.wl_cap;
     }
-    const bool replay_all = p.worklist == nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 3, r = lane & 7, gbase = lane & 24;
     float(*T)[9] = reinterpret_cast<float(*)[9]>(&sh.tile[warp][g][0][0]);
     double(*Td)[9] = sh.tile[warp][g];
@@ -389,12 +391,10 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
         uint8_t *dst = p.px_out + (long long)by * 8 * p.pitch + (long long)bx * 8;
 
         double inv_two_minus_nv = 1.0, two_minus_nv = 1.0;
-        float s32 = 1.0f;
         if (p.adaptive) {
             const double var = p.var_in ? p.var_in[b] : 0.0;
             two_minus_nv = __dsub_rn(2.0, norm_variance(var));
             inv_two_minus_nv = __ddiv_rn(1.0, two_minus_nv);   // src/quantization.c:193
-            s32 = adaptive_scale(var);
         }
 
         // the record goes through the tile so that thread r can pick column r in any layout
@@ -410,66 +410,10 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_inv(const ReplayPa
         }
         __syncwarp();
 
-        // ---- phase 1: K2's fp32 arithmetic again (columns, then rows), to find the flagged pixels ----
+        // This kernel now serves only plans whose tables are outside the fast path's domain (K2 skipped, every pixel
+        // of every block replayed); blocks flagged by K2 go through the one-lane-per-block kernel (replay_lane.cuh),
+        // which is where K2's fp32 arithmetic is repeated to find the flagged pixels.
         unsigned long long need = ~0ull;
-        if (!replay_all) {
-            float x[8];
-            float bound = 0.0f;
-            if (p.adaptive) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int k = 8 * i + r;
-                    float f;
-                    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(q[i]));
-                    if (k != 0) f = __fmul_rn(f, s32);
-                    x[i] = __fmul_rn(f, tab.rs32[k]);
-                    bound = __fmaf_rn(fabsf(x[i]), tab.gain32[k], bound);
-                }
-                idct8<float, 1>(x);                       // column r
-            } else {
-                // K2's folded first stage (idct8_dequant), scalar: same operations on the same operands
-                constexpr int ra[4] = {0, 2, 5, 1}, rb[4] = {4, 6, 3, 7};
-                float ma[4];
-                PosNeg1 mb[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ma[j] = tab.rs32[8 * ra[j] + r];
-                    mb[j].pos = tab.rs32[8 * rb[j] + r];
-                    mb[j].neg = -mb[j].pos;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(x[i]) : "r"(q[i]));
-                    bound = __fmaf_rn(fabsf(x[i]), tab.rg32[8 * i + r], bound);
-                }
-                idct8_dequant<float, 1>(x, ma, mb);       // column r
-            }
-#pragma unroll
-            for (int d = 1; d < 8; d <<= 1) bound += __shfl_xor_sync(0xffffffffu, bound, d);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) T[i][r] = x[i];
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = T[r][j];
-            __syncwarp();
-            idct8<float, 1>(x);                           // row r: x[j] = sample (r, j)
-            // K2 and this sum the bound in different orders; both are valid bounds (the 1.0625 in
-            // pixel_threshold covers the accumulation's own rounding), so a pixel unflagged here is
-            // provably right even if K2 flagged it.
-            const float thr = pixel_threshold(bound, tab.band_floor);
-            need = 0;
-            if (!(bound < 1.4e5f)) {
-                need = 0xFFull << (8 * r);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float t, e;
-                    pixel_residual(x[j], t, e);
-                    if (fabsf(e) >= thr) need |= 1ull << (8 * r + j);
-                }
-            }
-            need = group_or(need);
-        }
 
         // ---- phase 2 and 3 -------------------------------------------------------------------
         if (__any_sync(0xffffffffu, need != 0)) {
