@@ -232,11 +232,12 @@ struct alignas(64) InvTmaParams {
 
 constexpr int kTmaInBytes = 4096;                                   // per warp and stage: 32 records
 constexpr int kTmaCtlBytes = 64;                                    // per warp: up to 8 mbarriers
+constexpr int kTmaVarBytes = 256;                                   // per warp and stage: 32 variances (adaptive plans)
 
 // geometry of one kernel variant: warps per CTA, CTAs per SM the register budget is cut for, record stages per warp
 template <int WARPS, int MIN_CTAS, int STAGES> struct TmaCfg {
     static constexpr int kWarpsT = WARPS, kMinCtas = MIN_CTAS, kStages = STAGES, kThreadsT = 32 * WARPS;
-    static constexpr int kSmem = 1024 /* alignment slack */ + WARPS * (STAGES * kTmaInBytes + kTmaCtlBytes + (int)sizeof(InvLaneScratch));
+    static constexpr int kSmem = 1024 /* alignment slack */ + WARPS * (STAGES * (kTmaInBytes + kTmaVarBytes) + kTmaCtlBytes + (int)sizeof(InvLaneScratch));
     static_assert(STAGES >= 2 && STAGES <= 8, "stages");
 };
 
@@ -252,6 +253,11 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
     uint8_t *in_p = sm + warp * (kS * kTmaInBytes);
     uint32_t *ctl_p = reinterpret_cast<uint32_t *>(sm + kW * kS * kTmaInBytes + warp * kTmaCtlBytes);
     InvLaneScratch *ws = reinterpret_cast<InvLaneScratch *>(sm + kW * (kS * kTmaInBytes + kTmaCtlBytes)) + warp;
+    double *var_p = reinterpret_cast<double *>(sm + kW * (kS * kTmaInBytes + kTmaCtlBytes + (int)sizeof(InvLaneScratch)) + warp * (kS * kTmaVarBytes));
+    const uint32_t var_s = (uint32_t)__cvta_generic_to_shared(var_p);
+    // adaptive plans: the tile's 32 variances (side information) ride the same mbarrier as its records when the
+    // array allows a bulk copy (16-byte aligned, an even number of blocks per row); a plain load otherwise
+    const bool var_bulk = ADAPTIVE && p.var_in != nullptr && (p.bw % 2 == 0) && ((uintptr_t)p.var_in % 16 == 0);
     const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in_p);
     const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(ctl_p);           // kS 8-byte mbarriers
 
@@ -274,8 +280,10 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
     uint32_t fy = ty, fx = tx, fstage = 0;
     auto fetch = [&]() {        // fetch tile (fy, fx) into stage fstage, then advance both
         if (fy < P.nby && lane == 0) {
-            tma::mbar_expect_tx(bar_s + fstage * 8, kTmaInBytes);
+            const uint32_t vbytes = var_bulk ? min(32u, p.bw - fx * 32) * 8u : 0u;
+            tma::mbar_expect_tx(bar_s + fstage * 8, kTmaInBytes + vbytes);
             tma::load_2d(in_s + fstage * kTmaInBytes, &P.map_rec, 0, (int)(fy * p.bw + fx * 32), bar_s + fstage * 8);
+            if (var_bulk) tma::load_1d(var_s + fstage * kTmaVarBytes, p.var_in + (size_t)fy * p.bw + fx * 32, vbytes, bar_s + fstage * 8);
         }
         fx += P.step_tx;
         fy += P.step_ty;
@@ -307,10 +315,11 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
         const uint32_t nvalid = min(32u, p.bw - bx0);
         uint8_t *dst = p.px + (long long)ty * 8 * p.pitch + (long long)(bx0 + lane) * 8;
         fetch();                                                  // into the stage the previous iteration consumed
-        // adaptive plans: the lane's variance (8 bytes of side information per block).  Loading it one tile ahead was
-        // measured slower (353 against 334 us per 64 4K frames: the kernel sits on its 128 registers)
-        const double var = (ADAPTIVE && p.var_in != nullptr && lane < nvalid) ? p.var_in[warp_base + lane] : 0.0;
         tma::mbar_wait(bar_s + stage * 8, phase);
+        // adaptive plans: the lane's variance (8 bytes of side information per block), from the stage or from memory
+        double var = 0.0;
+        if (ADAPTIVE && p.var_in != nullptr && lane < nvalid)
+            var = var_bulk ? var_p[stage * (kTmaVarBytes / 8) + lane] : p.var_in[warp_base + lane];
 
         const uint32_t b = warp_base + lane;
         const bool valid = lane < nvalid;

@@ -62,6 +62,13 @@ __device__ __forceinline__ void store_2d(const CUtensorMap *map, int c0, int c1,
                  "r"(c0), "r"(c1), "r"(src)
                  : "memory");
 }
+// global -> shared, `bytes` contiguous bytes (a multiple of 16, both addresses 16-byte aligned); counted on `bar`
+__device__ __forceinline__ void load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the issuing thread's bulk stores have finished READING shared memory (the stage may be rewritten)
 __device__ __forceinline__ void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
