@@ -23,7 +23,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CU_SOURCES = ["fwd_quant.cu", "dequant_idct.cu", "replay_f64.cu", "rle.cu", "generic_n.cu", "planar.cu", "narrow.cu", "tma_host.cu", "shim.cu", "shim_frames.cu", "shim_peer.cu", "shim_blocks.cu"]
 C_SOURCES = ["host_context.c"]
-HEADERS = ["butterfly.cuh", "fast_core.cuh", "kernels.cuh", "plan.cuh", "band_tables.h", "tma.cuh"]
+HEADERS = ["butterfly.cuh", "fast_core.cuh", "kernels.cuh", "plan.cuh", "band_tables.h", "tma.cuh", "replay_lane.cuh"]
 
 
 def _newer(target: str, deps: list[str]) -> bool:

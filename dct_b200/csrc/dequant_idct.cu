@@ -61,9 +61,9 @@ __device__ __forceinline__ bool inv_block(const InvParams &p, const uint32_t (&w
     if constexpr (ADAPTIVE) s = adaptive_scale(var);
 
     // v holds the converted q themselves: the multiplication by the table happens inside the first butterfly stage
-    // (idct8_dequant: one FMA gives v_a +- q_b * rs_b).  ADAPTIVE: the block's factor (2 - nv) goes into the 32
-    // multiplier pairs (48 packed multiplications per block; the DC entry keeps the unscaled table,
-    // src/quantization.c:199-201) -- the product rs_k * s is one more rounding inside the 8u the inputs are allowed.
+    // (idct8_dequant: one FMA gives v_a +- q_b * rs_b).  ADAPTIVE: the block's factor (2 - nv) goes onto the 63 AC
+    // values first (32 packed multiplications per block; the DC entry is not scaled, src/quantization.c:199-201) --
+    // the product q_k * s is one more rounding inside the 8u the inputs are allowed.
     float v[64];
     float bound = 0.f, bound_dc = 0.f;   // bound >= sum gain_k * |v_k|
     static_for<0, 32>([&](auto M) {
@@ -91,21 +91,15 @@ __device__ __forceinline__ bool inv_block(const InvParams &p, const uint32_t (&w
     for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) cpv[c][i] = make_float2(v[8 * i + kPairA[c]], v[8 * i + kPairB[c]]);
-        if constexpr (ADAPTIVE) {
+        if constexpr (ADAPTIVE) {          // the block's (2 - nv) goes onto the 63 AC values; the tables stay constant operands
             const float2 s2 = make_float2(s, s);
-            float2 mas[4];
-            PosNeg2 mbs[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                mas[j] = Ops<float2>::mul(p.ma[c][j], s2);
-                mbs[j].pos = Ops<float2>::mul(p.mb[c][j].pos, s2);
-                mbs[j].neg = Ops<float2>::mul(p.mb[c][j].neg, s2);
+            for (int i = 0; i < 8; ++i) {
+                if (c == 0 && i == 0) cpv[0][0].y = __fmul_rn(cpv[0][0].y, s);      // natural index 0: the DC entry is not scaled
+                else cpv[c][i] = Ops<float2>::mul(cpv[c][i], s2);
             }
-            if (c == 0) mas[0].x = p.ma[0][0].x;          // natural index 0: the DC entry is not scaled
-            idct8_dequant<float2, 1>(cpv[c], mas, mbs);
-        } else {
-            idct8_dequant<float2, 1>(cpv[c], p.ma[c], p.mb[c]);
         }
+        idct8_dequant<float2, 1>(cpv[c], p.ma[c], p.mb[c]);
     }
 
     // Row pass on row pairs (2a, 2a+1), then per pixel: t = x + (1.5*2^23 + 128): the low 16 mantissa bits
@@ -226,6 +220,7 @@ struct alignas(64) InvTmaParams {
     uint32_t tpr;              // tiles per block row = ceil(bw / 32)
     uint32_t nby;              // block rows
     uint32_t step_ty, step_tx; // divmod(warps in the grid, tpr)
+    uint32_t n_segs, rot;      // warps in the grid; the warp that takes the plane's tile 0
     uint32_t *seg_count;       // one entry per warp of the grid
     uint32_t seg_cap;          // worklist entries per segment
 };
@@ -233,15 +228,178 @@ struct alignas(64) InvTmaParams {
 constexpr int kTmaInBytes = 4096;                                   // per warp and stage: 32 records
 constexpr int kTmaCtlBytes = 64;                                    // per warp: up to 8 mbarriers
 constexpr int kTmaVarBytes = 256;                                   // per warp and stage: 32 variances (adaptive plans)
+constexpr int kTmaMaxPlanes = 3;                                    // planes one launch may cover
+constexpr int kTmaCntBytes = 256;                                   // per CTA: flagged blocks per (plane, warp), up to 3 x 16
 
 // geometry of one kernel variant: warps per CTA, CTAs per SM the register budget is cut for, record stages per warp
 template <int WARPS, int MIN_CTAS, int STAGES> struct TmaCfg {
     static constexpr int kWarpsT = WARPS, kMinCtas = MIN_CTAS, kStages = STAGES, kThreadsT = 32 * WARPS;
-    static constexpr int kSmem = 1024 /* alignment slack */ + WARPS * (STAGES * (kTmaInBytes + kTmaVarBytes) + kTmaCtlBytes + (int)sizeof(InvLaneScratch));
+    static constexpr int kSmem = 1024 /* alignment slack */ + WARPS * (STAGES * (kTmaInBytes + kTmaVarBytes) + kTmaCtlBytes) + kTmaCntBytes;
     static_assert(STAGES >= 2 && STAGES <= 8, "stages");
+    static_assert(sizeof(InvLaneScratch) <= STAGES * kTmaInBytes, "the replay's scratch is the warp's record stages");
+    static_assert(kTmaMaxPlanes * WARPS * 4 <= kTmaCntBytes, "per-CTA counts");
 };
 
-template <int LAYOUT, bool ADAPTIVE, typename CFG, bool FOLD>
+// the warp's shared memory: [record stages, 1024-aligned for the swizzle][mbarriers][variance stages], then the CTA's
+// counts of flagged blocks; the replay's scratch is the warp's (by then idle) record stages
+template <typename CFG> struct InvWarpSmem {
+    uint8_t *in_p;
+    InvLaneScratch *ws;
+    double *var_p;
+    uint32_t *cnt_all;     // CTA-wide: blocks flagged per (plane, warp), for the pooled replay
+    uint32_t bar_s;
+    __device__ __forceinline__ InvWarpSmem(uint8_t *smem_raw, uint32_t warp, uint32_t lane)
+    {
+        constexpr int kW = CFG::kWarpsT, kS = CFG::kStages;
+        uint8_t *sm = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+        in_p = sm + warp * (kS * kTmaInBytes);
+        uint32_t *ctl_p = reinterpret_cast<uint32_t *>(sm + kW * kS * kTmaInBytes + warp * kTmaCtlBytes);
+        ws = reinterpret_cast<InvLaneScratch *>(in_p);
+        var_p = reinterpret_cast<double *>(sm + kW * (kS * kTmaInBytes + kTmaCtlBytes) + warp * (kS * kTmaVarBytes));
+        cnt_all = reinterpret_cast<uint32_t *>(sm + kW * (kS * (kTmaInBytes + kTmaVarBytes) + kTmaCtlBytes));
+        bar_s = (uint32_t)__cvta_generic_to_shared(ctl_p);           // kS 8-byte mbarriers
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < kS; ++i) tma::mbar_init(bar_s + 8 * i, 1);
+            tma::fence_barrier_init();
+        }
+        __syncwarp();
+    }
+};
+
+// All the tiles of ONE plane that fall to this warp; returns how many blocks it flagged.  `phases` holds the parity bit
+// of each stage's mbarrier and is carried from plane to plane by the multi-plane kernel (as in K1).
+template <int LAYOUT, bool ADAPTIVE, typename CFG, bool MULTI>
+__device__ __forceinline__ uint32_t inv_plane_tiles(const InvTmaParams &P, const uint32_t lane, const uint32_t gwarp, uint8_t *in_p,
+                                                    double *var_p, const uint32_t bar_s, uint32_t &phases)
+{
+    constexpr int kS = CFG::kStages;
+    const InvParams &p = P.f;
+    const uint32_t var_s = (uint32_t)__cvta_generic_to_shared(var_p);
+    // adaptive plans: the tile's 32 variances (side information) ride the same mbarrier as its records when the
+    // array allows a bulk copy (16-byte aligned, an even number of blocks per row); a plain load otherwise
+    const bool var_bulk = ADAPTIVE && p.var_in != nullptr && (p.bw % 2 == 0) && ((uintptr_t)p.var_in % 16 == 0);
+    const uint32_t in_s = (uint32_t)__cvta_generic_to_shared(in_p);
+
+    // (ty, tx): block row and tile-in-row of the tile being transformed; (fy, fx): of the next tile to fetch, kS - 1 ahead;
+    // the plane's tile 0 belongs to warp `rot` of the grid (see K1)
+    uint32_t ty, tx;
+    {
+        const uint32_t t = !MULTI ? gwarp : (gwarp >= P.rot ? gwarp - P.rot : gwarp + P.n_segs - P.rot);
+        ty = t / P.tpr;
+        tx = t - ty * P.tpr;
+    }
+    uint32_t fy = ty, fx = tx, fstage = 0;
+    auto fetch = [&]() {        // fetch tile (fy, fx) into stage fstage, then advance both
+        if (fy < P.nby && lane == 0) {
+            const uint32_t vbytes = var_bulk ? min(32u, p.bw - fx * 32) * 8u : 0u;
+            tma::mbar_expect_tx(bar_s + fstage * 8, kTmaInBytes + vbytes);
+            tma::load_2d(in_s + fstage * kTmaInBytes, &P.map_rec, 0, (int)(fy * p.bw + fx * 32), bar_s + fstage * 8);
+            if (var_bulk) tma::load_1d(var_s + fstage * kTmaVarBytes, p.var_in + (size_t)fy * p.bw + fx * 32, vbytes, bar_s + fstage * 8);
+        }
+        fx += P.step_tx;
+        fy += P.step_ty;
+        if (fx >= P.tpr) fx -= P.tpr, ++fy;
+        fstage = fstage + 1 == kS ? 0 : fstage + 1;
+    };
+#pragma unroll
+    for (int i = 0; i < kS - 1; ++i) fetch();
+    const uint32_t swz = (lane & 7) << 4;
+    uint32_t wl_n = 0;          // entries this warp has appended to its worklist segment
+
+    uint32_t stage = 0;
+    while (ty < P.nby) {
+        const uint32_t bx0 = tx * 32;
+        const uint32_t warp_base = ty * p.bw + bx0;
+        const uint32_t nvalid = min(32u, p.bw - bx0);
+        uint8_t *dst = p.px + (long long)ty * 8 * p.pitch + (long long)(bx0 + lane) * 8;
+        fetch();                                                  // into the stage the previous iteration consumed
+        // one plane per launch: the stages' parities move in step (one bit); planes sharing a launch leave the stages
+        // with different parities (a warp may get an odd number of tiles of a plane): one bit per stage
+        if constexpr (MULTI) {
+            tma::mbar_wait(bar_s + stage * 8, (phases >> stage) & 1u);
+            phases ^= 1u << stage;
+        } else {
+            tma::mbar_wait(bar_s + stage * 8, phases);
+        }
+        // adaptive plans: the lane's variance (8 bytes of side information per block), from the stage or from memory
+        double var = 0.0;
+        if (ADAPTIVE && p.var_in != nullptr && lane < nvalid)
+            var = var_bulk ? var_p[stage * (kTmaVarBytes / 8) + lane] : p.var_in[warp_base + lane];
+
+        const uint32_t b = warp_base + lane;
+        const bool valid = lane < nvalid;
+        const uint8_t *rec = in_p + stage * kTmaInBytes + lane * 128;
+        uint32_t w[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 t = *reinterpret_cast<const uint4 *>(rec + ((j << 4) ^ swz));
+            w[4 * j] = t.x, w[4 * j + 1] = t.y, w[4 * j + 2] = t.z, w[4 * j + 3] = t.w;
+        }
+        __syncwarp();           // every lane has its record: the next fetch overwrites this stage
+
+        const bool flag = inv_block<LAYOUT, ADAPTIVE>(p, w, valid, dst, var);
+        const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
+        if (ballot != 0) {
+            if (flag && valid) p.worklist[(size_t)gwarp * P.seg_cap + wl_n + __popc(ballot & ((1u << lane) - 1u))] = b;
+            wl_n += __popc(ballot);
+        }
+        tx += P.step_tx;
+        ty += P.step_ty;
+        if (tx >= P.tpr) tx -= P.tpr, ++ty;
+        if (++stage == kS) {
+            stage = 0;
+            if constexpr (!MULTI) phases ^= 1u;
+        }
+    }
+    if (lane == 0) P.seg_count[gwarp] = 0;                    // nothing for K3: replayed below (inv_replay_pooled)
+    __syncwarp();
+    return wl_n;
+}
+
+// Small planes: the flagged blocks are replayed in the kernel's tail and no K3 is launched.  As in K1
+// (fwd_replay_pooled, fwd_quant.cu) the CTA pools the entries of all its warps and of all the planes of the launch and
+// deals them out in batches of 32, one block per lane.  The barrier also orders the pixels K2 stored before the bytes the
+// replay patches into them.  Large planes leave the segments to K3's grid of replay-only warps.
+template <int LAYOUT, bool ADAPTIVE, typename CFG, int NPL>
+__device__ __forceinline__ void inv_replay_pooled(const InvTmaParams *pl, const uint32_t (&n_mine)[NPL], uint32_t *cnt_all, const uint32_t lane,
+                                                  const uint32_t warp, InvLaneScratch *ws)
+{
+    constexpr int kW = CFG::kWarpsT;
+    if (lane == 0) {
+        static_for<0, NPL>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            cnt_all[i * kW + warp] = n_mine[i];
+            if (n_mine[i] != 0) atomicAdd(&pl[i].f.ctr->replayed, (unsigned long long)n_mine[i]);
+        });
+    }
+    __syncthreads();
+    uint32_t total = 0;
+    for (int it = 0; it < NPL * kW; ++it) total += cnt_all[it];
+    for (uint32_t first = warp * 32; first < total; first += kW * 32) {
+        int item = 0;
+        uint32_t e = 0;
+        const bool active = locate_entry(cnt_all, NPL * kW, first + lane, item, e);
+        const int plane = item / kW;
+        const uint32_t gw = blockIdx.x * kW + (uint32_t)(item - plane * kW);     // the warp that flagged the block
+        InvReplayCtx cx{};
+        uint32_t b = 0;
+        static_for<0, NPL>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            if (i == 0 || plane == i) {       // idle lanes run the arithmetic on plane 0's tables
+                const InvParams &p = pl[i].f;
+                cx = InvReplayCtx{p.rs, p.rg, p.band_floor, p.tab->D, p.tab->R, p.tab->mult64, p.coef, p.var_in, p.px, p.pitch, p.bw, p.ctr};
+                if (active && plane == i) b = p.worklist[(size_t)gw * pl[i].seg_cap + e];
+            }
+        });
+        replay_inv_lanes<LAYOUT, ADAPTIVE>(cx, ws, active, b);
+    }
+}
+
+// The streaming kernel: one large plane, flagged blocks left to K3.  (Kept apart from the frame kernel below, which shares
+// its tile loop in spirit but not in text: at 128 registers per thread the schedule of this loop is worth 6 % of the
+// kernel, and any code around it moves it.)
+template <int LAYOUT, bool ADAPTIVE, typename CFG>
 __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_u8_tma(const __grid_constant__ InvTmaParams P)
 {
     constexpr int kW = CFG::kWarpsT, kS = CFG::kStages;
@@ -252,8 +410,7 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
     uint8_t *sm = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     uint8_t *in_p = sm + warp * (kS * kTmaInBytes);
     uint32_t *ctl_p = reinterpret_cast<uint32_t *>(sm + kW * kS * kTmaInBytes + warp * kTmaCtlBytes);
-    InvLaneScratch *ws = reinterpret_cast<InvLaneScratch *>(sm + kW * (kS * kTmaInBytes + kTmaCtlBytes)) + warp;
-    double *var_p = reinterpret_cast<double *>(sm + kW * (kS * kTmaInBytes + kTmaCtlBytes + (int)sizeof(InvLaneScratch)) + warp * (kS * kTmaVarBytes));
+    double *var_p = reinterpret_cast<double *>(sm + kW * (kS * kTmaInBytes + kTmaCtlBytes) + warp * (kS * kTmaVarBytes));
     const uint32_t var_s = (uint32_t)__cvta_generic_to_shared(var_p);
     // adaptive plans: the tile's 32 variances (side information) ride the same mbarrier as its records when the
     // array allows a bulk copy (16-byte aligned, an even number of blocks per row); a plain load otherwise
@@ -296,18 +453,6 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
     uint32_t wl_n = 0;          // entries this warp has appended to its worklist segment
     const uint32_t gwarp = blockIdx.x * kW + warp;
 
-    // Entries [replayed_n, replayed_n + n) of this warp's worklist segment, one per lane, through replay_lane.cuh
-    uint32_t replayed_n = 0;
-    auto replay_batch = [&](uint32_t n) {
-        if constexpr (!FOLD) return;
-        __syncwarp();                                     // the pixels K2 stored above are patched by other lanes below
-        const InvReplayCtx cx{p.rs, p.rg, p.band_floor, p.tab->D, p.tab->R, p.tab->mult64, p.coef, p.var_in, p.px, p.pitch, p.bw, p.ctr};
-        const bool active = lane < n;
-        const uint32_t b = active ? p.worklist[(size_t)gwarp * P.seg_cap + replayed_n + lane] : 0u;
-        replay_inv_lanes<LAYOUT, ADAPTIVE>(cx, ws, active, b);
-        replayed_n += n;
-    };
-
     uint32_t stage = 0, phase = 0;
     while (ty < P.nby) {
         const uint32_t bx0 = tx * 32;
@@ -343,13 +488,32 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_
         if (tx >= P.tpr) tx -= P.tpr, ++ty;
         if (++stage == kS) stage = 0, phase ^= 1;
     }
-    // ---- tail.  FOLD (small planes): the warp replays the blocks of its own segment right here (replay_lane.cuh) and no
-    // K3 is launched; large planes leave them to K3's grid of replay-only warps (see K1's tail, fwd_quant.cu).
-    if constexpr (FOLD) {
-        while (replayed_n < wl_n) replay_batch(min(32u, wl_n - replayed_n));
-        if (lane == 0 && wl_n != 0) atomicAdd(&p.ctr->replayed, (unsigned long long)wl_n);
-    }
-    if (lane == 0) P.seg_count[gwarp] = FOLD ? 0u : wl_n;     // <= 32 per tile visited, < seg_cap by construction
+    // the flagged blocks are left to K3's grid of replay-only warps (small planes: k_dequant_idct_u8_tma_frame below)
+    if (lane == 0) P.seg_count[gwarp] = wl_n;                 // <= 32 per tile visited, < seg_cap by construction
+}
+
+// The frame kernel: one small plane, or the 2 or 3 planes of one frame (Y, Cb, Cr) in ONE launch as in K1 (fwd_quant.cu);
+// the flagged blocks of all the planes are replayed in one pooled tail and no K3 is launched.
+template <int NPL> struct alignas(64) InvTmaMulti {
+    InvTmaParams pl[NPL];
+};
+
+template <int LAYOUT, bool ADAPTIVE, typename CFG, int NPL>
+__global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_dequant_idct_u8_tma_frame(const __grid_constant__ InvTmaMulti<NPL> M)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const InvWarpSmem<CFG> sm(smem_raw, warp, lane);
+    pdl_launch_dependents();
+    pdl_wait();
+    uint32_t phases = 0;
+    uint32_t n_mine[NPL];
+    static_for<0, NPL>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        n_mine[i] = inv_plane_tiles<LAYOUT, ADAPTIVE, CFG, (NPL > 1)>(M.pl[i], lane, blockIdx.x * CFG::kWarpsT + warp, sm.in_p, sm.var_p, sm.bar_s, phases);
+    });
+    inv_replay_pooled<LAYOUT, ADAPTIVE, CFG, NPL>(M.pl, n_mine, sm.cnt_all, lane, warp, sm.ws);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -473,61 +637,99 @@ static int sm_count_k2()
     return n;
 }
 
-template <typename CFG, typename K>
-static cudaError_t launch_persistent_tma(K kernel, const InvParams &p, cudaStream_t s, WorklistSegments *segments)
+template <typename CFG, typename K> static unsigned tma_ctas_per_sm(K kernel)
 {
-    constexpr int kW = CFG::kWarpsT;
-    cudaError_t e = ensure_smem_attributes(reinterpret_cast<const void *>(kernel), CFG::kSmem);
-    if (e != cudaSuccess) return e;
     static int per_sm = 0;   // one instance per CFG; the same for every variant of it: identical launch bounds and shared memory
     if (per_sm == 0) {
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, CFG::kThreadsT, CFG::kSmem) != cudaSuccess || n < 1) n = 1;
         per_sm = n < CFG::kMinCtas ? n : CFG::kMinCtas;
         if (getenv("DCT_CUDA_DEBUG"))
-            fprintf(stderr, "libdct_cuda: K2 (bulk tensor, %d warps, %d stages): %d CTAs/SM (occupancy %d), %d B smem\n", kW, CFG::kStages,
-                    per_sm, n, CFG::kSmem);
+            fprintf(stderr, "libdct_cuda: K2 (bulk tensor, %d warps, %d stages): %d CTAs/SM (occupancy %d), %d B smem\n", CFG::kWarpsT,
+                    CFG::kStages, per_sm, n, CFG::kSmem);
     }
-    InvTmaParams q;
+    return (unsigned)per_sm;
+}
+
+static unsigned tma_tiles(const InvParams &p) { return (p.nblocks / p.bw) * ((p.bw + 31) / 32); }
+
+// one plane's share of a launch of `n_segs` warps whose warp `rot` takes the plane's first tile
+static cudaError_t fill_tma_plane(InvTmaParams &q, const InvParams &p, unsigned n_segs, unsigned rot, unsigned seg_off = 0)
+{
     q.f = p;
     q.nby = p.nblocks / p.bw;
     q.tpr = (p.bw + 31) / 32;
-    const unsigned ntiles = q.nby * q.tpr;
-    const unsigned resident = (unsigned)sm_count_k2() * (unsigned)per_sm;
-    const unsigned want = (ntiles + kW - 1) / kW;
-    const unsigned grid = want < resident ? want : resident;
-    const unsigned n_segs = grid * kW;
+    q.n_segs = n_segs;
+    q.rot = rot;
     q.step_ty = n_segs / q.tpr;
     q.step_tx = n_segs - q.step_ty * q.tpr;
-    const unsigned tiles_per_warp = (ntiles + n_segs - 1) / n_segs;
+    const unsigned tiles_per_warp = (q.nby * q.tpr + n_segs - 1) / n_segs;
     q.seg_cap = p.wl_cap / n_segs;
     q.seg_count = p.seg_count;
-    if (n_segs > kMaxWorklistSegments - 128 || q.seg_cap < tiles_per_warp * 32 || p.seg_count == nullptr) return cudaErrorInvalidValue;
-    if ((e = make_record_map(&q.map_rec, p.coef, p.nblocks, 32)) != cudaSuccess) return e;
-    if (segments) *segments = WorklistSegments{n_segs, q.seg_cap, 0};
+    q.f.worklist = p.worklist + seg_off;       // planes of one plan share its worklist: each has its own range of every segment
+    if (n_segs > kMaxWorklistSegments - 128 || q.seg_cap < seg_off + tiles_per_warp * 32 || p.seg_count == nullptr) return cudaErrorInvalidValue;
+    return make_record_map(&q.map_rec, p.coef, p.nblocks, 32);
+}
+
+template <typename CFG, typename K>
+static cudaError_t launch_persistent_tma(K kernel, const InvParams &p, cudaStream_t s, WorklistSegments *segments)
+{
+    constexpr int kW = CFG::kWarpsT;
+    cudaError_t e = ensure_smem_attributes(reinterpret_cast<const void *>(kernel), CFG::kSmem);
+    if (e != cudaSuccess) return e;
+    const unsigned resident = (unsigned)sm_count_k2() * tma_ctas_per_sm<CFG>(kernel);
+    const unsigned want = (tma_tiles(p) + kW - 1) / kW;
+    const unsigned grid = want < resident ? want : resident;
+    InvTmaParams q;
+    if ((e = fill_tma_plane(q, p, grid * kW, 0)) != cudaSuccess) return e;
+    if (segments) *segments = WorklistSegments{q.n_segs, q.seg_cap, 0};
     return launch_pdl(kernel, grid, CFG::kThreadsT, CFG::kSmem, s, q);
 }
 
-template <typename CFG, bool FOLD>
-static cudaError_t launch_k2_tma_fold(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments)
+// several planes, one launch (k_dequant_idct_u8_tma_multi): each plane starts at the warp where the previous one ended
+template <typename CFG, int NPL, typename K>
+static cudaError_t launch_multi_tma(K kernel, const InvParams *pl, cudaStream_t s)
 {
-    if (layout == LAYOUT_ZIGZAG)
-        return adaptive ? launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, true, CFG, FOLD>, p, s, segments)
-                        : launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, false, CFG, FOLD>, p, s, segments);
-    return adaptive ? launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_NATURAL, true, CFG, FOLD>, p, s, segments)
-                    : launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_NATURAL, false, CFG, FOLD>, p, s, segments);
+    constexpr int kW = CFG::kWarpsT;
+    cudaError_t e = ensure_smem_attributes(reinterpret_cast<const void *>(kernel), CFG::kSmem);
+    if (e != cudaSuccess) return e;
+    const unsigned resident = (unsigned)sm_count_k2() * tma_ctas_per_sm<CFG>(kernel);
+    unsigned total = 0;
+    for (int i = 0; i < NPL; ++i) total += tma_tiles(pl[i]);
+    const unsigned want = (total + kW - 1) / kW;
+    const unsigned grid = want < resident ? want : resident;
+    const unsigned n_segs = grid * kW;
+    InvTmaMulti<NPL> m;
+    unsigned rot = 0;
+    for (int i = 0; i < NPL; ++i) {
+        unsigned seg_off = 0;
+        for (int j = 0; j < i; ++j)
+            if (pl[j].worklist == pl[i].worklist) seg_off += (tma_tiles(pl[j]) + n_segs - 1) / n_segs * 32;
+        if ((e = fill_tma_plane(m.pl[i], pl[i], n_segs, rot, seg_off)) != cudaSuccess)
+            return NPL == 1 ? e : cudaErrorNotSupported;       // several planes: queued one by one instead
+        rot = (rot + tma_tiles(pl[i])) % n_segs;
+    }
+    return launch_pdl(kernel, grid, CFG::kThreadsT, CFG::kSmem, s, m);
 }
 
-// small planes fold the replay into K2's tail (one launch instead of two)
+// small planes go through the frame kernel (replay folded into its tail: one launch instead of two)
 template <typename CFG>
 static cudaError_t launch_k2_tma(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments, bool *folded)
 {
     static const bool no_fold = getenv("DCT_CUDA_NO_FOLD") != nullptr;   // measurement aid
     if (!no_fold && p.tab != nullptr && p.ctr != nullptr && p.nblocks <= kFoldMaxBlocks) {
         if (folded) *folded = true;
-        return launch_k2_tma_fold<CFG, true>(p, layout, adaptive, s, segments);
+        if (layout == LAYOUT_ZIGZAG)
+            return adaptive ? launch_multi_tma<CFG, 1>(k_dequant_idct_u8_tma_frame<LAYOUT_ZIGZAG, true, CFG, 1>, &p, s)
+                            : launch_multi_tma<CFG, 1>(k_dequant_idct_u8_tma_frame<LAYOUT_ZIGZAG, false, CFG, 1>, &p, s);
+        return adaptive ? launch_multi_tma<CFG, 1>(k_dequant_idct_u8_tma_frame<LAYOUT_NATURAL, true, CFG, 1>, &p, s)
+                        : launch_multi_tma<CFG, 1>(k_dequant_idct_u8_tma_frame<LAYOUT_NATURAL, false, CFG, 1>, &p, s);
     }
-    return launch_k2_tma_fold<CFG, false>(p, layout, adaptive, s, segments);
+    if (layout == LAYOUT_ZIGZAG)
+        return adaptive ? launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, true, CFG>, p, s, segments)
+                        : launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_ZIGZAG, false, CFG>, p, s, segments);
+    return adaptive ? launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_NATURAL, true, CFG>, p, s, segments)
+                    : launch_persistent_tma<CFG>(k_dequant_idct_u8_tma<LAYOUT_NATURAL, false, CFG>, p, s, segments);
 }
 
 static bool tma_eligible(const InvParams &p)
@@ -537,6 +739,27 @@ static bool tma_eligible(const InvParams &p)
     if (p.bw < 32 || ((uintptr_t)p.coef % 16)) return false;
     const unsigned long long padded = (unsigned long long)(p.nblocks / p.bw) * ((p.bw + 31) / 32) * 32;
     return padded + (unsigned long long)kMaxWorklistSegments * 64 <= p.wl_cap;
+}
+
+// 2 or 3 non-adaptive planes in one launch; cudaErrorNotSupported when the planes do not qualify (the caller then
+// queues them one by one)
+cudaError_t launch_dequant_idct_u8_multi(const InvParams *pl, int n, int layout, cudaStream_t s)
+{
+    static const bool off = getenv("DCT_CUDA_NO_MULTI") != nullptr || getenv("DCT_CUDA_NO_FOLD") != nullptr;   // measurement aids
+    if (off || n < 2 || n > 3) return cudaErrorNotSupported;
+    unsigned long long blocks = 0;
+    for (int i = 0; i < n; ++i) {
+        if (pl[i].nblocks == 0 || !tma_eligible(pl[i]) || pl[i].tab == nullptr || pl[i].ctr == nullptr || pl[i].nblocks > kFoldMaxBlocks)
+            return cudaErrorNotSupported;
+        blocks += pl[i].nblocks;
+    }
+    if (blocks > 2ull * kFoldMaxBlocks) return cudaErrorNotSupported;
+    using CFG = TmaCfg<16, 1, 2>;
+    if (layout == LAYOUT_ZIGZAG)
+        return n == 2 ? launch_multi_tma<CFG, 2>(k_dequant_idct_u8_tma_frame<LAYOUT_ZIGZAG, false, CFG, 2>, pl, s)
+                      : launch_multi_tma<CFG, 3>(k_dequant_idct_u8_tma_frame<LAYOUT_ZIGZAG, false, CFG, 3>, pl, s);
+    return n == 2 ? launch_multi_tma<CFG, 2>(k_dequant_idct_u8_tma_frame<LAYOUT_NATURAL, false, CFG, 2>, pl, s)
+                  : launch_multi_tma<CFG, 3>(k_dequant_idct_u8_tma_frame<LAYOUT_NATURAL, false, CFG, 3>, pl, s);
 }
 
 cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments, bool *folded)

@@ -106,10 +106,10 @@ __device__ __forceinline__ bool fwd_block(const FwdParams &p, const uint2 (&raw)
     static_for<0, 32>([&](auto M) {
         constexpr int m = decltype(M)::value;      // natural pair: coefficients 2m, 2m+1
         constexpr int u = m >> 2, b = m & 3;
-        float2 r2 = reinterpret_cast<const float2 *>(p.r)[m];
-        if constexpr (ADAPTIVE) {
-            if (m == 0) r2.y = __fmul_rn(r2.y, inv_s);       // DC keeps the unscaled table entry
-            else r2 = Ops<float2>::mul(r2, make_float2(inv_s, inv_s));
+        const float2 r2 = reinterpret_cast<const float2 *>(p.r)[m];
+        if constexpr (ADAPTIVE) {   // the block's 1/(2 - nv) goes onto the coefficient (in place), the table stays a constant operand
+            if (m == 0) cp[b][u].y = __fmul_rn(cp[b][u].y, inv_s);       // DC keeps the unscaled table entry
+            else cp[b][u] = Ops<float2>::mul(cp[b][u], make_float2(inv_s, inv_s));
         }
         float2 t2, e2;
         quant_residual2(cp[b][u], r2, t2, e2);
@@ -267,20 +267,215 @@ struct alignas(64) FwdTmaParams {
     uint32_t tpr;              // tiles per block row = ceil(bw / 32)
     uint32_t nby;              // block rows
     uint32_t step_ty, step_tx; // divmod(warps in the grid, tpr): how a warp's tile coordinates advance
+    uint32_t n_segs, rot;      // warps in the grid; the warp that takes the plane's tile 0
 };
 
 constexpr int kTmaOutBytes = 4096;                                  // per warp: 32 records
 constexpr int kTmaInBytes = 2048;                                   // per warp and stage: 8 rows x 256 B
 constexpr int kTmaCtlBytes = 64;                                    // per warp: up to 7 mbarriers, then the worklist count
+constexpr int kTmaMaxPlanes = 3;                                    // planes one launch may cover
+constexpr int kTmaCntBytes = 256;                                   // per CTA: flagged blocks per (plane, warp), up to 3 x 16
 
 // geometry of one kernel variant: warps per CTA, CTAs per SM the register budget is cut for, input stages per warp
 template <int WARPS, int MIN_CTAS, int STAGES> struct TmaCfg {
     static constexpr int kWarpsT = WARPS, kMinCtas = MIN_CTAS, kStages = STAGES, kThreadsT = 32 * WARPS;
-    static constexpr int kSmem = 1024 /* alignment slack */ + WARPS * (kTmaOutBytes + STAGES * kTmaInBytes + kTmaCtlBytes);
+    static constexpr int kSmem = 1024 /* alignment slack */ + WARPS * (kTmaOutBytes + STAGES * kTmaInBytes + kTmaCtlBytes) + kTmaCntBytes;
     static_assert(STAGES >= 2 && STAGES <= 7, "stages");
+    static_assert(kTmaMaxPlanes * WARPS * 4 <= kTmaCntBytes, "per-CTA counts");
 };
 
-template <int LAYOUT, bool ADAPTIVE, bool UNIFORM, typename CFG, bool FOLD>
+// What a warp carries from one plane of a launch to the next: the parity bit of each stage's mbarrier (bit i: stage i).
+struct WarpPipe {
+    uint32_t phases;
+};
+
+// All the tiles of ONE plane that fall to this warp; returns how many blocks it flagged.  The single-plane
+// kernel calls it once; the multi-plane kernel once per plane, the parameters of each plane being compile-time offsets
+// into the kernel's parameter block (so the tables stay constant-bank operands).
+template <int LAYOUT, bool ADAPTIVE, bool UNIFORM, typename CFG>
+__device__ __forceinline__ uint32_t fwd_plane_tiles(const FwdTmaParams &P, const uint32_t lane, const uint32_t gwarp, uint8_t *out_p,
+                                                uint8_t *in_p, uint32_t *cnt_p, const uint32_t bar_s, WarpPipe &pipe)
+{
+    constexpr int kS = CFG::kStages;
+    const FwdParams &p = P.f;
+    const uint32_t out_s = (uint32_t)__cvta_generic_to_shared(out_p), in_s = (uint32_t)__cvta_generic_to_shared(in_p);
+
+    // (ty, tx): block row and tile-in-row of the tile being transformed; (fy, fx): of the next tile to fetch, kS - 1 ahead.
+    // The plane's tile 0 belongs to warp `rot` of the grid (0 unless planes share the launch: each starts where the
+    // previous one ended, so the warps' tile counts differ by at most one over the whole launch).
+    uint32_t ty, tx;
+    {
+        const uint32_t t = gwarp >= P.rot ? gwarp - P.rot : gwarp + P.n_segs - P.rot;
+        ty = t / P.tpr;
+        tx = t - ty * P.tpr;
+    }
+    uint32_t fy = ty, fx = tx, fstage = 0;
+    auto fetch = [&]() {        // fetch tile (fy, fx) into stage fstage, then advance both
+        if (fy < P.nby && lane == 0) {
+            tma::mbar_expect_tx(bar_s + fstage * 8, kTmaInBytes);
+            tma::load_2d(in_s + fstage * kTmaInBytes, &P.map_px, (int)(fx * 256), (int)(fy * 8), bar_s + fstage * 8);
+        }
+        fx += P.step_tx;
+        fy += P.step_ty;
+        if (fx >= P.tpr) fx -= P.tpr, ++fy;
+        fstage = fstage + 1 == kS ? 0 : fstage + 1;
+    };
+#pragma unroll
+    for (int i = 0; i < kS - 1; ++i) fetch();
+    // my chunk j goes to 16-byte slot j ^ (lane & 7) of my 128-byte row
+    uint8_t *const my_out = out_p + lane * 128;
+    const uint32_t swz = (lane & 7) << 4;
+
+    uint32_t stage = 0;
+    while (ty < P.nby) {
+        const uint32_t bx0 = tx * 32;
+        const uint32_t warp_base = ty * p.bw + bx0;               // first record of this tile
+        const uint32_t nvalid = min(32u, p.bw - bx0);
+        fetch();                                                  // into the stage the previous iteration consumed
+        tma::mbar_wait(bar_s + stage * 8, (pipe.phases >> stage) & 1u);
+        pipe.phases ^= 1u << stage;
+
+        const uint32_t b = warp_base + lane;
+        const bool valid = lane < nvalid;
+        const uint8_t *in_stage = in_p + stage * kTmaInBytes;
+        uint2 raw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) raw[i] = *reinterpret_cast<const uint2 *>(in_stage + i * 256 + lane * 8);
+
+        uint32_t w[32];
+        const bool flag = fwd_block<LAYOUT, ADAPTIVE, UNIFORM>(p, raw, w, valid, b);
+        const unsigned ballot = __ballot_sync(0xffffffffu, flag && valid);
+
+        // the previous tile's store must have finished reading the stage before it is rewritten
+        if (lane == 0) tma::store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4 *>(my_out + ((j << 4) ^ swz)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        tma::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tma::store_2d(nvalid == 32 ? &P.map_rec : &P.map_rec_tail, 0, (int)warp_base, out_s);
+            tma::store_commit();
+        }
+
+        if (ballot != 0) {
+            // The warp appends to its own segment of the worklist (no global atomic); lane 8 writes the entry,
+            // lanes 0-7 copy one pixel row each from the input stage to the 64 bytes that go with it (read by K3).
+            uint32_t wl_n = *cnt_p;
+            __syncwarp();
+            if (lane == 0) *cnt_p = wl_n + __popc(ballot);
+            for (unsigned todo = ballot; todo != 0; todo &= todo - 1, ++wl_n) {
+                const unsigned f = __ffs(todo) - 1;
+                if (lane < 8) {
+                    if (wl_n < p.side_seg_lim)
+                        reinterpret_cast<uint2 *>(p.side + ((size_t)gwarp * p.side_seg_cap + wl_n) * 64)[lane] =
+                            *reinterpret_cast<const uint2 *>(in_stage + lane * 256 + f * 8);
+                } else if (lane == 8) {
+                    p.worklist[(size_t)gwarp * p.seg_cap + wl_n] = warp_base + f;
+                }
+            }
+        }
+        __syncwarp();   // every lane is done with this input stage: the next fetch overwrites it
+        tx += P.step_tx;
+        ty += P.step_ty;
+        if (tx >= P.tpr) tx -= P.tpr, ++ty;
+        if (++stage == kS) stage = 0;
+    }
+    // entries this warp appended to its segment for this plane; the count in shared memory starts the next plane at zero
+    __syncwarp();
+    const uint32_t n_mine = *cnt_p;
+    __syncwarp();
+    if (lane == 0) {
+        p.seg_count[gwarp] = 0;                       // replayed before the kernel ends (fwd_replay_pooled): nothing left for K3
+        *cnt_p = 0;
+    }
+    __syncwarp();
+    return n_mine;
+}
+
+// FOLD (small planes, where a launch costs more than the work): the flagged blocks are replayed in the kernel's tail and no
+// K3 is launched.  The CTA pools the entries of all its warps (and of all the planes of the launch) and deals them out in
+// batches of 32, one block per lane (replay_lane.cuh): a warp of a 4K plane flags three or four blocks, and a pass costs
+// the same for 3 lanes as for 32.  The record stage of each warp is the scratch of its passes.
+// Large planes leave the segments to K3, whose grid of replay-only warps hides the replay's latency better than a
+// tile-loop warp that stops to do it.
+template <int LAYOUT, bool ADAPTIVE, typename CFG, int NPL>
+__device__ __forceinline__ void fwd_replay_pooled(const FwdTmaParams *pl, const uint32_t (&n_mine)[NPL], uint32_t *cnt_all, const uint32_t lane,
+                                                  const uint32_t warp, uint8_t *out_p)
+{
+    constexpr int kW = CFG::kWarpsT;
+    if (lane == 0) {
+        // the patches are generic-proxy stores to records that bulk stores wrote: those must be complete, not just read
+        tma::store_wait_all();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        static_for<0, NPL>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            cnt_all[i * kW + warp] = n_mine[i];
+            if (n_mine[i] != 0) atomicAdd(&pl[i].f.ctr->replayed, (unsigned long long)n_mine[i]);
+        });
+    }
+    __syncthreads();
+    uint32_t total = 0;
+    for (int it = 0; it < NPL * kW; ++it) total += cnt_all[it];
+    LaneScratch *ws = reinterpret_cast<LaneScratch *>(out_p);
+    for (uint32_t first = warp * 32; first < total; first += kW * 32) {
+        int item = 0;
+        uint32_t e = 0;
+        const bool active = locate_entry(cnt_all, NPL * kW, first + lane, item, e);
+        const int plane = item / kW;
+        const uint32_t gw = blockIdx.x * kW + (uint32_t)(item - plane * kW);     // the warp that flagged the block
+        FwdReplayCtx cx{};
+        uint32_t b = 0;
+        const uint8_t *src = nullptr;
+        long long src_pitch = 8;
+        static_for<0, NPL>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            if (i == 0 || plane == i) {       // idle lanes run the arithmetic on plane 0's tables
+                const FwdParams &p = pl[i].f;
+                cx = FwdReplayCtx{p.r, p.thr, p.tab->D, p.tab->Q, ADAPTIVE ? 1 : 0, p.coef, p.ctr};
+                if (active && plane == i) {
+                    b = p.worklist[(size_t)gw * p.seg_cap + e];
+                    const bool side = e < p.side_seg_lim;      // the block's pixels sit next to its entry (8-byte rows), else in the plane
+                    const uint32_t by = b / p.bw, bx = b - by * p.bw;
+                    src = side ? p.side + ((size_t)gw * p.side_seg_cap + e) * 64 : p.px + ((long long)by * p.pitch + bx) * 8;
+                    src_pitch = side ? 8 : p.pitch;
+                }
+            }
+        });
+        replay_fwd_lanes<LAYOUT>(cx, ws, active, b, src, src_pitch);
+    }
+}
+
+// the warp's shared memory: [record stages, 1024-aligned for the swizzle][pixel stages][per warp: mbarriers + count]
+template <typename CFG> struct FwdWarpSmem {
+    uint8_t *out_p, *in_p;
+    uint32_t *cnt_p;
+    uint32_t *cnt_all;     // CTA-wide: blocks flagged per (plane, warp), for the pooled replay
+    uint32_t bar_s;
+    __device__ __forceinline__ FwdWarpSmem(uint8_t *smem_raw, uint32_t warp, uint32_t lane)
+    {
+        constexpr int kW = CFG::kWarpsT, kS = CFG::kStages;
+        uint8_t *sm = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+        out_p = sm + warp * kTmaOutBytes;
+        in_p = sm + kW * kTmaOutBytes + warp * (kS * kTmaInBytes);
+        uint32_t *ctl_p = reinterpret_cast<uint32_t *>(sm + kW * (kTmaOutBytes + kS * kTmaInBytes) + warp * kTmaCtlBytes);
+        cnt_p = ctl_p + 2 * kS;                                       // after the kS 8-byte mbarriers
+        cnt_all = reinterpret_cast<uint32_t *>(sm + kW * (kTmaOutBytes + kS * kTmaInBytes + kTmaCtlBytes));
+        bar_s = (uint32_t)__cvta_generic_to_shared(ctl_p);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < kS; ++i) tma::mbar_init(bar_s + 8 * i, 1);
+            *cnt_p = 0;                      // entries this warp has appended to its worklist segment
+            tma::fence_barrier_init();
+        }
+        __syncwarp();
+    }
+};
+
+// The streaming kernel: one large plane, flagged blocks left to K3.  (Kept apart from the frame kernel below, which shares
+// its tile loop in spirit but not in text: the schedule of this loop is tuned, and any code around it moves it.)
+template <int LAYOUT, bool ADAPTIVE, bool UNIFORM, typename CFG>
 __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_fwd_quant_u8_tma(const __grid_constant__ FwdTmaParams P)
 {
     constexpr int kW = CFG::kWarpsT, kS = CFG::kStages;
@@ -330,31 +525,6 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_fwd_quant_u8_
     // my chunk j goes to 16-byte slot j ^ (lane & 7) of my 128-byte row
     uint8_t *const my_out = out_p + lane * 128;
     const uint32_t swz = (lane & 7) << 4;
-
-    // Entries [first, first + n) of this warp's worklist segment, one per lane, through replay_lane.cuh.  The record
-    // stage doubles as the replay's scratch, and the patches are generic-proxy stores to records that bulk stores wrote:
-    // every bulk store of this warp must be complete (not just read) first.
-    uint32_t replayed_n = 0;                                      // entries of my segment already replayed
-    auto replay_batch = [&](uint32_t n) {
-        if constexpr (!FOLD) return;
-        if (lane == 0) {
-            tma::store_wait_all();
-            asm volatile("fence.proxy.async;" ::: "memory");
-        }
-        __syncwarp();
-        const uint32_t gwarp = blockIdx.x * kW + warp;
-        LaneScratch *ws = reinterpret_cast<LaneScratch *>(out_p);
-        const FwdReplayCtx cx{p.r, p.thr, p.tab->D, p.tab->Q, ADAPTIVE ? 1 : 0, p.coef, p.ctr};
-        const uint32_t e = replayed_n + lane;
-        const bool active = lane < n;
-        const uint32_t b = active ? p.worklist[(size_t)gwarp * p.seg_cap + e] : 0u;
-        const bool side = e < p.side_seg_cap;             // the block's pixels sit next to its entry (8-byte rows), else in the plane
-        const uint32_t by = b / p.bw, bx = b - by * p.bw;
-        const uint8_t *src = side ? p.side + ((size_t)gwarp * p.side_seg_cap + e) * 64 : p.px + ((long long)by * p.pitch + bx) * 8;
-        replay_fwd_lanes<LAYOUT>(cx, ws, active, b, src, side ? 8 : p.pitch);
-        replayed_n += n;
-        __syncwarp();                                     // the scratch is the record stage again
-    };
 
     uint32_t stage = 0, phase = 0;
     while (ty < P.nby) {
@@ -412,19 +582,38 @@ __global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_fwd_quant_u8_
         if (tx >= P.tpr) tx -= P.tpr, ++ty;
         if (++stage == kS) stage = 0, phase ^= 1;
     }
-    // ---- tail.  FOLD (small planes, where a launch costs more than the work): the warp replays the blocks of its own
-    // segment right here (replay_lane.cuh) and no K3 is launched.  Large planes leave the segments to K3, whose grid
-    // of replay-only warps hides the replay's latency better than a tile-loop warp that stops to do it (measured: in
-    // the tile loop a batch of 32 costs the warp its full latency, and 1/12 of the SM's tile throughput with it).
-    const uint32_t n_mine = *cnt_p;
-    if constexpr (FOLD) {
-        while (replayed_n < n_mine) replay_batch(min(32u, n_mine - replayed_n));
-        if (lane == 0 && n_mine != 0) atomicAdd(&p.ctr->replayed, (unsigned long long)n_mine);
-    }
+    // the flagged blocks are left to K3, whose grid of replay-only warps hides the replay's latency better than a tile-loop
+    // warp that stops to do it (small planes: k_fwd_quant_u8_tma_frame below)
     if (lane == 0) {
-        p.seg_count[blockIdx.x * kW + warp] = FOLD ? 0u : n_mine;
+        p.seg_count[blockIdx.x * kW + warp] = *cnt_p;
         tma::store_wait_read();               // shared memory must outlive the last store's reads
     }
+}
+
+// The frame kernel: one small plane, or the 2 or 3 planes of one frame (Y, Cb, Cr) in ONE launch: a persistent grid's ramp
+// and tail cost more than the tiles of a 4K plane, so a frame's planes share them, and the flagged blocks of all of them
+// are replayed in one pooled tail.  Every plane has its own worklist range (the host offsets planes of one plan).
+template <int NPL> struct alignas(64) FwdTmaMulti {
+    FwdTmaParams pl[NPL];
+};
+
+template <int LAYOUT, bool ADAPTIVE, bool UNIFORM, typename CFG, int NPL>
+__global__ void __launch_bounds__(CFG::kThreadsT, CFG::kMinCtas) k_fwd_quant_u8_tma_frame(const __grid_constant__ FwdTmaMulti<NPL> M)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const FwdWarpSmem<CFG> sm(smem_raw, warp, lane);
+    pdl_launch_dependents();
+    pdl_wait();
+    WarpPipe pipe{0};
+    uint32_t n_mine[NPL];
+    static_for<0, NPL>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        n_mine[i] = fwd_plane_tiles<LAYOUT, ADAPTIVE, UNIFORM, CFG>(M.pl[i], lane, blockIdx.x * CFG::kWarpsT + warp, sm.out_p, sm.in_p,
+                                                                   sm.cnt_p, sm.bar_s, pipe);
+    });
+    fwd_replay_pooled<LAYOUT, ADAPTIVE, CFG, NPL>(M.pl, n_mine, sm.cnt_all, lane, warp, sm.out_p);
 }
 
 
@@ -574,6 +763,50 @@ static cudaError_t launch_persistent(K kernel, const FwdParams &p, cudaStream_t 
     return cudaGetLastError();
 }
 
+// CTAs of a bulk-tensor variant that fit one SM (one value per CFG: its variants share launch bounds and shared memory)
+template <typename CFG, typename K> static unsigned tma_ctas_per_sm(K kernel)
+{
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, CFG::kThreadsT, CFG::kSmem) != cudaSuccess || n < 1) n = 1;
+        per_sm = n < CFG::kMinCtas ? n : CFG::kMinCtas;
+        if (getenv("DCT_CUDA_DEBUG"))
+            fprintf(stderr, "libdct_cuda: K1 (bulk tensor, %d warps, %d stages): %d CTAs/SM (occupancy %d), %d B smem\n", CFG::kWarpsT,
+                    CFG::kStages, per_sm, n, CFG::kSmem);
+    }
+    return (unsigned)per_sm;
+}
+
+static unsigned tma_tiles(const FwdParams &p) { return (p.nblocks / p.bw) * ((p.bw + 31) / 32); }
+
+// one plane's share of a launch of `n_segs` warps whose warp `rot` takes the plane's first tile; `seg_off`: entries of
+// every worklist segment that earlier planes of the launch (same plan, same worklist) may fill
+static cudaError_t fill_tma_plane(FwdTmaParams &q, const FwdParams &p, unsigned n_segs, unsigned rot, unsigned seg_off = 0)
+{
+    q.f = p;
+    q.nby = p.nblocks / p.bw;
+    q.tpr = (p.bw + 31) / 32;
+    q.n_segs = n_segs;
+    q.rot = rot;
+    q.step_ty = n_segs / q.tpr;
+    q.step_tx = n_segs - q.step_ty * q.tpr;
+    const unsigned ntiles = q.nby * q.tpr;
+    const unsigned tiles_per_warp = (ntiles + n_segs - 1) / n_segs;
+    q.f.seg_cap = p.wl_cap / n_segs;
+    q.f.side_seg_cap = p.side ? p.side_cap / n_segs : 0;
+    q.f.side_seg_lim = q.f.side_seg_cap > seg_off ? q.f.side_seg_cap - seg_off : 0;
+    q.f.worklist = p.worklist + seg_off;
+    if (p.side) q.f.side = p.side + (size_t)seg_off * 64;
+    if (n_segs > kMaxWorklistSegments - 128 || q.f.seg_cap < seg_off + tiles_per_warp * 32 || p.seg_count == nullptr) return cudaErrorInvalidValue;
+    const int W = (int)p.bw * 8, H = (int)q.nby * 8;
+    cudaError_t e;
+    if ((e = make_pixel_map(&q.map_px, p.px, p.pitch, W, H)) != cudaSuccess) return e;
+    if ((e = make_record_map(&q.map_rec, p.coef, p.nblocks, 32)) != cudaSuccess) return e;
+    const int tail = (int)(p.bw % 32);
+    return make_record_map(&q.map_rec_tail, p.coef, p.nblocks, tail ? tail : 32);
+}
+
 // bulk-tensor kernel: persistent grid like the cp.async one, tiles = 32 blocks of one block row
 template <typename CFG, typename K>
 static cudaError_t launch_persistent_tma(K kernel, const FwdParams &p, cudaStream_t s, unsigned *launches, WorklistSegments *segments)
@@ -581,39 +814,41 @@ static cudaError_t launch_persistent_tma(K kernel, const FwdParams &p, cudaStrea
     constexpr int kW = CFG::kWarpsT;
     cudaError_t e = ensure_smem_attributes(reinterpret_cast<const void *>(kernel), CFG::kSmem);
     if (e != cudaSuccess) return e;
-    static int per_sm = 0;   // one instance per CFG; the same for every variant of it: identical launch bounds and shared memory
-    if (per_sm == 0) {
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, CFG::kThreadsT, CFG::kSmem) != cudaSuccess || n < 1) n = 1;
-        per_sm = n < CFG::kMinCtas ? n : CFG::kMinCtas;
-        if (getenv("DCT_CUDA_DEBUG"))
-            fprintf(stderr, "libdct_cuda: K1 (bulk tensor, %d warps, %d stages): %d CTAs/SM (occupancy %d), %d B smem\n", kW, CFG::kStages,
-                    per_sm, n, CFG::kSmem);
-    }
-    FwdTmaParams q;
-    q.f = p;
-    q.nby = p.nblocks / p.bw;
-    q.tpr = (p.bw + 31) / 32;
-    const unsigned ntiles = q.nby * q.tpr;
-    const unsigned resident = (unsigned)sm_count() * (unsigned)per_sm;
-    const unsigned want = (ntiles + kW - 1) / kW;
+    const unsigned resident = (unsigned)sm_count() * tma_ctas_per_sm<CFG>(kernel);
+    const unsigned want = (tma_tiles(p) + kW - 1) / kW;
     const unsigned grid = want < resident ? want : resident;
-    const unsigned n_segs = grid * kW;
-    q.step_ty = n_segs / q.tpr;
-    q.step_tx = n_segs - q.step_ty * q.tpr;
-    const unsigned tiles_per_warp = (ntiles + n_segs - 1) / n_segs;
-    q.f.seg_cap = p.wl_cap / n_segs;
-    q.f.side_seg_cap = p.side ? p.side_cap / n_segs : 0;
-    if (n_segs > kMaxWorklistSegments - 128 || q.f.seg_cap < tiles_per_warp * 32 || p.seg_count == nullptr) return cudaErrorInvalidValue;
-    const int W = (int)p.bw * 8, H = (int)q.nby * 8;
-    if ((e = make_pixel_map(&q.map_px, p.px, p.pitch, W, H)) != cudaSuccess) return e;
-    if ((e = make_record_map(&q.map_rec, p.coef, p.nblocks, 32)) != cudaSuccess) return e;
-    const int tail = (int)(p.bw % 32);
-    if ((e = make_record_map(&q.map_rec_tail, p.coef, p.nblocks, tail ? tail : 32)) != cudaSuccess) return e;
-    if (segments) *segments = WorklistSegments{n_segs, q.f.seg_cap, q.f.side_seg_cap};
+    FwdTmaParams q;
+    if ((e = fill_tma_plane(q, p, grid * kW, 0)) != cudaSuccess) return e;
+    if (segments) *segments = WorklistSegments{q.n_segs, q.f.seg_cap, q.f.side_seg_cap};
     e = launch_pdl(kernel, grid, CFG::kThreadsT, CFG::kSmem, s, q);
     if (launches) ++*launches;
     return e;
+}
+
+// several planes, one launch (k_fwd_quant_u8_tma_multi): each plane starts at the warp where the previous one ended
+template <typename CFG, int NPL, typename K>
+static cudaError_t launch_multi_tma(K kernel, const FwdParams *pl, cudaStream_t s)
+{
+    constexpr int kW = CFG::kWarpsT;
+    cudaError_t e = ensure_smem_attributes(reinterpret_cast<const void *>(kernel), CFG::kSmem);
+    if (e != cudaSuccess) return e;
+    const unsigned resident = (unsigned)sm_count() * tma_ctas_per_sm<CFG>(kernel);
+    unsigned total = 0;
+    for (int i = 0; i < NPL; ++i) total += tma_tiles(pl[i]);
+    const unsigned want = (total + kW - 1) / kW;
+    const unsigned grid = want < resident ? want : resident;
+    const unsigned n_segs = grid * kW;
+    FwdTmaMulti<NPL> m;
+    unsigned rot = 0;
+    for (int i = 0; i < NPL; ++i) {
+        unsigned seg_off = 0;        // planes of one plan share its worklist: each gets its own range of every segment
+        for (int j = 0; j < i; ++j)
+            if (pl[j].worklist == pl[i].worklist) seg_off += (tma_tiles(pl[j]) + n_segs - 1) / n_segs * 32;
+        if ((e = fill_tma_plane(m.pl[i], pl[i], n_segs, rot, seg_off)) != cudaSuccess)
+            return NPL == 1 ? e : cudaErrorNotSupported;       // several planes: queued one by one instead
+        rot = (rot + tma_tiles(pl[i])) % n_segs;
+    }
+    return launch_pdl(kernel, grid, CFG::kThreadsT, CFG::kSmem, s, m);
 }
 
 // Small planes fold the replay into K1's tail (one launch instead of two); see the kernel's tail for why large ones do not.
@@ -628,11 +863,12 @@ static cudaError_t launch_k1_tma(const FwdParams &p, cudaStream_t s, unsigned *l
 {
     if (fold_small_plane(p)) {
         if (folded) *folded = true;
-        return p.uniform_band ? launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, true, CFG, true>, p, s, launches, segments)
-                              : launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, false, CFG, true>, p, s, launches, segments);
+        if (launches) ++*launches;
+        return p.uniform_band ? launch_multi_tma<CFG, 1>(k_fwd_quant_u8_tma_frame<LAYOUT, ADAPTIVE, true, CFG, 1>, &p, s)
+                              : launch_multi_tma<CFG, 1>(k_fwd_quant_u8_tma_frame<LAYOUT, ADAPTIVE, false, CFG, 1>, &p, s);
     }
-    return p.uniform_band ? launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, true, CFG, false>, p, s, launches, segments)
-                          : launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, false, CFG, false>, p, s, launches, segments);
+    return p.uniform_band ? launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, true, CFG>, p, s, launches, segments)
+                          : launch_persistent_tma<CFG>(k_fwd_quant_u8_tma<LAYOUT, ADAPTIVE, false, CFG>, p, s, launches, segments);
 }
 
 // the bulk-tensor kernel needs: the driver's tensor-map encoder, a 16-byte aligned plane whose pitch is a multiple
@@ -669,6 +905,31 @@ cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s)
     if (layout == LAYOUT_ZIGZAG) k_fwd_quant_f32<LAYOUT_ZIGZAG><<<grid, kThreads, 0, s>>>(p);
     else k_fwd_quant_f32<LAYOUT_NATURAL><<<grid, kThreads, 0, s>>>(p);
     return cudaGetLastError();
+}
+
+// 2 or 3 non-adaptive planes in one launch; cudaErrorNotSupported when the planes do not qualify (the caller then
+// queues them one by one)
+cudaError_t launch_fwd_quant_u8_multi(const FwdParams *pl, int n, int layout, cudaStream_t s)
+{
+    static const bool off = getenv("DCT_CUDA_NO_MULTI") != nullptr;      // measurement aid
+    if (off || n < 2 || n > 3) return cudaErrorNotSupported;
+    bool uniform = true;
+    unsigned long long blocks = 0;
+    for (int i = 0; i < n; ++i) {
+        if (pl[i].nblocks == 0 || !tma_eligible(pl[i]) || !fold_small_plane(pl[i])) return cudaErrorNotSupported;
+        uniform = uniform && pl[i].uniform_band;
+        blocks += pl[i].nblocks;
+    }
+    if (blocks > 2ull * kFoldMaxBlocks) return cudaErrorNotSupported;
+    using CFG = TmaCfg<12, 1, 2>;
+#define DCTB_MULTI(L, U, N) launch_multi_tma<CFG, N>(k_fwd_quant_u8_tma_frame<L, false, U, CFG, N>, pl, s)
+    if (layout == LAYOUT_ZIGZAG) {
+        if (n == 2) return uniform ? DCTB_MULTI(LAYOUT_ZIGZAG, true, 2) : DCTB_MULTI(LAYOUT_ZIGZAG, false, 2);
+        return uniform ? DCTB_MULTI(LAYOUT_ZIGZAG, true, 3) : DCTB_MULTI(LAYOUT_ZIGZAG, false, 3);
+    }
+    if (n == 2) return uniform ? DCTB_MULTI(LAYOUT_NATURAL, true, 2) : DCTB_MULTI(LAYOUT_NATURAL, false, 2);
+    return uniform ? DCTB_MULTI(LAYOUT_NATURAL, true, 3) : DCTB_MULTI(LAYOUT_NATURAL, false, 3);
+#undef DCTB_MULTI
 }
 
 cudaError_t launch_fwd_quant_u8(const FwdParams &p, int layout, int adaptive, cudaStream_t s, unsigned *launches,

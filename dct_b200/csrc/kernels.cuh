@@ -66,6 +66,7 @@ struct FwdParams {
     uint32_t *seg_count;       // one entry per warp of the grid
     uint32_t seg_cap;          // worklist entries per segment (>= 32 * tiles per warp)
     uint32_t side_seg_cap;     // side slots per segment (entries beyond it have no pixel copy)
+    uint32_t side_seg_lim;     // bulk-tensor kernel: entries of this plane with a pixel copy (= side_seg_cap unless planes share the segment)
     int no_tma;                // 1: keep the cp.async kernel (planes mapped from a peer GPU)
     // bulk-tensor kernel only: every warp replays the blocks of its own worklist segment at the end of its tile loop
     // (replay_lane.cuh) instead of leaving them to a K3 launch; needs the exact tables
@@ -149,6 +150,10 @@ cudaError_t launch_fwd_quant_f32(const FwdParams &p, int layout, cudaStream_t s)
 // `segments`: geometry of the segmented worklist the launch produced (n_segs == 0: flat worklist counted in ctr->wl_count)
 cudaError_t launch_dequant_idct_u8(const InvParams &p, int layout, int adaptive, cudaStream_t s, WorklistSegments *segments = nullptr,
                                    bool *folded = nullptr);
+// 2 or 3 small non-adaptive planes (one frame's Y, Cb, Cr) in ONE launch each way, every plane replaying its own flagged
+// blocks; cudaErrorNotSupported (nothing launched) when the planes do not qualify
+cudaError_t launch_fwd_quant_u8_multi(const FwdParams *planes, int n, int layout, cudaStream_t s);
+cudaError_t launch_dequant_idct_u8_multi(const InvParams *planes, int n, int layout, cudaStream_t s);
 cudaError_t launch_dequant_idct_u8_f64(const InvParams &p, const ExactTables *d_tab, int layout, cudaStream_t s);
 cudaError_t launch_replay_fwd(const ReplayParams &p, cudaStream_t s);
 cudaError_t launch_replay_inv(const ReplayParams &p, cudaStream_t s);

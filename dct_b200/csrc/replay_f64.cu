@@ -183,10 +183,9 @@ __global__ void __launch_bounds__(kReplayThreads, 4) k_replay_fwd(const ReplayPa
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int k = 8 * u + r;
-                float rk = tab.r32[k];
-                if (p.adaptive && k != 0) rk = __fmul_rn(rk, inv_s);
+                const float xu = (p.adaptive && k != 0) ? __fmul_rn(x[u], inv_s) : x[u];   // as fwd_block (fwd_quant.cu)
                 float t, e;
-                quant_residual(x[u], rk, t, e);
+                quant_residual(xu, tab.r32[k], t, e);
                 if (fabsf(e) >= (F32 ? tab.thr32f[k] : tab.thr32[k])) need |= 1ull << k;
             }
             need = group_or(need);            // full-warp shuffles: every lane must take part

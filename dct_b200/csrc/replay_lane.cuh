@@ -53,13 +53,39 @@ __device__ __forceinline__ double byte_centered(uint2 raw, int m)
 
 constexpr int kPairsPerRound = 4;                  // (block, value) pairs one lane may append per round
 
-// per-warp scratch of the lane replays (2 944 bytes; the bulk-tensor kernels lend their idle record stage)
+// per-warp scratch of the lane replays (3 712 bytes; the bulk-tensor kernels lend their idle record stage)
 struct alignas(16) LaneScratch {
     uint2 px[32][9];                               // [block][row + pad]: the blocks' pixels for the replay phase
-    unsigned blk[32];
+    int16_t *rec[32];                              // each block's record,
+    const double *Q[32];                           // its plan's quant_matrix
+    Counters *ctr[32];                             // and its plan's counters: the blocks of one pass may belong to several planes
+    unsigned ties[32];                             // near-ties found in each block by the lanes that replayed its values
     double scale[32];                              // adaptive: 2 - nv (forward) or 1 / (2 - nv) (inverse) of each block
     unsigned short pairs[32 * kPairsPerRound];     // (source lane << 6) | natural index
 };
+
+// The lanes' counts `mine` added to their own counters, one atomic per distinct set of counters in the warp
+__device__ __forceinline__ void add_near_ties(Counters *ctr, unsigned mine)
+{
+    const unsigned grp = __match_any_sync(0xffffffffu, (unsigned long long)ctr);
+    const unsigned sum = __reduce_add_sync(grp, mine);
+    if ((threadIdx.x & 31) == (unsigned)__ffs(grp) - 1u && sum != 0) atomicAdd(&ctr->near_ties, (unsigned long long)sum);
+}
+
+// Entry g of a list made of `n_items` runs of cnt[0], cnt[1], ... entries: which run, and where in it (false: past the end)
+__device__ __forceinline__ bool locate_entry(const uint32_t *cnt, int n_items, uint32_t g, int &item, uint32_t &e)
+{
+    uint32_t base = 0;
+    for (int it = 0; it < n_items; ++it) {
+        const uint32_t c = cnt[it];
+        if (g - base < c) {
+            item = it, e = g - base;
+            return true;
+        }
+        base += c;
+    }
+    return false;
+}
 
 // where the forward replay finds its tables and its output (any address space behind the pointers)
 struct FwdReplayCtx {
@@ -77,7 +103,9 @@ struct FwdReplayCtx {
 //   2. the warp compacts the flagged (block, coefficient) pairs into a list and every lane replays ONE value on its
 //      own: the reference's 64 + 8 non-contracted fp64 multiply-adds in its own order (src/dct.c:57-74), true
 //      division, half-away rounding (src/quantization.c:122-126), and patches it into the record.
-// Adds the near-tie / saturation counts to cx.ctr.  Every lane of the warp must call it.
+// Adds the near-tie / saturation counts to cx.ctr.  Every lane of the warp must call it.  The context may differ from
+// lane to lane (blocks of several planes, each with its own tables, in one pass): what phase 2 needs of another lane's
+// block goes through the scratch.  D (the 8x8 DCT matrix) and `adaptive` are the same for all lanes.
 template <int LAYOUT>
 __device__ __noinline__ void replay_fwd_lanes(const FwdReplayCtx cx, LaneScratch *ws, bool active, unsigned b, const uint8_t *src,
                                               long long src_pitch)
@@ -110,9 +138,8 @@ __device__ __noinline__ void replay_fwd_lanes(const FwdReplayCtx cx, LaneScratch
 #pragma unroll
     for (int k = 0; k < 64; ++k) {
         float t, e;
-        float rk = cx.r32[k];
-        if (k != 0) rk = __fmul_rn(rk, inv_s);        // inv_s == 1.0f exactly when the table is not adaptive
-        quant_residual(c[k], rk, t, e);
+        const float ck = k != 0 ? __fmul_rn(c[k], inv_s) : c[k];   // as fwd_block; inv_s == 1.0f exactly when the table is not adaptive
+        quant_residual(ck, cx.r32[k], t, e);
         if (fabsf(e) >= cx.thr32[k]) (k < 32 ? need_lo : need_hi) |= 1u << (k & 31);
     }
     if (!active) need_lo = need_hi = 0;
@@ -120,8 +147,10 @@ __device__ __noinline__ void replay_fwd_lanes(const FwdReplayCtx cx, LaneScratch
     if (cx.adaptive) ws->scale[lane] = scale;
 #pragma unroll
     for (int i = 0; i < 8; ++i) ws->px[lane][i] = row[i];
-    ws->blk[lane] = b;
-    unsigned ties = 0, sat = 0;
+    ws->rec[lane] = cx.coef + (size_t)b * 64;
+    ws->Q[lane] = cx.Q;
+    ws->ctr[lane] = cx.ctr;
+    ws->ties[lane] = 0;
 
     // ---- phase 2: rounds of (compact the pairs, one lane replays one value) until no lane has any left
     while (__any_sync(0xffffffffu, (need_lo | need_hi) != 0)) {
@@ -162,7 +191,7 @@ __device__ __noinline__ void replay_fwd_lanes(const FwdReplayCtx cx, LaneScratch
                 for (int m = 0; m < 8; ++m) temp = __dadd_rn(temp, __dmul_rn(byte_centered(raw, m), dj[m]));
                 out = __dadd_rn(out, __dmul_rn(Di[kk], temp));
             }
-            double mq = cx.Q[k];
+            double mq = ws->Q[sl][k];
             if (cx.adaptive && k != 0) {                          // src/quantization.c:196-204
                 mq = __dmul_rn(mq, ws->scale[sl]);
                 if (mq < 1.0) mq = 1.0;
@@ -170,20 +199,17 @@ __device__ __noinline__ void replay_fwd_lanes(const FwdReplayCtx cx, LaneScratch
             const double y = __ddiv_rn(out, mq);                 // src/quantization.c:124
             const double rr = round_half_away(y);
             int q = (int)rr;
-            if (rr > 32767.0) q = 32767, ++sat;
-            if (rr < -32768.0) q = -32768, ++sat;
-            ties += near_half(y);
+            if (rr > 32767.0 || rr < -32768.0) {                 // exotic tables only: counted where it happens
+                q = rr > 0.0 ? 32767 : -32768;
+                atomicAdd(&ws->ctr[sl]->saturated, 1ull);
+            }
+            if (near_half(y)) atomicAdd(&ws->ties[sl], 1u);      // integer pixels make exact ties common (DC = sum / 8)
             const int pos = LAYOUT == LAYOUT_ZIGZAG ? cZigZagInv.pos[k] : k;
-            cx.coef[(size_t)ws->blk[sl] * 64 + pos] = (int16_t)q;
+            ws->rec[sl][pos] = (int16_t)q;
         }
         __syncwarp();
     }
-    ties = __reduce_add_sync(0xffffffffu, ties);
-    sat = __reduce_add_sync(0xffffffffu, sat);
-    if (lane == 0) {
-        if (ties) atomicAdd(&cx.ctr->near_ties, (unsigned long long)ties);
-        if (sat) atomicAdd(&cx.ctr->saturated, (unsigned long long)sat);
-    }
+    add_near_ties(cx.ctr, ws->ties[lane]);
 }
 
 
@@ -191,7 +217,11 @@ __device__ __noinline__ void replay_fwd_lanes(const FwdReplayCtx cx, LaneScratch
 // inverse: dequantize (src/quantization.c:133-151) and dct_inverse (src/dct.c:80-105), one lane per flagged block
 // ------------------------------------------------------------------------------------------------------------------
 struct alignas(16) InvLaneScratch {
-    unsigned blk[32];
+    const int16_t *rec[32];                        // each block's record,
+    uint8_t *dst[32];                              // its first pixel and the pitch of its plane,
+    long long pitch[32];
+    const double *R[32];                           // and its plan's dequant_matrix: the blocks of one pass may belong to several planes
+    unsigned ties[32];                             // near-ties found in each block by the lanes that replayed its pixels
     double inv_s[32];                              // adaptive: 1 / (2 - nv) of each block (src/quantization.c:193)
     double s[32];                                  // adaptive: 2 - nv
     float bound[32];                               // the block's fp32 bound (sum gain_k |v_k|)
@@ -296,7 +326,8 @@ __device__ __noinline__ double fast_inverse_sample(const uint4 *q4, const double
 //      the block; every other pixel is already right in memory and is not touched;
 //   2. the warp compacts the flagged (block, pixel) pairs into a list and every lane replays ONE pixel on its own,
 //      in the reference's own operation order (exact_inverse_sample), then the pixel rule; one byte store.
-// Adds the near-tie count to cx.ctr.  Every lane of the warp must call it.
+// Adds the near-tie count to cx.ctr.  Every lane of the warp must call it.  As in replay_fwd_lanes the context may
+// differ from lane to lane (non-adaptive plans; D is the same for all).
 template <int LAYOUT, bool ADAPTIVE>
 __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScratch *ws, bool active, unsigned b)
 {
@@ -311,7 +342,14 @@ __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScra
         ws->inv_s[lane] = __ddiv_rn(1.0, two_minus_nv);
         s32 = adaptive_scale(var);
     }
-    ws->blk[lane] = b;
+    {
+        const unsigned by = b / cx.bw, bx = b - by * cx.bw;
+        ws->rec[lane] = rec;
+        ws->dst[lane] = cx.px + (long long)by * 8 * cx.pitch + (long long)bx * 8;
+        ws->pitch[lane] = cx.pitch;
+        ws->R[lane] = cx.R;
+        ws->ties[lane] = 0;
+    }
 
     // ---- phase 1: K2's fp32 arithmetic for the whole block (inv_block of dequant_idct.cu, scalar), flagged pixels
     float v[64];
@@ -334,8 +372,12 @@ __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScra
     if constexpr (ADAPTIVE) bound = adaptive_bound(bound, bound_dc, s32);
     {
         // K2's folded first stage (idct8_dequant), scalar: same operations on the same operands; adaptive plans scale
-        // the multipliers by the block's (2 - nv), the DC entry excepted
+        // the 63 AC values by the block's (2 - nv) first
         constexpr int ra[4] = {0, 2, 5, 1}, rb[4] = {4, 6, 3, 7};
+        if constexpr (ADAPTIVE) {
+#pragma unroll
+            for (int k = 1; k < 64; ++k) v[k] = __fmul_rn(v[k], s32);
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float ma[4];
@@ -344,10 +386,6 @@ __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScra
             for (int j = 0; j < 4; ++j) {
                 ma[j] = cx.rs32[8 * ra[j] + c];
                 mb[j].pos = cx.rs32[8 * rb[j] + c];
-                if constexpr (ADAPTIVE) {
-                    if (!(c == 0 && j == 0)) ma[j] = __fmul_rn(ma[j], s32);
-                    mb[j].pos = __fmul_rn(mb[j].pos, s32);
-                }
                 mb[j].neg = -mb[j].pos;
             }
             idct8_dequant<float, 8>(&v[c], ma, mb);
@@ -369,7 +407,6 @@ __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScra
         }
     }
     if (!active) need_lo = need_hi = 0;
-    unsigned ties = 0;
 
     // ---- phase 2: rounds of (compact the pairs, one lane replays one pixel) until no lane has any left
     while (__any_sync(0xffffffffu, (need_lo | need_hi) != 0)) {
@@ -397,11 +434,9 @@ __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScra
         for (int pi = lane; pi < total; pi += 32) {
             const unsigned pr = ws->pairs[pi];
             const int sl = pr >> 6, e = pr & 63, i = e >> 3, j = e & 7;
-            const unsigned bb = ws->blk[sl];
-            const uint4 *q4 = reinterpret_cast<const uint4 *>(cx.coef + (size_t)bb * 64);
+            const uint4 *q4 = reinterpret_cast<const uint4 *>(ws->rec[sl]);
             const double inv_two_minus_nv = ADAPTIVE ? ws->inv_s[sl] : 1.0;
-            const unsigned by = bb / cx.bw, bx = bb - by * cx.bw;
-            uint8_t *px = cx.px + ((long long)by * 8 + i) * cx.pitch + (long long)bx * 8 + j;
+            uint8_t *px = ws->dst[sl] + i * ws->pitch[sl] + j;
             if constexpr (ADAPTIVE) {
                 // plain fp64 first: |fast - reference| <= 1e-14 * bound (64 products, each within 2^-52 of terms that
                 // sum gain_k |v_k| dominates); farther than that (+ the 1e-9 tie-accounting margin) from a boundary
@@ -413,17 +448,16 @@ __device__ __noinline__ void replay_inv_lanes(const InvReplayCtx cx, InvLaneScra
                     continue;
                 }
             }
-            const double out = exact_inverse_sample<LAYOUT, ADAPTIVE>(q4, cx.D, cx.R, inv_two_minus_nv, i, j);
+            const double out = exact_inverse_sample<LAYOUT, ADAPTIVE>(q4, cx.D, ws->R[sl], inv_two_minus_nv, i, j);
             const double val = __dadd_rn(out, 128.0);
             double rr = round_half_away(val);
             rr = rr < 0.0 ? 0.0 : (rr > 255.0 ? 255.0 : rr);
-            ties += near_half(val);
+            if (near_half(val)) atomicAdd(&ws->ties[sl], 1u);
             *px = (uint8_t)rr;
         }
         __syncwarp();
     }
-    ties = __reduce_add_sync(0xffffffffu, ties);
-    if (lane == 0 && ties) atomicAdd(&cx.ctr->near_ties, (unsigned long long)ties);
+    add_near_ties(cx.ctr, ws->ties[lane]);
 }
 
 }  // namespace dctb

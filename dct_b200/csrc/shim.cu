@@ -231,6 +231,65 @@ int check_ragged(const void *a, const void *b, size_t pitch, int W, int H, int n
     return DCT_CUDA_OK;
 }
 
+// K1's parameters for one device-resident 8x8 plane on lane `ln`
+FwdParams fwd_params(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, uint32_t bw, uint32_t nblocks, int16_t *d_coef,
+                     double *d_var, bool use_side, int elem)
+{
+    FwdParams fp{};
+    fp.px = d_px;
+    fp.pitch = (long long)pitch;
+    fp.bw = bw;
+    fp.nblocks = nblocks;
+    fp.coef = d_coef;
+    fp.var_out = p->adaptive ? d_var : nullptr;
+    fp.worklist = ln.d_wl;
+    fp.wl_cap = ln.wl_cap;
+    fp.ctr = ln.d_ctr;
+    memcpy(fp.r, p->r, sizeof fp.r);
+    memcpy(fp.thr, elem == 4 ? p->thr_f32 : p->thr, sizeof fp.thr);
+    fp.thr_min = p->thr_min;
+    fp.uniform_band = p->uniform_band;
+    fp.side = use_side ? ln.d_side : nullptr;
+    fp.side_cap = use_side ? ln.side_cap : 0;
+    fp.seg_count = ln.d_seg_count;
+    fp.no_tma = p->no_tma ? 1 : 0;
+    fp.tab = p->skip_replay ? nullptr : p->d_tab;     // lets the bulk-tensor kernel replay its own flagged blocks
+    return fp;
+}
+
+// K2's parameters for one device-resident 8x8 plane on lane `ln`
+InvParams inv_params(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, const double *d_var, uint8_t *d_px, size_t pitch, uint32_t bw,
+                     uint32_t nblocks)
+{
+    InvParams ip{};
+    ip.coef = d_coef;
+    ip.var_in = p->adaptive ? d_var : nullptr;
+    ip.px = d_px;
+    ip.pitch = (long long)pitch;
+    ip.bw = bw;
+    ip.nblocks = nblocks;
+    ip.worklist = ln.d_wl;
+    ip.wl_cap = ln.wl_cap;
+    ip.ctr = ln.d_ctr;
+    memcpy(ip.rs, p->rs, sizeof ip.rs);
+    memcpy(ip.gain, p->gain, sizeof ip.gain);
+    memcpy(ip.rg, p->rg, sizeof ip.rg);
+    ip.band_floor = p->band_floor;
+    ip.seg_count = ln.d_seg_count;
+    ip.no_tma = p->no_tma ? 1 : 0;
+    ip.tab = p->skip_replay ? nullptr : p->d_tab;     // lets the bulk-tensor kernel replay its own flagged blocks
+    // multipliers of the folded first stage, in the kernel's pair order
+    static const int colA[4] = {0, 2, 5, 1}, colB[4] = {4, 6, 3, 7};
+    for (int c = 0; c < 4; ++c)
+        for (int j = 0; j < 4; ++j) {
+            const int ra = colA[j], rb = colB[j];                  // first-stage row pair (a_j, b_j)
+            ip.ma[c][j] = make_float2(p->rs[8 * ra + colA[c]], p->rs[8 * ra + colB[c]]);
+            ip.mb[c][j].pos = make_float2(p->rs[8 * rb + colA[c]], p->rs[8 * rb + colB[c]]);
+            ip.mb[c][j].neg = make_float2(-ip.mb[c][j].pos.x, -ip.mb[c][j].pos.y);
+        }
+    return ip;
+}
+
 // queue K1 (+K3) for one device-resident plane on lane `ln`, stream `s`
 // elem: bytes per pixel of the source plane -- 1 (uint8) or 4 (float tiles); pitch is in bytes
 int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int W, int H, int16_t *d_coef,
@@ -272,25 +331,7 @@ int queue_fwd(dct_cuda_plan *p, Lane &ln, const uint8_t *d_px, size_t pitch, int
     rp.var_out = p->adaptive ? d_var : nullptr;
     bool folded = false;                                  // K1 replayed its flagged blocks itself: no K3 launch
     if (!p->exotic) {
-        FwdParams fp{};
-        fp.px = d_px;
-        fp.pitch = (long long)pitch;
-        fp.bw = bw;
-        fp.nblocks = nblocks;
-        fp.coef = d_coef;
-        fp.var_out = p->adaptive ? d_var : nullptr;
-        fp.worklist = ln.d_wl;
-        fp.wl_cap = ln.wl_cap;
-        fp.ctr = ln.d_ctr;
-        memcpy(fp.r, p->r, sizeof fp.r);
-        memcpy(fp.thr, elem == 4 ? p->thr_f32 : p->thr, sizeof fp.thr);
-        fp.thr_min = p->thr_min;
-        fp.uniform_band = p->uniform_band;
-        fp.side = use_side ? ln.d_side : nullptr;
-        fp.side_cap = use_side ? ln.side_cap : 0;
-        fp.seg_count = ln.d_seg_count;
-        fp.no_tma = p->no_tma ? 1 : 0;
-        fp.tab = p->skip_replay ? nullptr : p->d_tab;     // lets the bulk-tensor kernel replay its own flagged blocks
+        const FwdParams fp = fwd_params(p, ln, d_px, pitch, bw, nblocks, d_coef, d_var, use_side, elem);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (p->profile) {
             CU_TRY(cudaEventCreate(&e0));
@@ -350,33 +391,7 @@ int queue_inv(dct_cuda_plan *p, Lane &ln, const int16_t *d_coef, int W, int H, i
     rp.px_out = d_px;
     bool folded = false;                                  // K2 replayed its flagged blocks itself: no K3 launch
     if (!p->exotic) {
-        InvParams ip{};
-        ip.coef = d_coef;
-        ip.var_in = p->adaptive ? d_var : nullptr;
-        ip.px = d_px;
-        ip.pitch = (long long)pitch;
-        ip.bw = bw;
-        ip.nblocks = nblocks;
-        ip.worklist = ln.d_wl;
-        ip.wl_cap = ln.wl_cap;
-        ip.ctr = ln.d_ctr;
-        memcpy(ip.rs, p->rs, sizeof ip.rs);
-        memcpy(ip.gain, p->gain, sizeof ip.gain);
-        memcpy(ip.rg, p->rg, sizeof ip.rg);
-        ip.band_floor = p->band_floor;
-        ip.seg_count = ln.d_seg_count;
-        ip.no_tma = p->no_tma ? 1 : 0;
-        ip.tab = p->skip_replay ? nullptr : p->d_tab;     // lets the bulk-tensor kernel replay its own flagged blocks
-        {   // multipliers of the folded first stage, in the kernel's pair order
-            static const int colA[4] = {0, 2, 5, 1}, colB[4] = {4, 6, 3, 7};
-            for (int c = 0; c < 4; ++c)
-                for (int j = 0; j < 4; ++j) {
-                    const int ra = colA[j], rb = colB[j];                  // first-stage row pair (a_j, b_j)
-                    ip.ma[c][j] = make_float2(p->rs[8 * ra + colA[c]], p->rs[8 * ra + colB[c]]);
-                    ip.mb[c][j].pos = make_float2(p->rs[8 * rb + colA[c]], p->rs[8 * rb + colB[c]]);
-                    ip.mb[c][j].neg = make_float2(-ip.mb[c][j].pos.x, -ip.mb[c][j].pos.y);
-                }
-        }
+        const InvParams ip = inv_params(p, ln, d_coef, d_var, d_px, pitch, bw, nblocks);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (p->profile) {
             CU_TRY(cudaEventCreate(&e0));
@@ -578,9 +593,73 @@ extern "C" int dct_cuda_dequant_idct_u8_dev(dct_cuda_plan *p, const int16_t *d_c
     return queue_inv(p, p->lane[0], d_coef, W, H, layout, d_var, d_px, pitch, (cudaStream_t)stream);
 }
 
+// The 2 or 3 planes of one frame (Y, Cb, Cr) in ONE launch each way.  A persistent grid's ramp and tail cost more than
+// the tiles of a 4K plane, so planes queued one by one pay them three times: 8K 4:2:0 took 107 us per frame that way.
+// Qualifying planes: 8x8 non-adaptive plans on one device, each plane small enough to replay its flagged blocks in the
+// kernel's tail (kFoldMaxBlocks) and laid out for the bulk-tensor kernels.  Returns false (nothing queued) otherwise:
+// the caller then queues the planes one by one, which also reports any argument error.
+static bool queue_planes_together(const dct_cuda_plane *pl, int n, int layout, cudaStream_t s, bool forward, int *rc_out)
+{
+    if (n < 2 || n > 3 || (layout != DCT_CUDA_NATURAL && layout != DCT_CUDA_ZIGZAG)) return false;
+    dct_cuda_plan *plans[3];
+    for (int i = 0; i < n; ++i) {
+        dct_cuda_plan *p = pl[i].plan;
+        if (!p || p->n != 8 || p->adaptive || p->exotic || p->skip_replay || p->profile || p->no_tma || p->device != pl[0].plan->device)
+            return false;
+        const void *px = forward ? pl[i].pixels_in : (const void *)pl[i].pixels_out;
+        if (!px || !pl[i].coef || pl[i].width <= 0 || pl[i].height <= 0 || (pl[i].width % 8) || (pl[i].height % 8)) return false;
+        if (pl[i].pitch < (size_t)pl[i].width || (pl[i].pitch % 8) || ((uintptr_t)px % 8) || ((uintptr_t)pl[i].coef % 16)) return false;
+        if ((uint64_t)(pl[i].width / 8) * (uint64_t)(pl[i].height / 8) > kFoldMaxBlocks) return false;
+        plans[i] = p;
+    }
+    // every distinct plan once, in address order (two threads queueing the same plans cannot deadlock)
+    dct_cuda_plan *uniq[3];
+    int nu = 0;
+    for (int i = 0; i < n; ++i) {
+        bool seen = false;
+        for (int j = 0; j < nu; ++j) seen = seen || uniq[j] == plans[i];
+        if (!seen) uniq[nu++] = plans[i];
+    }
+    std::sort(uniq, uniq + nu);
+    std::unique_lock<std::mutex> locks[3];
+    for (int j = 0; j < nu; ++j) locks[j] = std::unique_lock<std::mutex>(uniq[j]->mu);
+    DeviceGuard g(plans[0]->device);
+
+    FwdParams fp[3];
+    InvParams ip[3];
+    for (int j = 0; j < nu; ++j) {          // one worklist per plan: its planes take consecutive ranges of every warp's segment
+        size_t want = 0;
+        for (int i = 0; i < n; ++i)
+            if (plans[i] == uniq[j]) want += worklist_entries(pl[i].width / 8, pl[i].height / 8);
+        if (ensure_worklist(uniq[j]->lane[0], want) != DCT_CUDA_OK) return false;
+    }
+    static const bool no_side = getenv("DCT_CUDA_NO_SIDE") != nullptr;
+    for (int i = 0; i < n; ++i) {
+        Lane &ln = plans[i]->lane[0];
+        const uint32_t bw = pl[i].width / 8, nblocks = bw * (uint32_t)(pl[i].height / 8);
+        if (forward)
+            fp[i] = fwd_params(plans[i], ln, (const uint8_t *)pl[i].pixels_in, pl[i].pitch, bw, nblocks, (int16_t *)pl[i].coef, nullptr,
+                               !no_side, 1);
+        else
+            ip[i] = inv_params(plans[i], ln, (const int16_t *)pl[i].coef, nullptr, (uint8_t *)pl[i].pixels_out, pl[i].pitch, bw, nblocks);
+    }
+    const cudaError_t e = forward ? launch_fwd_quant_u8_multi(fp, n, layout, s) : launch_dequant_idct_u8_multi(ip, n, layout, s);
+    if (e == cudaErrorNotSupported) return false;
+    if (e != cudaSuccess) {
+        *rc_out = fail(DCT_CUDA_ECUDA, "%s planes in one launch: %s", forward ? "forward" : "inverse", cudaGetErrorString(e));
+        return true;
+    }
+    ++plans[0]->launches;
+    for (int i = 0; i < n; ++i) plans[i]->lane[0].blocks += (uint64_t)(pl[i].width / 8) * (uint64_t)(pl[i].height / 8);
+    *rc_out = DCT_CUDA_OK;
+    return true;
+}
+
 extern "C" int dct_cuda_fwd_quant_planes_dev(const dct_cuda_plane *pl, int n, int layout, void *stream)
 {
     if (!pl || n < 0) return fail(DCT_CUDA_EINVAL, "bad plane list");
+    int together = DCT_CUDA_OK;
+    if (queue_planes_together(pl, n, layout, (cudaStream_t)stream, true, &together)) return together;
     for (int i = 0; i < n; ++i) {
         int rc = dct_cuda_fwd_quant_u8_dev(pl[i].plan, (const uint8_t *)pl[i].pixels_in, pl[i].pitch, pl[i].width,
                                            pl[i].height, (int16_t *)pl[i].coef, layout, pl[i].variance, stream);
@@ -592,6 +671,8 @@ extern "C" int dct_cuda_fwd_quant_planes_dev(const dct_cuda_plane *pl, int n, in
 extern "C" int dct_cuda_dequant_idct_planes_dev(const dct_cuda_plane *pl, int n, int layout, void *stream)
 {
     if (!pl || n < 0) return fail(DCT_CUDA_EINVAL, "bad plane list");
+    int together = DCT_CUDA_OK;
+    if (queue_planes_together(pl, n, layout, (cudaStream_t)stream, false, &together)) return together;
     for (int i = 0; i < n; ++i) {
         int rc = dct_cuda_dequant_idct_u8_dev(pl[i].plan, (const int16_t *)pl[i].coef, pl[i].width, pl[i].height,
                                               layout, pl[i].variance, (uint8_t *)pl[i].pixels_out, pl[i].pitch,

@@ -412,6 +412,90 @@ def test_config3_8k_420_frame(api, oracle, torch):
             assert np.array_equal(d_out[i].cpu().numpy(), want_p), i
 
 
+@pytest.mark.parametrize("layout", ["natural", "zigzag"])
+@pytest.mark.parametrize("shapes", [
+    [(1088, 1920), (544, 960), (544, 960)],        # 4:2:0: partial tiles in every chroma block row (120 blocks)
+    [(720, 1280), (720, 1280), (720, 1280)],       # 4:4:4
+    [(1088, 1920), (544, 1920)],                   # NV12: luma + one interleaved chroma plane
+    [(64, 256), (2160, 3840), (8, 512)],           # planes with fewer tiles than the grid has warps
+])
+def test_planes_of_a_frame_share_one_launch(api, oracle, torch, shapes, layout):
+    """dct_cuda_*_planes_dev: the planes of one frame go through ONE launch each way (non-adaptive 8x8 plans), each
+    plane with its own table; results are those of the planes queued one by one (the oracle's)."""
+    lay = api.ZIGZAG if layout == "zigzag" else api.NATURAL
+    zz = 1 if layout == "zigzag" else 0
+    rng = np.random.default_rng(sum(h * w for h, w in shapes) + zz)
+    Ql = oracle.quant_table(90)
+    Qc = np.clip(np.full((8, 8), 99.0) * 0.5 + np.arange(64).reshape(8, 8) * 0.25, 1.0, 255.0)
+    n = len(shapes)
+    planes = [rng.integers(0, 256, size=s, dtype=np.uint8) for s in shapes]
+    planes[-1][:] = (np.add.outer(np.arange(shapes[-1][0]), np.arange(shapes[-1][1])) // 3 % 256).astype(np.uint8)   # smooth: many near-ties
+    with Ctx(api, 90, 0) as luma, Ctx(api, 50, 0, table=Qc) as chr_:
+        descs = (api.PlaneDesc * n)()
+        pitches = [s[1] + 16 * (i % 2) for i, s in enumerate(shapes)]            # one plane with padded rows
+        d_px = [torch.zeros((s[0], pt), dtype=torch.uint8, device="cuda") for s, pt in zip(shapes, pitches)]
+        for t, p_ in zip(d_px, planes):
+            t[:, :p_.shape[1]] = torch.from_numpy(p_).cuda()
+        d_out = [torch.zeros_like(t) for t in d_px]
+        d_coef = [torch.empty((s[0] // 8 * (s[1] // 8), 64), dtype=torch.int16, device="cuda") for s in shapes]
+        ctxs = [luma] + [chr_] * (n - 1)
+        for i, (s, cx) in enumerate(zip(shapes, ctxs)):
+            descs[i].plan = cx.plan._h
+            descs[i].pixels_in, descs[i].pixels_out = d_px[i].data_ptr(), d_out[i].data_ptr()
+            descs[i].pitch, descs[i].width, descs[i].height = pitches[i], s[1], s[0]
+            descs[i].coef, descs[i].variance = d_coef[i].data_ptr(), None
+        stream = torch.cuda.current_stream().cuda_stream
+        before = luma.plan.kernel_launches() + chr_.plan.kernel_launches()
+        assert api._fwd_planes(descs, n, lay, stream) == 0
+        assert api._inv_planes(descs, n, lay, stream) == 0
+        torch.cuda.synchronize()
+        assert luma.plan.kernel_launches() + chr_.plan.kernel_launches() - before == 2       # one launch each way
+        for i, (s, Q) in enumerate(zip(shapes, [Ql] + [Qc] * (n - 1))):
+            want_c, _, _ = oracle.fwd_quant_plane(planes[i], Q, 0, zz, nthreads=8)
+            assert np.array_equal(d_coef[i].cpu().numpy(), want_c), i
+            want_p, _ = oracle.dequant_idct_plane(want_c, s[1], s[0], Q, 0, zz, None, nthreads=8)
+            assert np.array_equal(d_out[i].cpu().numpy()[:, :s[1]], want_p), i
+        # twice in a row on the same plans: the warps' worklist segments were left empty
+        assert api._fwd_planes(descs, n, lay, stream) == 0
+        torch.cuda.synchronize()
+        want_c, _, _ = oracle.fwd_quant_plane(planes[0], Ql, 0, zz, nthreads=8)
+        assert np.array_equal(d_coef[0].cpu().numpy(), want_c)
+        st = luma.plan.stats()
+        assert st["replayed_blocks"] > 0
+
+
+def test_planes_that_do_not_qualify_are_queued_one_by_one(api, oracle, torch):
+    """an adaptive plan among the planes, or a plane too narrow for the bulk-tensor kernels: same results, more launches"""
+    rng = np.random.default_rng(77)
+    shapes = [(512, 1024), (256, 512), (256, 128)]
+    planes = [rng.integers(0, 256, size=s, dtype=np.uint8) for s in shapes]
+    Q = oracle.quant_table(60)
+    with Ctx(api, 60, 0) as plain, Ctx(api, 60, 1) as adaptive:
+        for ctxs in ([plain, adaptive, plain], [plain, plain, plain]):
+            descs = (api.PlaneDesc * 3)()
+            d_px = [torch.from_numpy(p_).cuda() for p_ in planes]
+            d_out = [torch.zeros_like(t) for t in d_px]
+            d_coef = [torch.empty((s[0] // 8 * (s[1] // 8), 64), dtype=torch.int16, device="cuda") for s in shapes]
+            d_var = [torch.empty(s[0] // 8 * (s[1] // 8), dtype=torch.float64, device="cuda") for s in shapes]
+            for i, (s, cx) in enumerate(zip(shapes, ctxs)):
+                descs[i].plan = cx.plan._h
+                descs[i].pixels_in, descs[i].pixels_out = d_px[i].data_ptr(), d_out[i].data_ptr()
+                descs[i].pitch, descs[i].width, descs[i].height = s[1], s[1], s[0]
+                descs[i].coef, descs[i].variance = d_coef[i].data_ptr(), d_var[i].data_ptr()
+            stream = torch.cuda.current_stream().cuda_stream
+            before = plain.plan.kernel_launches() + adaptive.plan.kernel_launches()
+            assert api._fwd_planes(descs, 3, api.NATURAL, stream) == 0
+            assert api._inv_planes(descs, 3, api.NATURAL, stream) == 0
+            torch.cuda.synchronize()
+            assert plain.plan.kernel_launches() + adaptive.plan.kernel_launches() - before >= 6
+            for i, (s, cx) in enumerate(zip(shapes, ctxs)):
+                ad = 1 if cx is adaptive else 0
+                want_c, want_v, _ = oracle.fwd_quant_plane(planes[i], Q, ad, 0, nthreads=4)
+                assert np.array_equal(d_coef[i].cpu().numpy(), want_c), i
+                want_p, _ = oracle.dequant_idct_plane(want_c, s[1], s[0], Q, ad, 0, want_v if ad else None, nthreads=4)
+                assert np.array_equal(d_out[i].cpu().numpy(), want_p), i
+
+
 def test_config4_full_batch_shards_by_frame(api, oracle, torch):
     """BASELINE config 4 at full size on one GPU: 4 096 frames of 1920x1080 (8.5 Gpixel) stored back to
     back are one tall plane.  Properties checked: (i) sharding by contiguous frame ranges over 8 "GPUs"
