@@ -528,7 +528,11 @@ def shapes_block(cx, peak):
             pq.fwd_quant_dev(px, coef_out=coef)
             pq.dequant_idct_dev(coef, S, r1 - r0, pixels_out=out)
 
+        sampler = ClockSampler(cx.local)          # this sweep runs minutes into the job: record what the clocks did
+        sampler.start()
+        t_c0 = time.perf_counter()
         ms = dev_ms(c5, reps=3, flush_l2=False)
+        clk = sampler.stop(t_c0, time.perf_counter())
         st = pq.stats()
         t = None
         if quality in e2e_q:
@@ -537,6 +541,7 @@ def shapes_block(cx, peak):
         e = entry(S * S, ms, t)
         e["replayed_fraction"] = cx.sum_over_ranks(st["replayed_blocks"]) / max(cx.sum_over_ranks(st["blocks"]), 1.0)
         e["exact_ties"] = int(cx.sum_over_ranks(st["near_ties"]))
+        e["clocks_rank0"] = {k: clk.get(k) for k in ("sm_mhz", "power_w_max", "reasons")}
         sweep[f"q{quality}"] = e
         pq.close(), pq_inv.close()
         api.quant_free(qq)
@@ -763,9 +768,9 @@ def main():
             roofline["traffic_source"] = tj.get("source", "profiles/k1_traffic.json") + " (an earlier ncu --set full capture of the same command, not this run)"
         except Exception:
             pass
-    kernels = [{"name": "K1 k_fwd_quant_u8", "us_per_step": k1_ms * 1e3},
+    kernels = [{"name": "K1 k_fwd_quant_u8_tma", "us_per_step": k1_ms * 1e3},
                {"name": "K3f k_replay_fwd_lane (+ launch gap)", "us_per_step": k3f_ms * 1e3},
-               {"name": "K2 k_dequant_idct_u8", "us_per_step": k2_ms * 1e3},
+               {"name": "K2 k_dequant_idct_u8_tma", "us_per_step": k2_ms * 1e3},
                {"name": "K3i k_replay_inv_lane (+ launch gap)", "us_per_step": k3i_ms * 1e3}]
 
     line = {
@@ -777,7 +782,7 @@ def main():
         "fwd_gpixel_per_s_per_gpu": npx / (fwd_ms / args.steps * 1e-3) / 1e9,
         "inv_gpixel_per_s_per_gpu": npx / (inv_ms / args.steps * 1e-3) / 1e9,
         "e2e": e2e, "gpu_launches": gpu_launches,
-        "launches_per_step": "K1 k_fwd_quant_u8, K3 k_replay_fwd_lane, K2 k_dequant_idct_u8, K3 k_replay_inv_lane",
+        "launches_per_step": "K1 k_fwd_quant_u8_tma, K3 k_replay_fwd_lane, K2 k_dequant_idct_u8_tma, K3 k_replay_inv_lane",
         "kernels": kernels,
         "roofline": roofline, "clocks": clocks,
         "parity_ok": parity_ok, "parity_detail_rank0": parity_detail,

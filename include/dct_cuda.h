@@ -101,6 +101,9 @@ int dct_cuda_fwd_quant_u8_dev(dct_cuda_plan *plan, const uint8_t *d_pixels, size
 int dct_cuda_dequant_idct_u8_dev(dct_cuda_plan *plan, const int16_t *d_coef, int width, int height,
                                  int layout, const double *d_variance, uint8_t *d_pixels, size_t pitch,
                                  void *stream);
+/* The planes of one frame (e.g. Y, Cb, Cr with a luma and a chroma plan).  2 or 3 planes of non-adaptive 8x8 plans
+ * on one device, each of at most 600 000 blocks, 16-byte aligned with pitches that are multiples of 16 and at least
+ * 256 pixels wide, go through ONE kernel launch per call; anything else is queued plane by plane.  Same results. */
 int dct_cuda_fwd_quant_planes_dev(const dct_cuda_plane *planes, int n_planes, int layout, void *stream);
 int dct_cuda_dequant_idct_planes_dev(const dct_cuda_plane *planes, int n_planes, int layout, void *stream);
 
