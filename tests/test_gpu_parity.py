@@ -464,6 +464,44 @@ def test_planes_of_a_frame_share_one_launch(api, oracle, torch, shapes, layout):
         assert st["replayed_blocks"] > 0
 
 
+def test_plane_calls_can_be_captured_into_a_cuda_graph(api, oracle, torch):
+    """once a plan has processed a plane of that size (its buffers exist), the device-plane calls are
+    capturable; replaying the graph on new pixels gives the oracle's records and pixels."""
+    rng = np.random.default_rng(2718)
+    shapes = [(544, 960), (272, 480), (272, 480)]
+    Ql, Qc = oracle.quant_table(80), oracle.quant_table(40)
+    with Ctx(api, 80, 0) as luma, Ctx(api, 40, 0) as chr_:
+        d_px = [torch.zeros(s, dtype=torch.uint8, device="cuda") for s in shapes]
+        d_out = [torch.zeros_like(t) for t in d_px]
+        d_coef = [torch.zeros((s[0] // 8 * (s[1] // 8), 64), dtype=torch.int16, device="cuda") for s in shapes]
+        descs = (api.PlaneDesc * 3)()
+        for i, (s, cx) in enumerate(zip(shapes, (luma, chr_, chr_))):
+            descs[i].plan = cx.plan._h
+            descs[i].pixels_in, descs[i].pixels_out = d_px[i].data_ptr(), d_out[i].data_ptr()
+            descs[i].pitch, descs[i].width, descs[i].height = s[1], s[1], s[0]
+            descs[i].coef, descs[i].variance = d_coef[i].data_ptr(), None
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            assert api._fwd_planes(descs, 3, api.NATURAL, side.cuda_stream) == 0      # warm: allocates the plans' worklists
+            assert api._inv_planes(descs, 3, api.NATURAL, side.cuda_stream) == 0
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            assert api._fwd_planes(descs, 3, api.NATURAL, torch.cuda.current_stream().cuda_stream) == 0
+            assert api._inv_planes(descs, 3, api.NATURAL, torch.cuda.current_stream().cuda_stream) == 0
+        for rep in range(2):
+            planes = [rng.integers(0, 256, size=s, dtype=np.uint8) for s in shapes]
+            for t, p_ in zip(d_px, planes):
+                t.copy_(torch.from_numpy(p_))
+            g.replay()
+            torch.cuda.synchronize()
+            for i, (s, Q) in enumerate(zip(shapes, (Ql, Qc, Qc))):
+                want_c, _, _ = oracle.fwd_quant_plane(planes[i], Q, nthreads=4)
+                assert np.array_equal(d_coef[i].cpu().numpy(), want_c), (rep, i)
+                want_p, _ = oracle.dequant_idct_plane(want_c, s[1], s[0], Q, nthreads=4)
+                assert np.array_equal(d_out[i].cpu().numpy(), want_p), (rep, i)
+
+
 def test_planes_that_do_not_qualify_are_queued_one_by_one(api, oracle, torch):
     """an adaptive plan among the planes, or a plane too narrow for the bulk-tensor kernels: same results, more launches"""
     rng = np.random.default_rng(77)
