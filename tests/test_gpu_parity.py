@@ -502,6 +502,61 @@ def test_plane_calls_can_be_captured_into_a_cuda_graph(api, oracle, torch):
                 assert np.array_equal(d_out[i].cpu().numpy(), want_p), (rep, i)
 
 
+def test_frame_kernels_match_plane_by_plane_on_random_frames(api, torch):
+    """40 random frames (2 or 3 planes, random sizes / pitches / plan per plane / content / layout): the planes call
+    (one launch each way) leaves the same bytes as the same planes queued one by one through the plane calls."""
+    rng = np.random.default_rng(31337)
+    with Ctx(api, 92, 0) as hi, Ctx(api, 35, 0) as lo:
+        ctxs = (hi, lo)
+        for trial in range(40):
+            n = int(rng.integers(2, 4))
+            lay = api.ZIGZAG if trial % 2 else api.NATURAL
+            shapes, pitches, which = [], [], []
+            for i in range(n):
+                w = 8 * int(rng.integers(32, 260))               # 256 .. 2072 pixels: partial last tiles in most rows
+                h = 8 * int(rng.integers(1, 90))
+                shapes.append((h, w))
+                pitches.append((w + 15) // 16 * 16 + 16 * int(rng.integers(0, 3)))   # the bulk-tensor kernels want 16-byte rows
+                which.append(int(rng.integers(0, 2)) if trial % 3 else 0)   # every third frame: one plan for all planes
+            d_px = []
+            for (h, w), pt in zip(shapes, pitches):
+                kind = int(rng.integers(0, 3))
+                if kind == 0:
+                    a = rng.integers(0, 256, size=(h, pt), dtype=np.uint8)
+                elif kind == 1:
+                    a = ((np.add.outer(np.arange(h), 2 * np.arange(pt)) // 5) % 256).astype(np.uint8)
+                else:                                                        # blocks whose sums force DC ties
+                    a = np.full((h, pt), 128, dtype=np.uint8)
+                    a[::8, ::8] = 192
+                d_px.append(torch.from_numpy(a).cuda())
+            outs = []
+            for together in (True, False):
+                d_coef = [torch.zeros((s[0] // 8 * (s[1] // 8), 64), dtype=torch.int16, device="cuda") for s in shapes]
+                d_out = [torch.zeros_like(t) for t in d_px]
+                descs = (api.PlaneDesc * n)()
+                for i, s in enumerate(shapes):
+                    descs[i].plan = ctxs[which[i]].plan._h
+                    descs[i].pixels_in, descs[i].pixels_out = d_px[i].data_ptr(), d_out[i].data_ptr()
+                    descs[i].pitch, descs[i].width, descs[i].height = pitches[i], s[1], s[0]
+                    descs[i].coef, descs[i].variance = d_coef[i].data_ptr(), None
+                stream = torch.cuda.current_stream().cuda_stream
+                if together:
+                    before = hi.plan.kernel_launches() + lo.plan.kernel_launches()
+                    assert api._fwd_planes(descs, n, lay, stream) == 0
+                    assert api._inv_planes(descs, n, lay, stream) == 0
+                    assert hi.plan.kernel_launches() + lo.plan.kernel_launches() - before == 2, (trial, shapes)
+                else:
+                    for i in range(n):
+                        one = (api.PlaneDesc * 1)(descs[i])
+                        assert api._fwd_planes(one, 1, lay, stream) == 0
+                        assert api._inv_planes(one, 1, lay, stream) == 0
+                torch.cuda.synchronize()
+                outs.append(([c.cpu().numpy() for c in d_coef], [o.cpu().numpy()[:, :s[1]] for o, s in zip(d_out, shapes)]))
+            for i in range(n):
+                assert np.array_equal(outs[0][0][i], outs[1][0][i]), (trial, i, shapes, "records")
+                assert np.array_equal(outs[0][1][i], outs[1][1][i]), (trial, i, shapes, "pixels")
+
+
 def test_planes_that_do_not_qualify_are_queued_one_by_one(api, oracle, torch):
     """an adaptive plan among the planes, or a plane too narrow for the bulk-tensor kernels: same results, more launches"""
     rng = np.random.default_rng(77)
